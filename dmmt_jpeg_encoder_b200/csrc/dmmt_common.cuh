@@ -1,0 +1,143 @@
+// dmmt_common.cuh -- shared device/host definitions of the sm_100a encode path.
+// Geometry, per-image metadata, decoupled look-back helpers, block scans.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dmmt_cuda.h"
+
+namespace dmmt {
+
+// ------------------------------------------------------------------------------------------
+// Geometry of one image (or one MCU-row shard of an image) -- SURVEY.md Appendix A steps 2,5,8
+struct Geom {
+    int W, H;          // original pixel size of this image / shard rows
+    int hr, vr;        // chroma rates (subsampling.rs:32-46)
+    int mcus_x, mcus_y;
+    int ypm;           // Y blocks per MCU = hr*vr
+    int bpm;           // blocks per MCU = ypm + 2   (block_fold_iterator.rs:75-148)
+    uint32_t n_mcus;
+    uint32_t n_blocks; // stream blocks = n_mcus * bpm
+};
+
+// Per-image device metadata written by K2b/K4 (mirrors dmmt_image_meta + internals)
+struct ImgMeta {
+    unsigned long long scan_bits;   // accumulated by the 4 table CTAs of K2b
+    unsigned long long out_len;     // whole file length, written by K4
+    uint32_t header_len;
+    uint32_t n_symbols[4];
+    int32_t error;                  // first device-side error (DMMT_E_*)
+    uint32_t n_stream_blocks;
+    uint32_t reserved;
+};
+static_assert(sizeof(ImgMeta) == sizeof(dmmt_image_meta), "meta layout is part of the C ABI");
+
+// Table indices
+enum { T_YDC = 0, T_YAC = 1, T_CDC = 2, T_CAC = 3 };
+
+// Encoder LUT entry: (len << 16) | right-aligned code.  len == 0 => symbol absent.
+struct EncTables {
+    uint32_t e[4][256];
+};
+// Length tables in the reference's Vec<SymbolCodeLength> order (ascending frequency), for DHT + tests
+struct LenTables {
+    uint8_t sym[4][256];
+    uint8_t len[4][256];
+};
+
+// quantisation divisors as f32, natural (row-major) order: [0] luma, [1] chroma
+struct QuantF {
+    float q[2][64];
+};
+
+// zig-zag (frequency_block.rs:1-5): ZZ[i] = natural index of the i-th zig-zag coefficient
+__host__ __device__ constexpr int zz_at(int i) {
+    constexpr int t[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,
+                           12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28,
+                           35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+                           58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    return t[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// Decoupled look-back state: one u64 per chunk = (flag << 62) | value.
+// flag 0 = not ready, 1 = chunk aggregate available, 2 = inclusive prefix available.
+constexpr unsigned long long LB_AGG = 1ull << 62;
+constexpr unsigned long long LB_INC = 2ull << 62;
+constexpr unsigned long long LB_VAL = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Called by ONE thread (thread 0) of the CTA that owns `chunk`.  Publishes the chunk aggregate,
+// walks predecessors until an inclusive prefix is found, publishes the inclusive prefix and
+// returns the EXCLUSIVE prefix.  Value and flag travel in one 64-bit word, so relaxed accesses
+// are sufficient (no payload outside the word).
+__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long* state,
+                                                                 int chunk,
+                                                                 unsigned long long aggregate) {
+    if (chunk == 0) {
+        st_relaxed_u64(&state[0], LB_INC | aggregate);
+        return 0ull;
+    }
+    st_relaxed_u64(&state[chunk], LB_AGG | aggregate);
+    unsigned long long excl = 0ull;
+    int j = chunk - 1;
+    while (true) {
+        unsigned long long s = ld_relaxed_u64(&state[j]);
+        unsigned long long flag = s & ~LB_VAL;
+        if (flag == 0ull) {
+            __nanosleep(20);
+            continue;
+        }
+        excl += (s & LB_VAL);
+        if (flag == LB_INC) break;
+        --j;  // flag == LB_AGG: keep walking (j >= 0 is guaranteed: chunk 0 always publishes INC)
+    }
+    st_relaxed_u64(&state[chunk], LB_INC | (excl + aggregate));
+    return excl;
+}
+
+// ------------------------------------------------------------------------------------------
+// Block-wide exclusive scan of one u32 per thread (blockDim.x == NT, multiple of 32, <= 1024).
+// Returns the exclusive prefix; *total receives the block sum.  `warp_sums` = NT/32 + 1 u32 of smem.
+template <int NT>
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums,
+                                                         uint32_t* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = (lane < NT / 32) ? warp_sums[lane] : 0u;
+        uint32_t winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += t;
+        }
+        if (lane < NT / 32) warp_sums[lane] = winc - w;  // exclusive warp offsets
+        if (lane == NT / 32 - 1) warp_sums[NT / 32] = winc;
+    }
+    __syncthreads();
+    uint32_t excl = warp_sums[wid] + inc - v;
+    *total = warp_sums[NT / 32];
+    __syncthreads();  // warp_sums may be reused by the caller
+    return excl;
+}
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+}  // namespace dmmt

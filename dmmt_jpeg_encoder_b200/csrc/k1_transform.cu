@@ -1,0 +1,421 @@
+// k1_transform.cu -- K1: fused normalise -> black pad -> RGB->YCbCr -> chroma average ->
+// Arai 8x8 DCT -> quantise -> zig-zag, one launch per batch of equally sized images.
+//
+// Replaces (file:line under /root/reference/src):
+//   color.rs:45-53 (v/max), image/writer/jpeg/padder.rs:12-42 (black pad to MCU),
+//   color.rs:75-100 (YCbCr, level shift inside Y), image/subsampling.rs:102-122,231-236,286-309
+//   (window average + 8x8 re-tiling), cosine_transform/arai.rs:29-104 (rows then columns),
+//   image/writer/jpeg/transformer/quantizer.rs:53-62, frequency_block.rs:1-5 (zig-zag),
+//   block_entangler.rs:69-77 + encoder/block_fold_iterator.rs:75-148 (MCU stream order).
+//
+// Numerics: every f32 operation is an explicit round-to-nearest intrinsic (__fmul_rn/__fadd_rn/
+// __fsub_rn/__fdiv_rn) in the reference's operation order, so nothing contracts to FMA and the
+// coefficients are bit-identical to the CPU path (the file is also compiled with -fmad=false).
+//
+// Mapping (B200): one CTA = 128 threads = one tile of 256 x (8*VR) pixels of one MCU row.
+//   phase A: thread = one 16 x VR pixel strip.  128-bit loads of the interleaved samples (scalar,
+//            bounds-checked loads at ragged edges / unaligned pitches), colour conversion and the
+//            chroma window sum in registers, planes staged in shared memory as
+//            [row][16-byte chunk][strip] so both the phase-A stores and the phase-B loads are
+//            conflict-free 128-bit accesses.
+//   phase B: thread = one 8x8 block, all 64 samples in registers: 8 row passes + 8 column passes of
+//            the Arai flow graph without any transpose, IEEE division by the quantiser, round half
+//            away from zero, zig-zag by register renaming, 8 x 16-byte stores of the block.
+// Output: int16 [n_mcus][blocks_per_mcu][64] in MCU-interleaved STREAM order, zig-zag inside a block.
+#include "dmmt_common.cuh"
+
+namespace dmmt {
+
+namespace {
+
+constexpr int K1_THREADS = 128;
+constexpr int TILE_W = 256;
+
+// arai.rs:7-26 -- the decimal literals of the reference (S0 != S4 on purpose)
+constexpr float kA1 = 0.70710678118654752440f;  // FRAC_1_SQRT_2
+constexpr float kA2 = 0.5411961f;
+constexpr float kA3 = kA1;
+constexpr float kA4 = 1.3065629f;
+constexpr float kA5 = 0.3826834f;
+constexpr float kS0 = 0.3535533f;
+constexpr float kS1 = 0.2548978f;
+constexpr float kS2 = 0.27059805f;
+constexpr float kS3 = 0.30067244f;
+constexpr float kS4 = 0.35355338f;
+constexpr float kS5 = 0.4499881f;
+constexpr float kS6 = 0.6532815f;
+constexpr float kS7 = 1.2814577f;
+
+// arai.rs:29-92, one 1-D pass on 8 registers
+__device__ __forceinline__ void fast_arai(float& x0, float& x1, float& x2, float& x3, float& x4,
+                                          float& x5, float& x6, float& x7) {
+    const float v10 = __fadd_rn(x0, x7), v11 = __fadd_rn(x1, x6), v12 = __fadd_rn(x2, x5),
+                v13 = __fadd_rn(x3, x4);
+    const float v14 = __fsub_rn(x3, x4), v15 = __fsub_rn(x2, x5), v16 = __fsub_rn(x1, x6),
+                v17 = __fsub_rn(x0, x7);
+
+    const float v20 = __fadd_rn(v10, v13), v21 = __fadd_rn(v11, v12), v22 = __fsub_rn(v11, v12),
+                v23 = __fsub_rn(v10, v13);
+    const float v24 = __fsub_rn(-v14, v15), v25 = __fadd_rn(v15, v16), v26 = __fadd_rn(v16, v17);
+
+    const float v30 = __fadd_rn(v20, v21), v31 = __fsub_rn(v20, v21), v32 = __fadd_rn(v22, v23);
+
+    const float v42 = __fmul_rn(v32, kA1);
+    const float t5 = __fmul_rn(__fadd_rn(v24, v26), kA5);  // (v24+v26)*A5 == (v26+v24)*A5
+    const float v44 = __fsub_rn(__fmul_rn(-v24, kA2), t5);
+    const float v45 = __fmul_rn(v25, kA3);
+    const float v46 = __fsub_rn(__fmul_rn(v26, kA4), t5);
+
+    const float v52 = __fadd_rn(v42, v23), v53 = __fsub_rn(v23, v42), v55 = __fadd_rn(v45, v17),
+                v57 = __fsub_rn(v17, v45);
+
+    const float v64 = __fadd_rn(v44, v57), v65 = __fadd_rn(v55, v46), v66 = __fsub_rn(v55, v46),
+                v67 = __fsub_rn(v57, v44);
+
+    x0 = __fmul_rn(v30, kS0);
+    x4 = __fmul_rn(v31, kS4);
+    x2 = __fmul_rn(v52, kS2);
+    x6 = __fmul_rn(v53, kS6);
+    x5 = __fmul_rn(v64, kS5);
+    x1 = __fmul_rn(v65, kS1);
+    x7 = __fmul_rn(v66, kS7);
+    x3 = __fmul_rn(v67, kS3);
+}
+
+// color.rs:75-100
+__device__ __forceinline__ void rgb_to_ycbcr(float r, float g, float b, float& y, float& cb,
+                                             float& cr) {
+    constexpr float kShift = 128.0f / 255.0f;  // folded in f32 like `128_f32 / 255_f32`
+    y = __fmul_rn(__fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(r, 0.299f), __fmul_rn(g, 0.587f)),
+                                      __fmul_rn(b, 0.114f)),
+                            kShift),
+                  255.0f);
+    cb = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(r, -0.1687f), __fmul_rn(g, -0.3312f)),
+                             __fmul_rn(b, 0.5f)),
+                   255.0f);
+    cr = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(r, 0.5f), __fmul_rn(g, -0.4186f)),
+                             __fmul_rn(b, -0.0813f)),
+                   255.0f);
+}
+
+// quantizer.rs:60 : (d / q as f32).round() as i16  (IEEE divide, half away from zero, saturate)
+__device__ __forceinline__ int quantize(float d, float q) {
+    const float x = __fdiv_rn(d, q);
+    // round half away from zero: trunc(x + copysign(pred(0.5), x)) is exact for |x| < 2^23
+    const float h = __int_as_float((__float_as_int(x) & 0x80000000) | 0x3EFFFFFF);
+    int r = __float2int_rz(__fadd_rn(x, h));
+    r = max(-32768, min(32767, r));
+    return r;
+}
+
+template <int FMT>
+struct Px;
+template <>
+struct Px<DMMT_RGB_U8> {
+    static constexpr int kBytes = 3;
+};
+template <>
+struct Px<DMMT_RGB_U16> {
+    static constexpr int kBytes = 6;
+};
+template <>
+struct Px<DMMT_RGB_F32_NORM> {
+    static constexpr int kBytes = 12;
+};
+
+// Loads one 16-pixel strip row, normalised (color.rs:45-53), into n[48] (r,g,b interleaved).
+// fast: the row segment is fully inside the image and 16-byte aligned -> 128-bit loads.
+template <int FMT>
+__device__ __forceinline__ void load_strip_row(const uint8_t* __restrict__ row_base, int x0, int W,
+                                               bool row_valid, bool vec_ok, float maxf,
+                                               float (&n)[48]) {
+    constexpr int PB = Px<FMT>::kBytes;
+    if (!row_valid) {
+#pragma unroll
+        for (int i = 0; i < 48; i++) n[i] = 0.0f;  // padder.rs:18,27-38 black
+        return;
+    }
+    if (vec_ok && x0 + 16 <= W) {
+        const uint4* p = reinterpret_cast<const uint4*>(row_base + (size_t)x0 * PB);
+        if constexpr (FMT == DMMT_RGB_U8) {
+            uint32_t w[12];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                uint4 v = __ldg(p + i);
+                w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 48; i++)
+                n[i] = __fdiv_rn((float)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu), maxf);
+        } else if constexpr (FMT == DMMT_RGB_U16) {
+            uint32_t w[24];
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                uint4 v = __ldg(p + i);
+                w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 48; i++)
+                n[i] = __fdiv_rn((float)((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu), maxf);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                uint4 v = __ldg(p + i);
+                n[4 * i] = __uint_as_float(v.x), n[4 * i + 1] = __uint_as_float(v.y);
+                n[4 * i + 2] = __uint_as_float(v.z), n[4 * i + 3] = __uint_as_float(v.w);
+            }
+        }
+        return;
+    }
+    // ragged edge / unaligned pitch: scalar, bounds-checked
+#pragma unroll
+    for (int px = 0; px < 16; px++) {
+        const bool in = (x0 + px) < W;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float v = 0.0f;
+            if (in) {
+                const uint8_t* q = row_base + ((size_t)(x0 + px) * 3 + c) * (PB / 3);
+                if constexpr (FMT == DMMT_RGB_U8)
+                    v = __fdiv_rn((float)(*q), maxf);
+                else if constexpr (FMT == DMMT_RGB_U16)
+                    v = __fdiv_rn((float)(*reinterpret_cast<const uint16_t*>(q)), maxf);
+                else
+                    v = *reinterpret_cast<const float*>(q);
+            }
+            n[3 * px + c] = v;
+        }
+    }
+}
+
+struct K1Args {
+    const uint8_t* pixels;       // n images, tightly packed
+    size_t img_stride_bytes;     // bytes between images
+    int W, H;                    // original size (pad region is synthesised)
+    int mcus_x;                  // MCUs per row
+    float maxf;                  // max_value as f32
+    int vec_ok;                  // row pitch and base are 16-byte aligned
+    int16_t* coef;               // [n][n_blocks][64]
+    size_t coef_img_stride;      // elements between images
+    float* dbg;                  // optional pre-quant coefficients [n_blocks][64] natural order (image 0 of launch)
+    QuantF qf;
+};
+
+template <int HR, int VR, int FMT, bool DBG>
+__global__ void __launch_bounds__(K1_THREADS) k1_transform(const __grid_constant__ K1Args a) {
+    constexpr int ROWS = 8 * VR;
+    constexpr int CCH = (HR == 2) ? 2 : 4;     // 16-byte chunks per strip in a chroma plane row
+    constexpr int YPM = HR * VR, BPM = YPM + 2;
+    constexpr int MPT = TILE_W / (8 * HR);     // MCUs per tile
+    constexpr int NYU = 32 * VR;               // Y blocks per tile
+    constexpr int NCU = (HR == 2) ? 16 : 32;   // blocks per chroma plane per tile
+    constexpr int NUNITS = NYU + 2 * NCU;
+
+    __shared__ float4 sY[ROWS][4][16];
+    __shared__ float4 sCb[8][CCH][16];
+    __shared__ float4 sCr[8][CCH][16];
+
+    const int tile_x = blockIdx.x, mrow = blockIdx.y, img = blockIdx.z;
+    const uint8_t* __restrict__ pix = a.pixels + (size_t)img * a.img_stride_bytes;
+    const size_t pitch = (size_t)a.W * Px<FMT>::kBytes;
+
+    // ---------------- phase A: strip = 16 px x VR rows ----------------
+    {
+        const int sx = threadIdx.x & 15, sy = threadIdx.x >> 4;  // sy in [0,8)
+        const int x0 = tile_x * TILE_W + sx * 16;
+        float cbs[16], crs[16];  // running chroma window sums (x outer, y inner: subsampling.rs:108-122)
+#pragma unroll
+        for (int r = 0; r < VR; r++) {
+            const int yl = sy * VR + r;
+            const int y = mrow * ROWS + yl;
+            const bool row_valid = (y < a.H) && (x0 < a.W);
+            float n[48];
+            load_strip_row<FMT>(pix + (size_t)y * pitch, x0, a.W, row_valid, a.vec_ok != 0, a.maxf, n);
+            float yv[16], cb[16], cr[16];
+#pragma unroll
+            for (int p = 0; p < 16; p++) rgb_to_ycbcr(n[3 * p], n[3 * p + 1], n[3 * p + 2], yv[p], cb[p], cr[p]);
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                sY[yl][c][sx] = make_float4(yv[4 * c], yv[4 * c + 1], yv[4 * c + 2], yv[4 * c + 3]);
+            if (r == 0) {
+#pragma unroll
+                for (int p = 0; p < 16; p++) cbs[p] = cb[p], crs[p] = cr[p];
+            } else {
+                // second row of the window: only reachable for VR == 2.  Window order is
+                // (x,y),(x,y+1),(x+1,y),(x+1,y+1): keep per-column partial sums apart until the
+                // horizontal combine so the additions happen in exactly that order.
+#pragma unroll
+                for (int p = 0; p < 16; p += 2) {
+                    // ((c00 + c10) + c01) + c11
+                    float sb = __fadd_rn(cbs[p], cb[p]);
+                    sb = __fadd_rn(sb, cbs[p + 1]);
+                    sb = __fadd_rn(sb, cb[p + 1]);
+                    cbs[p >> 1] = sb;
+                    float sr = __fadd_rn(crs[p], cr[p]);
+                    sr = __fadd_rn(sr, crs[p + 1]);
+                    sr = __fadd_rn(sr, cr[p + 1]);
+                    crs[p >> 1] = sr;
+                }
+            }
+        }
+        if constexpr (HR == 2 && VR == 2) {
+            // average(): sum / 4.0 (subsampling.rs:231-236) -- exact scaling, same as * 0.25
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                sCb[sy][c][sx] = make_float4(__fmul_rn(cbs[4 * c], 0.25f), __fmul_rn(cbs[4 * c + 1], 0.25f),
+                                             __fmul_rn(cbs[4 * c + 2], 0.25f), __fmul_rn(cbs[4 * c + 3], 0.25f));
+                sCr[sy][c][sx] = make_float4(__fmul_rn(crs[4 * c], 0.25f), __fmul_rn(crs[4 * c + 1], 0.25f),
+                                             __fmul_rn(crs[4 * c + 2], 0.25f), __fmul_rn(crs[4 * c + 3], 0.25f));
+            }
+        } else if constexpr (HR == 2 && VR == 1) {
+            // (c[x] + c[x+1]) / 2.0
+            float hb[8], hr_[8];
+#pragma unroll
+            for (int p = 0; p < 8; p++) {
+                hb[p] = __fmul_rn(__fadd_rn(cbs[2 * p], cbs[2 * p + 1]), 0.5f);
+                hr_[p] = __fmul_rn(__fadd_rn(crs[2 * p], crs[2 * p + 1]), 0.5f);
+            }
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                sCb[sy][c][sx] = make_float4(hb[4 * c], hb[4 * c + 1], hb[4 * c + 2], hb[4 * c + 3]);
+                sCr[sy][c][sx] = make_float4(hr_[4 * c], hr_[4 * c + 1], hr_[4 * c + 2], hr_[4 * c + 3]);
+            }
+        } else {
+            // P444: SubsamplingMethod::Skip (subsampling.rs:50-54)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                sCb[sy][c][sx] = make_float4(cbs[4 * c], cbs[4 * c + 1], cbs[4 * c + 2], cbs[4 * c + 3]);
+                sCr[sy][c][sx] = make_float4(crs[4 * c], crs[4 * c + 1], crs[4 * c + 2], crs[4 * c + 3]);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase B: unit = one 8x8 block ----------------
+    const int u = threadIdx.x;
+    if (u >= NUNITS) return;
+    int m, k, comp;
+    float d[64];
+    if (u < NYU) {
+        const int q = u >> 4, sx = u & 15;
+        const int byl = q >> 1, p = q & 1;
+        comp = 0;
+        if constexpr (HR == 2) {
+            m = sx;
+            k = byl * 2 + p;
+        } else {
+            m = 2 * sx + p;
+            k = 0;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const float4 lo = sY[byl * 8 + r][2 * p][sx], hi = sY[byl * 8 + r][2 * p + 1][sx];
+            d[8 * r] = lo.x, d[8 * r + 1] = lo.y, d[8 * r + 2] = lo.z, d[8 * r + 3] = lo.w;
+            d[8 * r + 4] = hi.x, d[8 * r + 5] = hi.y, d[8 * r + 6] = hi.z, d[8 * r + 7] = hi.w;
+        }
+    } else {
+        const int v = u - NYU;
+        const int ch = v / NCU, w = v % NCU;
+        comp = 1;
+        k = YPM + ch;
+        int sx, c0;
+        if constexpr (HR == 2) {
+            sx = w;
+            c0 = 0;
+            m = sx;
+        } else {
+            sx = w & 15;
+            c0 = 2 * (w >> 4);
+            m = 2 * sx + (w >> 4);
+        }
+        const float4(*pl)[CCH][16] = ch ? sCr : sCb;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const float4 lo = pl[r][c0][sx], hi = pl[r][c0 + 1][sx];
+            d[8 * r] = lo.x, d[8 * r + 1] = lo.y, d[8 * r + 2] = lo.z, d[8 * r + 3] = lo.w;
+            d[8 * r + 4] = hi.x, d[8 * r + 5] = hi.y, d[8 * r + 6] = hi.z, d[8 * r + 7] = hi.w;
+        }
+    }
+    const int gmx = tile_x * MPT + m;
+    if (gmx >= a.mcus_x) return;  // tile overhangs the padded image
+
+    // arai.rs:95-104: 8 row passes, then 8 column passes
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+        fast_arai(d[8 * r], d[8 * r + 1], d[8 * r + 2], d[8 * r + 3], d[8 * r + 4], d[8 * r + 5],
+                  d[8 * r + 6], d[8 * r + 7]);
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+        fast_arai(d[c], d[8 + c], d[16 + c], d[24 + c], d[32 + c], d[40 + c], d[48 + c], d[56 + c]);
+
+    const size_t sblk = ((size_t)mrow * a.mcus_x + gmx) * BPM + k;  // stream block index
+    if constexpr (DBG) {
+        if (img == 0) {
+            float4* o = reinterpret_cast<float4*>(a.dbg + sblk * 64);
+#pragma unroll
+            for (int i = 0; i < 16; i++) o[i] = make_float4(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
+        }
+    }
+
+    // quantise (natural-order table) and emit in zig-zag order
+    uint32_t w[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const int n0 = zz_at(2 * i), n1 = zz_at(2 * i + 1);
+        const int q0 = quantize(d[n0], a.qf.q[comp][n0]);
+        const int q1 = quantize(d[n1], a.qf.q[comp][n1]);
+        w[i] = ((uint32_t)q0 & 0xFFFFu) | ((uint32_t)q1 << 16);
+    }
+    uint4* out = reinterpret_cast<uint4*>(a.coef + (size_t)img * a.coef_img_stride + sblk * 64);
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+
+template <int HR, int VR, int FMT>
+cudaError_t launch_fmt(const K1Args& a, dim3 grid, bool dbg, cudaStream_t st) {
+    if (dbg)
+        k1_transform<HR, VR, FMT, true><<<grid, K1_THREADS, 0, st>>>(a);
+    else
+        k1_transform<HR, VR, FMT, false><<<grid, K1_THREADS, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int HR, int VR>
+cudaError_t launch_sub(const K1Args& a, dim3 grid, int fmt, bool dbg, cudaStream_t st) {
+    switch (fmt) {
+        case DMMT_RGB_U8: return launch_fmt<HR, VR, DMMT_RGB_U8>(a, grid, dbg, st);
+        case DMMT_RGB_U16: return launch_fmt<HR, VR, DMMT_RGB_U16>(a, grid, dbg, st);
+        default: return launch_fmt<HR, VR, DMMT_RGB_F32_NORM>(a, grid, dbg, st);
+    }
+}
+
+}  // namespace
+
+// Host launcher.  n_images equally sized images; dbg != nullptr selects the variant that also
+// writes the pre-quantisation coefficients of image 0.
+cudaError_t launch_k1(const Geom& g, int fmt, float maxf, const QuantF& qf, const void* d_pixels,
+                      size_t img_stride_bytes, int n_images, int16_t* d_coef,
+                      size_t coef_img_stride, float* d_dbg, cudaStream_t st) {
+    K1Args a;
+    a.pixels = static_cast<const uint8_t*>(d_pixels);
+    a.img_stride_bytes = img_stride_bytes;
+    a.W = g.W;
+    a.H = g.H;
+    a.mcus_x = g.mcus_x;
+    a.maxf = maxf;
+    const size_t pb = (fmt == DMMT_RGB_U8) ? 3 : (fmt == DMMT_RGB_U16 ? 6 : 12);
+    a.vec_ok = ((reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0) && (((size_t)g.W * pb) % 16 == 0) &&
+               (img_stride_bytes % 16 == 0);
+    a.coef = d_coef;
+    a.coef_img_stride = coef_img_stride;
+    a.dbg = d_dbg;
+    a.qf = qf;
+    const int pw = g.mcus_x * 8 * g.hr;
+    dim3 grid((pw + TILE_W - 1) / TILE_W, g.mcus_y, n_images);
+    const bool dbg = d_dbg != nullptr;
+    if (g.hr == 2 && g.vr == 2) return launch_sub<2, 2>(a, grid, fmt, dbg, st);
+    if (g.hr == 2 && g.vr == 1) return launch_sub<2, 1>(a, grid, fmt, dbg, st);
+    return launch_sub<1, 1>(a, grid, fmt, dbg, st);
+}
+
+}  // namespace dmmt

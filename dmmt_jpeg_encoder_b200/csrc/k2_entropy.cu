@@ -1,0 +1,818 @@
+// k2_entropy.cu -- the entropy stage of the sm_100a encode path:
+//   K2  symbol histogram                     (categorize.rs:153-169, symbol_counting.rs:55-74)
+//   K2b Huffman table construction + headers (symbol_counting.rs:85-94, huffman/length_limited.rs:37-134,
+//                                             huffman/encoder.rs:37-157, jpeg/encoder.rs:137-262)
+//   K3  bit-length pass -> decoupled look-back exclusive scan -> bit packing
+//                                            (jpeg/encoder.rs:264-404, binary_stream.rs:38-96)
+//   K4  0xFF byte stuffing as a scan-compaction (segment_marker_injector.rs:13-30) + EOI
+// All file:line citations are relative to /root/reference/src.
+//
+// Input is K1's coefficient stream: int16 [n_blocks][64], zig-zag inside a block, MCU-interleaved
+// stream order.  K2 and K3 stage 256 blocks (32 KB) per CTA into shared memory with a 16-byte-chunk
+// XOR swizzle (chunk c of block b at slot c ^ (b & 7)), so the coalesced global loads AND the
+// thread-per-block 128-bit shared loads are both conflict-free; each thread then walks only the
+// NON-ZERO coefficients of its block (64-bit occupancy mask + ffs).
+#include "dmmt_common.cuh"
+
+namespace dmmt {
+
+namespace {
+
+constexpr int EB = 256;           // blocks per CTA chunk in K2/K3 (= threads)
+constexpr int K3_OUT_WORDS = 2560;  // 10 KB shared bit buffer per K3 chunk (avg 40 B per block)
+constexpr int K4_THREADS = 256;
+constexpr int K4_BYTES_PER_THREAD = 32;
+constexpr int K4_CHUNK = K4_THREADS * K4_BYTES_PER_THREAD;  // 8 KB of unstuffed scan per CTA
+
+// ---- staging: 256 blocks x 128 B -> swizzled shared memory --------------------------------
+__device__ __forceinline__ void stage_chunk(uint4* s_coef, const int16_t* __restrict__ coef,
+                                            uint32_t first_block, uint32_t n_blocks) {
+    const uint4* g = reinterpret_cast<const uint4*>(coef) + (size_t)first_block * 8;
+    const uint32_t avail = (n_blocks - first_block < EB) ? (n_blocks - first_block) : EB;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t gi = i * EB + threadIdx.x;  // 16-byte chunk index within the CTA chunk
+        const uint32_t b = gi >> 3, c = gi & 7;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (b < avail) v = __ldg(g + gi);
+        s_coef[b * 8 + (c ^ (b & 7))] = v;
+    }
+}
+
+__device__ __forceinline__ int s_coef_at(const uint4* s_coef, int b, int pos) {
+    const int16_t* p = reinterpret_cast<const int16_t*>(s_coef + b * 8 + ((pos >> 3) ^ (b & 7)));
+    return p[pos & 7];
+}
+
+// 64-bit occupancy mask of the thread's own block (bit i set <=> zig-zag coefficient i != 0)
+__device__ __forceinline__ unsigned long long block_mask(const uint4* s_coef, int b) {
+    unsigned long long m = 0ull;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const uint4 v = s_coef[b * 8 + (c ^ (b & 7))];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            bits |= ((w[j] & 0xFFFFu) != 0u ? 1u : 0u) << (2 * j);
+            bits |= ((w[j] >> 16) != 0u ? 1u : 0u) << (2 * j + 1);
+        }
+        m |= (unsigned long long)bits << (8 * c);
+    }
+    return m;
+}
+
+// previous block of the same component in stream order (categorize.rs:157-161 runs one DC chain
+// per component over the entangled/stream order); -1 => first block of the component
+__device__ __forceinline__ long long prev_block_same_comp(uint32_t s, int ypm, int bpm) {
+    const uint32_t m = s / bpm, k = s - m * bpm;
+    if ((int)k < ypm) {
+        if (k > 0) return (long long)s - 1;
+        return m ? (long long)(m - 1) * bpm + ypm - 1 : -1;
+    }
+    return m ? (long long)s - bpm : -1;
+}
+
+// categorize.rs:22-41 for a non-zero value: category and the cat low bits of the pattern
+__device__ __forceinline__ void cat_bits(int v, int& cat, uint32_t& bits) {
+    const int a = abs(v);
+    cat = 32 - __clz(a);
+    bits = (uint32_t)(v > 0 ? v : v - 1) & ((1u << cat) - 1u);
+}
+
+// Walks the tokens of block `b` (thread-private).  emit(table, symbol, extra_bits, extra_len).
+// DC: categorize.rs:159-160; AC: categorize.rs:132-151 (ZRL 0xF0 while run > 15, EOB 0x00).
+template <class Emit>
+__device__ __forceinline__ bool walk_block(const uint4* s_coef, int b, unsigned long long mask,
+                                           int dc_pred, int comp_tables, Emit&& emit) {
+    bool ok = true;
+    {
+        const int dc = s_coef_at(s_coef, b, 0);
+        const int diff = (int)(int16_t)(dc - dc_pred);
+        int cat = 0;
+        uint32_t bits = 0;
+        if (diff != 0) cat_bits(diff, cat, bits);
+        ok &= cat <= 15;
+        emit(comp_tables, cat, bits, cat);
+    }
+    unsigned long long m = mask & ~1ull;
+    int prev = 0;
+    while (m) {
+        const int pos = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        int run = pos - prev - 1;
+        prev = pos;
+        while (run > 15) {
+            emit(comp_tables + 1, 0xF0, 0u, 0);
+            run -= 16;
+        }
+        const int v = s_coef_at(s_coef, b, pos);
+        int cat;
+        uint32_t bits;
+        cat_bits(v, cat, bits);
+        ok &= cat <= 15;
+        emit(comp_tables + 1, (run << 4) | (cat & 15), bits, cat);
+    }
+    if (prev != 63) emit(comp_tables + 1, 0x00, 0u, 0);
+    return ok;
+}
+
+// =========================================== K2 ===========================================
+struct K2Args {
+    const int16_t* coef;
+    size_t coef_img_stride;
+    uint32_t n_blocks;
+    int ypm, bpm;
+    unsigned int* hist;        // [n][4][256]
+    ImgMeta* meta;             // [n]
+    const int16_t* seed_dc;    // optional [3] predictors for the first block of each component (shards)
+};
+
+__global__ void __launch_bounds__(EB) k2_histogram(const K2Args a) {
+    __shared__ uint4 s_coef[EB * 8];
+    __shared__ unsigned int s_hist[4 * 256];
+    const int img = blockIdx.y;
+    const int16_t* __restrict__ coef = a.coef + (size_t)img * a.coef_img_stride;
+    const uint32_t first = blockIdx.x * EB;
+    for (int i = threadIdx.x; i < 1024; i += EB) s_hist[i] = 0;
+    stage_chunk(s_coef, coef, first, a.n_blocks);
+    __syncthreads();
+    const uint32_t s = first + threadIdx.x;
+    if (s < a.n_blocks) {
+        const int b = threadIdx.x;
+        const uint32_t m_idx = s / a.bpm, k = s - m_idx * a.bpm;
+        const int comp = (int)k < a.ypm ? 0 : ((int)k == a.ypm ? 1 : 2);
+        const long long pb = prev_block_same_comp(s, a.ypm, a.bpm);
+        const int dc_pred = pb >= 0 ? (int)coef[(size_t)pb * 64] : (a.seed_dc ? (int)a.seed_dc[comp] : 0);
+        const unsigned long long mask = block_mask(s_coef, b);
+        const bool ok = walk_block(s_coef, b, mask, dc_pred, comp ? T_CDC : T_YDC,
+                                   [&](int t, int sym, uint32_t, int) { atomicAdd(&s_hist[t * 256 + sym], 1u); });
+        if (!ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_RANGE);
+    }
+    __syncthreads();
+    unsigned int* gh = a.hist + (size_t)img * 1024;
+    for (int i = threadIdx.x; i < 1024; i += EB) {
+        const unsigned int v = s_hist[i];
+        if (v) atomicAdd(&gh[i], v);
+    }
+}
+
+// =========================================== K2b ==========================================
+// One CTA (256 threads) per (table, image).  Package-merge with limit 15 in shared memory:
+// every level is a parallel merge-by-rank of the sorted leaves with the pairwise packages of the
+// previous level (Leaf < Package on equal frequency, length_limited.rs:7-26,104-115).
+struct K2bArgs {
+    const unsigned int* hist;      // [n][4][256] local counts (u32)
+    const unsigned long long* ghist;  // optional [4][256] u64 GLOBAL counts (sharded mode), else nullptr
+    EncTables* enc;                // [n]
+    LenTables* lens;               // [n]
+    ImgMeta* meta;                 // [n]
+    uint8_t* out;                  // [n][out_stride]  (header is written at offset 0)
+    size_t out_stride;
+    unsigned long long scan_cap_bits;
+    int W, H;                      // ORIGINAL width/height for SOF0 (transformer.rs:210-211)
+    int hr, vr;
+    int bits_per_channel;
+    uint8_t qzz[2][64];            // quantisation tables in zig-zag order for DQT
+    uint32_t n_stream_blocks;
+    int write_header;
+};
+
+constexpr int PM_LIMIT = 15;
+
+__global__ void __launch_bounds__(256) k2b_tables(const __grid_constant__ K2bArgs a) {
+    __shared__ unsigned long long s_freq[256];        // sorted leaf frequencies
+    __shared__ uint8_t s_sym[256];                    // sorted symbols (ascending frequency, ties by symbol)
+    __shared__ unsigned long long s_list[2][512];     // ping-pong merged lists (frequencies)
+    __shared__ uint16_t s_pkgpos[PM_LIMIT][256];      // position of package j in level k's merged list
+    __shared__ int s_npk[PM_LIMIT];                   // number of packages in level k
+    __shared__ int s_nleaves[PM_LIMIT];               // back-trace: leaves taken at level k
+    __shared__ int s_len[256];
+    __shared__ uint32_t s_scan[256];
+    __shared__ unsigned int s_cnt[4];
+    __shared__ unsigned int s_lcount[17];
+    __shared__ unsigned long long s_bits;
+    __shared__ uint32_t s_warp[9];
+    __shared__ int s_err;
+
+    const int t = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+    const int nsym_max = (t & 1) ? 256 : 16;
+    const unsigned int* lh = a.hist + (size_t)img * 1024;
+
+    if (tid < 4) s_cnt[tid] = 0;
+    if (tid < 17) s_lcount[tid] = 0;
+    if (tid == 0) s_bits = 0ull, s_err = 0;
+    __syncthreads();
+    // symbol counts of all four tables (header offsets need them) -- symbol_counting.rs:25-32
+#pragma unroll
+    for (int tt = 0; tt < 4; tt++) {
+        const unsigned long long f = a.ghist ? a.ghist[tt * 256 + tid] : (unsigned long long)lh[tt * 256 + tid];
+        const bool nz = (tid < ((tt & 1) ? 256 : 16)) && f != 0ull;
+        const unsigned int bal = __ballot_sync(0xffffffffu, nz);
+        if ((tid & 31) == 0 && bal) atomicAdd(&s_cnt[tt], (unsigned)__popc(bal));
+    }
+    const unsigned long long myf = (tid < nsym_max)
+                                       ? (a.ghist ? a.ghist[t * 256 + tid] : (unsigned long long)lh[t * 256 + tid])
+                                       : 0ull;
+    s_list[0][tid] = myf;  // scratch: raw frequencies by symbol
+    __syncthreads();
+    const int n = (int)s_cnt[t];
+    // stable sort by frequency of the ascending-symbol list (symbol_counting.rs:92-94): rank sort
+    if (myf != 0ull) {
+        int rank = 0;
+        for (int j = 0; j < nsym_max; j++) {
+            const unsigned long long fj = s_list[0][j];
+            rank += (fj != 0ull) && (fj < myf || (fj == myf && j < tid));
+        }
+        s_freq[rank] = myf;
+        s_sym[rank] = (uint8_t)tid;
+    }
+    __syncthreads();
+    if (n == 0) {  // no blocks at all: the reference panics (symbol_counting.rs:88 indexes [0])
+        if (tid == 0) atomicCAS(&a.meta[img].error, 0, DMMT_E_INVALID);
+        return;
+    }
+
+    // ---- package-merge levels (length_limited.rs:63-73,104-115) ----
+    int cur = 0;
+    int len_prev = n;
+    if (tid < n) s_list[1][tid] = s_freq[tid];
+    if (tid == 0) s_npk[0] = 0;
+    cur = 1;
+    __syncthreads();
+    for (int k = 1; k < PM_LIMIT; k++) {
+        const unsigned long long* prev = s_list[cur];
+        unsigned long long* nxt = s_list[cur ^ 1];
+        const int np = len_prev >> 1;  // chunks_exact(2)
+        // package j
+        unsigned long long pf = 0ull;
+        if (tid < np) pf = prev[2 * tid] + prev[2 * tid + 1];
+        __syncthreads();  // everybody has read prev before anyone overwrites (nxt != prev, but keep levels apart)
+        if (tid < np) {
+            // leaves with freq <= pf come first (leaf wins ties)
+            int lo = 0, hi = n;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_freq[mid] <= pf) lo = mid + 1;
+                else hi = mid;
+            }
+            const int pos = tid + lo;
+            nxt[pos] = pf;
+            s_pkgpos[k][tid] = (uint16_t)pos;
+        }
+        if (tid < n) {
+            // packages with freq < leaf come first.  Package frequencies are non-decreasing in j
+            // (pair sums of a sorted list), so binary search over j on the fly.
+            const unsigned long long lf = s_freq[tid];
+            int lo = 0, hi = np;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const unsigned long long pm = prev[2 * mid] + prev[2 * mid + 1];
+                if (pm < lf) lo = mid + 1;
+                else hi = mid;
+            }
+            nxt[tid + lo] = lf;
+        }
+        if (tid == 0) s_npk[k] = np;
+        len_prev = n + np;
+        cur ^= 1;
+        __syncthreads();
+    }
+    // ---- back-trace (length_limited.rs:75-89,117-133): thread 0, 15 binary searches ----
+    if (tid == 0) {
+        int p = n - 1;
+        for (int k = PM_LIMIT - 1; k >= 0; k--) {
+            const int count = 2 * p;
+            const int len_k = n + s_npk[k];
+            if (count > len_k) {  // slice panic in the reference; impossible for n <= 2^15
+                s_err = DMMT_E_INVALID;
+                s_nleaves[k] = 0;
+                p = 0;
+                continue;
+            }
+            int lo = 0, hi = s_npk[k];  // packages with position < count
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((int)s_pkgpos[k][mid] < count) lo = mid + 1;
+                else hi = mid;
+            }
+            s_nleaves[k] = count - lo;
+            p = lo;
+        }
+    }
+    __syncthreads();
+    // sum_up_codeword_lengths (length_limited.rs:91-102) then the +1 quirk (symbol_counting.rs:88)
+    int mylen = 0;
+    if (tid < n) {
+#pragma unroll
+        for (int k = 0; k < PM_LIMIT; k++) mylen += (tid < s_nleaves[k]);
+        if (tid == 0) mylen += 1;
+        s_len[tid] = mylen;
+        atomicAdd(&s_lcount[mylen <= 16 ? mylen : 0], 1u);
+        if (mylen < 1 || mylen > 16) s_err = DMMT_E_INVALID;
+    }
+    // ---- canonical codes (huffman/encoder.rs:45-67,116-119): walk from the END of the table:
+    // code(i) = sum_{j > i} 2^(16 - len_j)  -> exclusive scan over the reversed order ----
+    const int ri = n - 1 - tid;  // reversed index handled by this thread
+    uint32_t inc = 0;
+    __syncthreads();
+    if (tid < n) inc = 1u << (16 - s_len[ri]);
+    uint32_t total;
+    const uint32_t excl = block_exclusive_scan<256>(tid < n ? inc : 0u, s_warp, &total);
+    if (tid < n) {
+        const int len = s_len[ri];
+        if (excl > 0xFFFFu) s_err = DMMT_E_INVALID;
+        const uint32_t code = (excl & 0xFFFFu) >> (16 - len);  // right-aligned
+        s_scan[ri] = ((uint32_t)len << 16) | code;
+    }
+    __syncthreads();
+    // LUT by symbol + length tables + this table's share of the scan bits
+    EncTables* enc = a.enc + img;
+    LenTables* lt = a.lens + img;
+    enc->e[t][tid] = 0u;
+    lt->sym[t][tid] = 0;
+    lt->len[t][tid] = 0;
+    __syncthreads();
+    if (tid < n) {
+        const int sym = s_sym[tid];
+        enc->e[t][sym] = s_scan[tid];
+        lt->sym[t][tid] = (uint8_t)sym;
+        lt->len[t][tid] = (uint8_t)s_len[tid];
+        // bits contributed by this symbol in THIS image/shard: local count x (code length + category bits)
+        const unsigned long long cnt = lh[t * 256 + sym];
+        atomicAdd(&s_bits, cnt * (unsigned long long)(s_len[tid] + (sym & 15)));
+    }
+    __syncthreads();
+    ImgMeta* meta = a.meta + img;
+    if (tid == 0) {
+        atomicAdd(&meta->scan_bits, s_bits);
+        meta->n_symbols[t] = (uint32_t)n;
+        if (s_err) atomicCAS(&meta->error, 0, s_err);
+    }
+    if (!a.write_header) return;
+
+    // ---- headers (jpeg/encoder.rs:125-262) ----
+    // layout: SOI(2) APP0(18) DQT(69) DQT(69) SOF0(19) | DHT YAC, YDC, CAC, CDC (21 + n each) | SOS(14)
+    uint8_t* out = a.out + (size_t)img * a.out_stride;
+    const uint32_t nY_AC = s_cnt[T_YAC], nY_DC = s_cnt[T_YDC], nC_AC = s_cnt[T_CAC], nC_DC = s_cnt[T_CDC];
+    uint32_t off = 177;
+    if (t == T_YDC) off += 21 + nY_AC;
+    else if (t == T_CAC) off += 42 + nY_AC + nY_DC;
+    else if (t == T_CDC) off += 63 + nY_AC + nY_DC + nC_AC;
+    const uint32_t hdr_len = 177 + 84 + nY_AC + nY_DC + nC_AC + nC_DC + 14;
+    {
+        // DHT: FF C4, len = 2 + 17 + n, Tc/Th id (encoder.rs:78-84), counts[16] (:92-98),
+        // symbols in REVERSE table order (:177)
+        uint8_t* p = out + off;
+        const uint8_t ids[4] = {0x00, 0x11, 0x02, 0x13};
+        if (tid == 0) {
+            p[0] = 0xFF, p[1] = 0xC4;
+            p[2] = (uint8_t)((19 + n) >> 8), p[3] = (uint8_t)((19 + n) & 0xFF);
+            p[4] = ids[t];
+        }
+        if (tid < 16) p[5 + tid] = (uint8_t)s_lcount[tid + 1];
+        if (tid < n) p[21 + tid] = s_sym[n - 1 - tid];
+    }
+    if (t == 0) {
+        if (tid == 0) {
+            uint8_t* p = out;
+            const uint8_t fixed[20] = {0xFF, 0xD8, 0xFF, 0xE0, 0x00, 0x10, 'J', 'F', 'I', 'F', 0,
+                                       0x01, 0x02, 0x00, 0x00, 0x48, 0x00, 0x48, 0x00, 0x00};
+            for (int i = 0; i < 20; i++) p[i] = fixed[i];
+            p = out + 158;  // SOF0 (encoder.rs:227-245)
+            const uint8_t sof[19] = {0xFF, 0xC0, 0x00, 0x11, (uint8_t)a.bits_per_channel,
+                                     (uint8_t)(a.H >> 8), (uint8_t)a.H, (uint8_t)(a.W >> 8), (uint8_t)a.W,
+                                     0x03, 0x01, (uint8_t)((a.hr << 4) | a.vr), 0x00,
+                                     0x02, 0x11, 0x01, 0x03, 0x11, 0x01};
+            for (int i = 0; i < 19; i++) p[i] = sof[i];
+            p = out + hdr_len - 14;  // SOS (encoder.rs:247-262)
+            const uint8_t sos[14] = {0xFF, 0xDA, 0x00, 0x0C, 0x03, 0x01, 0x01, 0x02, 0x23, 0x03, 0x23,
+                                     0x00, 0x3F, 0x00};
+            for (int i = 0; i < 14; i++) p[i] = sos[i];
+            meta->header_len = hdr_len;
+            meta->n_stream_blocks = a.n_stream_blocks;
+        }
+        if (tid < 138) {  // two DQT segments (encoder.rs:190-209), 69 bytes each
+            const int which = tid / 69, i = tid % 69;
+            uint8_t v;
+            if (i == 0) v = 0xFF;
+            else if (i == 1) v = 0xDB;
+            else if (i == 2) v = 0x00;
+            else if (i == 3) v = 0x43;
+            else if (i == 4) v = (uint8_t)which;
+            else v = a.qzz[which][i - 5];
+            out[20 + tid] = v;
+        }
+    }
+}
+
+// After K2b: flags images whose scan would not fit the plan's capacity (one thread per image)
+__global__ void k_check_capacity(ImgMeta* meta, int n, unsigned long long cap_bits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && meta[i].scan_bits + 8 > cap_bits) atomicCAS(&meta[i].error, 0, DMMT_E_OVERFLOW);
+}
+
+// Zeroes the words of the unstuffed scan buffers that K3 will OR into (sizes are only known on
+// the device): grid (Z, n), each row strides over that image's words.
+__global__ void k_zero_scan(uint32_t* scan, size_t scan_img_stride_words, const ImgMeta* meta,
+                            unsigned long long seed_bits) {
+    const int img = blockIdx.y;
+    if (meta[img].error) return;
+    const unsigned long long words = (meta[img].scan_bits + seed_bits + 8 + 31) / 32 + 1;
+    uint32_t* p = scan + (size_t)img * scan_img_stride_words;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < words;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        p[i] = 0u;
+}
+
+// =========================================== K3 ===========================================
+struct K3Args {
+    const int16_t* coef;
+    size_t coef_img_stride;
+    uint32_t n_blocks;
+    uint32_t n_chunks;
+    int ypm, bpm;
+    const EncTables* enc;          // [n]
+    ImgMeta* meta;                 // [n]
+    unsigned long long* lb_state;  // [n][n_chunks]  zero-initialised per run
+    unsigned int* ticket;          // [n]            zero-initialised per run
+    uint32_t* scan;                // [n][scan_img_stride_words] big-endian bit stream, zero-initialised by k_zero_scan
+    size_t scan_img_stride_words;
+    const int16_t* seed_dc;        // optional [3]
+    unsigned long long seed_bits;  // bit offset of this shard's first bit inside its first byte/word (< 32)
+    int pad_ones;                  // append the 1-padding after the last block (binary_stream.rs:89-96)
+};
+
+// bit sink: OR `len` bits (right-aligned in `code`) at absolute bit position *pos of a big-endian
+// word stream; Shared = 32-bit shared-memory atomics, else global atomics on byte-swapped words.
+template <bool Shared>
+struct BitSink {
+    uint32_t* words;
+    unsigned long long acc;  // left-aligned pending bits
+    int fill;                // valid bits in acc (< 32 between appends)
+    unsigned long long wpos;
+    __device__ __forceinline__ void init(uint32_t* w, unsigned long long bitpos) {
+        words = w;
+        acc = 0ull;
+        fill = (int)(bitpos & 31);
+        wpos = bitpos >> 5;
+    }
+    __device__ __forceinline__ void or_word(uint32_t v) {
+        if (v == 0u) return;
+        if (Shared) atomicOr(&words[wpos], v);
+        else atomicOr(&words[wpos], bswap32(v));
+    }
+    __device__ __forceinline__ void put(uint32_t code, int len) {  // len <= 31
+        acc |= (unsigned long long)code << (64 - fill - len);
+        fill += len;
+        if (fill >= 32) {
+            or_word((uint32_t)(acc >> 32));
+            ++wpos;
+            acc <<= 32;
+            fill -= 32;
+        }
+    }
+    __device__ __forceinline__ void flush() {
+        if (fill > 0) or_word((uint32_t)(acc >> 32));
+    }
+};
+
+__global__ void __launch_bounds__(EB) k3_pack(const K3Args a) {
+    __shared__ uint4 s_coef[EB * 8];
+    __shared__ uint32_t s_out[K3_OUT_WORDS];
+    __shared__ uint32_t s_enc[4 * 256];
+    __shared__ uint32_t s_warp[EB / 32 + 1];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_chunk;
+
+    const int img = blockIdx.y;
+    // chunk index in START order, so a waiting CTA's predecessors are always running or done.
+    // Images flagged by K2/K2b (range / capacity) are skipped; the flag is read once per CTA
+    // (K3 itself may set it concurrently, so it must not be re-read per thread).
+    if (threadIdx.x == 0) {
+        const int err = *reinterpret_cast<volatile int32_t*>(&a.meta[img].error);
+        s_chunk = (err == 0 || err == DMMT_E_SYMBOL) ? atomicAdd(&a.ticket[img], 1u) : 0xFFFFFFFFu;
+    }
+    for (int i = threadIdx.x; i < 1024; i += EB) s_enc[i] = a.enc[img].e[i >> 8][i & 255];
+    __syncthreads();
+    const uint32_t chunk = s_chunk;
+    if (chunk == 0xFFFFFFFFu) return;
+    const int16_t* __restrict__ coef = a.coef + (size_t)img * a.coef_img_stride;
+    const uint32_t first = chunk * EB;
+    stage_chunk(s_coef, coef, first, a.n_blocks);
+    __syncthreads();
+
+    const uint32_t s = first + threadIdx.x;
+    const bool active = s < a.n_blocks;
+    const int b = threadIdx.x;
+    unsigned long long mask = 0ull;
+    int dc_pred = 0, tbl = 0;
+    uint32_t nbits = 0;
+    bool ok = true, sym_ok = true;
+    if (active) {
+        const uint32_t m_idx = s / a.bpm, k = s - m_idx * a.bpm;
+        const int comp = (int)k < a.ypm ? 0 : ((int)k == a.ypm ? 1 : 2);
+        tbl = comp ? T_CDC : T_YDC;
+        const long long pb = prev_block_same_comp(s, a.ypm, a.bpm);
+        dc_pred = pb >= 0 ? (int)coef[(size_t)pb * 64] : (a.seed_dc ? (int)a.seed_dc[comp] : 0);
+        mask = block_mask(s_coef, b);
+        // pass 1: bit length of the block
+        ok = walk_block(s_coef, b, mask, dc_pred, tbl, [&](int t, int sym, uint32_t, int extra) {
+            const uint32_t e = s_enc[t * 256 + sym];
+            if ((e >> 16) == 0u) sym_ok = false;  // Error::HuffmanSymbolNotPresentInTranslator
+            nbits += (e >> 16) + (uint32_t)extra;
+        });
+    }
+    uint32_t chunk_bits;
+    const uint32_t off = block_exclusive_scan<EB>(nbits, s_warp, &chunk_bits);
+    if (threadIdx.x == 0)
+        s_prefix = lookback_exclusive(a.lb_state + (size_t)img * a.n_chunks, (int)chunk, chunk_bits);
+    __syncthreads();
+    const unsigned long long g0 = a.seed_bits + s_prefix;        // global bit position of the chunk
+    const unsigned long long gw0 = g0 >> 5;                      // first global word touched
+    const uint32_t phase = (uint32_t)(g0 & 31);
+    const bool last_chunk = (chunk == a.n_chunks - 1);
+    uint32_t pad = 0;
+    if (last_chunk && a.pad_ones) pad = (uint32_t)((8 - ((g0 + chunk_bits) & 7)) & 7);
+    const uint32_t span_bits = phase + chunk_bits + pad;
+    const uint32_t n_words = (span_bits + 31) >> 5;
+    uint32_t* gscan = a.scan + (size_t)img * a.scan_img_stride_words;
+    if (!ok || !sym_ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_SYMBOL);
+
+    if (n_words <= K3_OUT_WORDS) {
+        // fast path: assemble the chunk's bits in shared memory, then one coalesced flush
+        for (uint32_t i = threadIdx.x; i < n_words; i += EB) s_out[i] = 0u;
+        __syncthreads();
+        if (active) {
+            BitSink<true> sink;
+            sink.init(s_out, phase + off);
+            walk_block(s_coef, b, mask, dc_pred, tbl, [&](int t, int sym, uint32_t bits, int extra) {
+                const uint32_t e = s_enc[t * 256 + sym];
+                const int len = (int)(e >> 16);
+                sink.put(((e & 0xFFFFu) << extra) | bits, len + extra);
+            });
+            sink.flush();
+        }
+        if (pad && threadIdx.x == 0) {
+            BitSink<true> sink;
+            sink.init(s_out, phase + chunk_bits);
+            sink.put((1u << pad) - 1u, (int)pad);
+            sink.flush();
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n_words; i += EB) {
+            const uint32_t v = bswap32(s_out[i]);
+            if (i == 0 || i == n_words - 1) {  // words shared with the neighbouring chunks
+                if (v) atomicOr(&gscan[gw0 + i], v);
+            } else {
+                gscan[gw0 + i] = v;
+            }
+        }
+    } else {
+        // dense chunk (> 24 KB of code): OR straight into the zeroed global stream
+        if (active) {
+            BitSink<false> sink;
+            sink.init(gscan, g0 + off);
+            walk_block(s_coef, b, mask, dc_pred, tbl, [&](int t, int sym, uint32_t bits, int extra) {
+                const uint32_t e = s_enc[t * 256 + sym];
+                const int len = (int)(e >> 16);
+                sink.put(((e & 0xFFFFu) << extra) | bits, len + extra);
+            });
+            sink.flush();
+        }
+        if (pad && threadIdx.x == 0) {
+            BitSink<false> sink;
+            sink.init(gscan, g0 + chunk_bits);
+            sink.put((1u << pad) - 1u, (int)pad);
+            sink.flush();
+        }
+    }
+}
+
+// =========================================== K4 ===========================================
+// Byte stuffing as scan + compaction: each thread owns 32 consecutive unstuffed bytes, counts its
+// 0xFF bytes, a block scan + decoupled look-back gives its output offset, then it writes its
+// bytes with the inserted zeros.  The CTA that owns the last byte also writes EOI and the length.
+struct K4Args {
+    const uint8_t* scan;           // [n][scan_img_stride_bytes]
+    size_t scan_img_stride_bytes;
+    ImgMeta* meta;                 // [n]
+    unsigned long long* lb_state;  // [n][max_chunks]
+    unsigned int* ticket;          // [n]
+    uint32_t max_chunks;
+    uint8_t* out;                  // [n][out_stride]
+    size_t out_stride;
+    unsigned long long* out_lens;  // [n] optional
+    // shard controls (whole-image encode: first_byte = 0, use meta bits, header from meta, eoi = 1)
+    unsigned long long first_byte; // first unstuffed byte this call owns
+    long long n_bytes_override;    // < 0: ceil((seed_bits + scan_bits) / 8) - first_byte
+    unsigned long long seed_bits;
+    int prepend_header;            // output starts after the header written by K2b
+    int append_eoi;
+    uint8_t or_first_byte;         // previous shard's tail bits, OR-ed into the first owned byte
+};
+
+__global__ void __launch_bounds__(K4_THREADS) k4_stuff(const K4Args a) {
+    __shared__ uint32_t s_warp[K4_THREADS / 32 + 1];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_chunk;
+    const int img = blockIdx.y;
+    ImgMeta* meta = a.meta + img;
+    if (meta->error) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && a.out_lens) a.out_lens[img] = 0ull;
+        return;
+    }
+    const unsigned long long total_bytes =
+        a.n_bytes_override >= 0 ? (unsigned long long)a.n_bytes_override
+                                : (a.seed_bits + meta->scan_bits + 7) / 8 - a.first_byte;
+    const uint32_t n_chunks = (uint32_t)((total_bytes + K4_CHUNK - 1) / K4_CHUNK);
+    const uint32_t hdr = a.prepend_header ? meta->header_len : 0u;
+    uint8_t* out = a.out + (size_t)img * a.out_stride;
+    if (n_chunks == 0) {  // nothing owned (possible for a shard); still terminate the file
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long len = hdr;
+            if (a.append_eoi) out[len] = 0xFF, out[len + 1] = 0xD9, len += 2;
+            meta->out_len = len;
+            if (a.out_lens) a.out_lens[img] = len;
+        }
+        return;
+    }
+    if (threadIdx.x == 0) s_chunk = atomicAdd(&a.ticket[img], 1u);
+    __syncthreads();
+    const uint32_t chunk = s_chunk;
+    if (chunk >= n_chunks) return;
+
+    const uint8_t* __restrict__ src = a.scan + (size_t)img * a.scan_img_stride_bytes + a.first_byte;
+    const unsigned long long base = (unsigned long long)chunk * K4_CHUNK + (unsigned long long)threadIdx.x * K4_BYTES_PER_THREAD;
+    // load up to 32 bytes (the scan buffer is padded, reading past total_bytes is safe but masked)
+    uint32_t w[8];
+    int nvalid = 0;
+    if (base < total_bytes) {
+        const unsigned long long rem = total_bytes - base;
+        nvalid = rem < K4_BYTES_PER_THREAD ? (int)rem : K4_BYTES_PER_THREAD;
+        const uint8_t* p = src + base;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            const uint4 v0 = *reinterpret_cast<const uint4*>(p), v1 = *reinterpret_cast<const uint4*>(p + 16);
+            w[0] = v0.x, w[1] = v0.y, w[2] = v0.z, w[3] = v0.w, w[4] = v1.x, w[5] = v1.y, w[6] = v1.z, w[7] = v1.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                w[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) |
+                       ((uint32_t)p[4 * i + 3] << 24);
+        }
+        if (base == 0 && a.or_first_byte) w[0] |= a.or_first_byte;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = 0;
+    }
+    uint32_t nff = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        // bytes beyond nvalid are ignored
+        uint32_t eq = __vcmpeq4(w[i], 0xFFFFFFFFu);  // 0xFF per matching byte
+        const int valid_in_word = nvalid - 4 * i;
+        if (valid_in_word < 4) eq &= valid_in_word <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - valid_in_word)));
+        nff += __popc(eq) >> 3;
+    }
+    uint32_t chunk_ff;
+    const uint32_t ff_before = block_exclusive_scan<K4_THREADS>(nff, s_warp, &chunk_ff);
+    if (threadIdx.x == 0)
+        s_prefix = lookback_exclusive(a.lb_state + (size_t)img * a.max_chunks, (int)chunk, chunk_ff);
+    __syncthreads();
+    unsigned long long o = hdr + base + s_prefix + ff_before;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (4 * i + j < nvalid) {
+                const uint8_t v = (uint8_t)(w[i] >> (8 * j));
+                out[o++] = v;
+                if (v == 0xFF) out[o++] = 0x00;
+            }
+        }
+    }
+    if (chunk == n_chunks - 1 && nvalid > 0 && base + nvalid == total_bytes) {
+        // owner of the last byte: EOI (encoder.rs:164-167) + file length
+        unsigned long long len = o;
+        if (a.append_eoi) out[len] = 0xFF, out[len + 1] = 0xD9, len += 2;
+        meta->out_len = len;
+        if (a.out_lens) a.out_lens[img] = len;
+    }
+}
+
+// extracts the quantised DC of the last Y / Cb / Cr block (shard hand-over)
+__global__ void k_last_dc(const int16_t* coef, uint32_t n_blocks, int ypm, int bpm, int16_t* out3) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const size_t last_mcu = (size_t)(n_blocks / bpm - 1) * bpm;
+        out3[0] = coef[(last_mcu + ypm - 1) * 64];
+        out3[1] = coef[(last_mcu + ypm) * 64];
+        out3[2] = coef[(last_mcu + ypm + 1) * 64];
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host launchers
+cudaError_t launch_k2(const Geom& g, const int16_t* coef, size_t coef_img_stride, int n, unsigned int* hist,
+                      ImgMeta* meta, const int16_t* seed_dc, cudaStream_t st) {
+    K2Args a{coef, coef_img_stride, g.n_blocks, g.ypm, g.bpm, hist, meta, seed_dc};
+    dim3 grid((g.n_blocks + EB - 1) / EB, n);
+    k2_histogram<<<grid, EB, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+struct K2bHostArgs {
+    const unsigned int* hist;
+    const unsigned long long* ghist;
+    EncTables* enc;
+    LenTables* lens;
+    ImgMeta* meta;
+    uint8_t* out;
+    size_t out_stride;
+    unsigned long long scan_cap_bits;
+    int W, H, bits_per_channel;
+    const uint8_t* qtab_luma;    // natural order
+    const uint8_t* qtab_chroma;
+    int write_header;
+};
+
+cudaError_t launch_k2b(const Geom& g, const K2bHostArgs& h, int n, cudaStream_t st) {
+    K2bArgs a;
+    a.hist = h.hist;
+    a.ghist = h.ghist;
+    a.enc = h.enc;
+    a.lens = h.lens;
+    a.meta = h.meta;
+    a.out = h.out;
+    a.out_stride = h.out_stride;
+    a.scan_cap_bits = h.scan_cap_bits;
+    a.W = h.W;
+    a.H = h.H;
+    a.hr = g.hr;
+    a.vr = g.vr;
+    a.bits_per_channel = h.bits_per_channel;
+    for (int i = 0; i < 64; i++) {
+        a.qzz[0][i] = h.qtab_luma[zz_at(i)];
+        a.qzz[1][i] = h.qtab_chroma[zz_at(i)];
+    }
+    a.n_stream_blocks = g.n_blocks;
+    a.write_header = h.write_header;
+    k2b_tables<<<dim3(4, n), 256, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_check_capacity<<<(n + 127) / 128, 128, 0, st>>>(h.meta, n, h.scan_cap_bits);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_zero_scan(uint32_t* scan, size_t stride_words, const ImgMeta* meta, int n,
+                             unsigned long long seed_bits, int blocks_per_image, cudaStream_t st) {
+    k_zero_scan<<<dim3(blocks_per_image, n), 256, 0, st>>>(scan, stride_words, meta, seed_bits);
+    return cudaGetLastError();
+}
+
+uint32_t k3_chunks(const Geom& g) { return (g.n_blocks + EB - 1) / EB; }
+uint32_t k4_max_chunks(size_t scan_cap_bytes) { return (uint32_t)((scan_cap_bytes + K4_CHUNK - 1) / K4_CHUNK); }
+
+cudaError_t launch_k3(const Geom& g, const int16_t* coef, size_t coef_img_stride, int n, const EncTables* enc,
+                      ImgMeta* meta, unsigned long long* lb_state, unsigned int* ticket, uint32_t* scan,
+                      size_t scan_stride_words, const int16_t* seed_dc, unsigned long long seed_bits,
+                      int pad_ones, cudaStream_t st) {
+    K3Args a{coef, coef_img_stride, g.n_blocks, k3_chunks(g), g.ypm, g.bpm, enc, meta, lb_state, ticket,
+             scan, scan_stride_words, seed_dc, seed_bits, pad_ones};
+    k3_pack<<<dim3(a.n_chunks, n), EB, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+struct K4HostArgs {
+    const uint8_t* scan;
+    size_t scan_stride_bytes;
+    ImgMeta* meta;
+    unsigned long long* lb_state;
+    unsigned int* ticket;
+    uint32_t max_chunks;
+    uint8_t* out;
+    size_t out_stride;
+    unsigned long long* out_lens;
+    unsigned long long first_byte;
+    long long n_bytes_override;
+    unsigned long long seed_bits;
+    int prepend_header, append_eoi;
+    uint8_t or_first_byte;
+};
+
+cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStream_t st) {
+    K4Args a{h.scan, h.scan_stride_bytes, h.meta, h.lb_state, h.ticket, h.max_chunks, h.out, h.out_stride,
+             h.out_lens, h.first_byte, h.n_bytes_override, h.seed_bits, h.prepend_header, h.append_eoi,
+             h.or_first_byte};
+    if (grid_chunks == 0) grid_chunks = 1;
+    k4_stuff<<<dim3(grid_chunks, n), K4_THREADS, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_last_dc(const Geom& g, const int16_t* coef, int16_t* d_out3, cudaStream_t st) {
+    k_last_dc<<<1, 32, 0, st>>>(coef, g.n_blocks, g.ypm, g.bpm, d_out3);
+    return cudaGetLastError();
+}
+
+}  // namespace dmmt

@@ -1,0 +1,189 @@
+/*
+ * dmmt_cuda.h -- C ABI of the B200-native (sm_100a) encode hot path of dmmt-jpeg-encoder.
+ *
+ * This is the drop-in boundary: the body of the reference's
+ *     impl ImageWriter for JpegImageWriter { fn write_image(&mut self) }   (src/image/writer/jpeg.rs:64-75)
+ * i.e. Transformer::transform (src/image/writer/jpeg/transformer.rs:188-221) followed by
+ * Encoder::encode (src/image/writer/jpeg/encoder.rs:125-135) becomes ONE call, dmmt_encode();
+ * the returned bytes are what the reference `write_all`s into its `T: Write`.
+ * INTEGRATION.md shows the Rust `extern "C"` block / build.rs that binds these symbols.
+ *
+ * Conventions: plain pointers and sizes only; 0 = OK, negative = error (dmmt_strerror);
+ * no exceptions cross the boundary; there is NO CPU fallback: without a CUDA device every
+ * entry point that computes returns DMMT_E_NODEVICE.  A context is bound to one device and
+ * one stream and is not thread-safe (one host thread per context).
+ */
+#ifndef DMMT_CUDA_H
+#define DMMT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (mapping onto the reference's crate::Error, src/error.rs:4-23) ---------- */
+#define DMMT_OK 0
+#define DMMT_E_INVALID (-1)   /* bad argument (null, zero-sized image, unknown preset, sample > max: color.rs:62-65 panics) */
+#define DMMT_E_NODEVICE (-2)  /* no usable CUDA device; never falls back to the CPU */
+#define DMMT_E_CUDA (-3)      /* CUDA runtime failure (see dmmt_last_cuda_error) */
+#define DMMT_E_NCCL (-4)      /* collective failure in the sharded path */
+#define DMMT_E_NOMEM (-5)     /* host or device allocation failed */
+#define DMMT_E_OVERFLOW (-6)  /* entropy-coded scan exceeded the plan's scan capacity (retry with dmmt_plan_set_scan_capacity) */
+#define DMMT_E_SYMBOL (-7)    /* Error::HuffmanSymbolNotPresentInTranslator (error.rs:21) */
+#define DMMT_E_RANGE (-8)     /* coefficient not categorisable (categorize.rs:25-30 panics on -32768) */
+#define DMMT_E_WRITE (-9)     /* Error::FailedToWriteImageData / FailedToWriteBlock family: output arena too small */
+#define DMMT_E_SIZE (-10)     /* geometry beyond the reference's u16 image model (image.rs:8-9, padder.rs:13-14) */
+
+/* ---- reference option enums -------------------------------------------------------------- */
+/* ChromaSubsamplingPreset, src/image/subsampling.rs:11-16 */
+#define DMMT_P444 0
+#define DMMT_P422 1
+#define DMMT_P420 2
+/* QuantizationTablePreset in enum order, src/image/writer/jpeg/quantization_tables.rs:232-243 */
+#define DMMT_Q_SPECIFICATION 0
+#define DMMT_Q_FLAT 1
+#define DMMT_Q_MSSIM_KODAK_TUNED 2
+#define DMMT_Q_PSNR_HVS_N_KODAK_TUNED 3
+#define DMMT_Q_DCTUNE_PERCEPTUAL_OPTIMIZATION 4
+#define DMMT_Q_A_VISUAL_DETECTION_MODEL 5
+#define DMMT_Q_AN_IMPROVED_DETECTION_MODEL 6
+
+/* Pixel formats.  F32_NORM is the exact stand-in for the reference's Image<f32>
+ * (src/image.rs:7-11: Vec<RGBColorFormat<f32>>, already v/max normalised by the reader,
+ * src/image/reader/ppm.rs:153-157 + src/color.rs:45-53).  U8/U16 are the throughput formats:
+ * the device performs the same IEEE `v as f32 / max as f32`. */
+typedef enum { DMMT_RGB_F32_NORM = 0, DMMT_RGB_U8 = 1, DMMT_RGB_U16 = 2 } dmmt_fmt;
+
+typedef struct dmmt_ctx dmmt_ctx;   /* one device + one stream + cached plans */
+typedef struct dmmt_plan dmmt_plan; /* fixed geometry/options, owns all device scratch for n images */
+
+typedef struct {
+    uint16_t width, height;   /* Image<T>::{width,height} are u16 (image.rs:8-9) */
+    uint16_t max_value;       /* PPM max value (ignored for F32_NORM) */
+    dmmt_fmt fmt;
+    const void *pixels;       /* interleaved R,G,B, row-major, tightly packed */
+    int pixels_on_device;     /* 0: host memory, 1: device memory of the context's device */
+} dmmt_image;
+
+/* JpegTransformationOptions, src/image/writer/jpeg.rs:25-29 */
+typedef struct {
+    uint8_t subsampling;      /* DMMT_P444 / P422 / P420 */
+    uint8_t bits_per_channel; /* copied into SOF0 only (encoder.rs:235) */
+    uint8_t qtable_preset;    /* DMMT_Q_* */
+} dmmt_options;
+
+/* ---- contexts ---------------------------------------------------------------------------- */
+int dmmt_device_count(void);                                /* 0 when no GPU / no driver */
+int dmmt_ctx_create(int device, dmmt_ctx **out);            /* own non-blocking stream */
+/* Same, but all work is issued on the caller's cudaStream_t (e.g. torch's current stream). */
+int dmmt_ctx_create_on_stream(int device, void *cuda_stream, dmmt_ctx **out);
+void dmmt_ctx_destroy(dmmt_ctx *);
+int dmmt_ctx_synchronize(dmmt_ctx *);
+void *dmmt_ctx_stream(dmmt_ctx *);                          /* the cudaStream_t in use */
+
+/* ---- the drop-in call: replaces JpegImageWriter::write_image (jpeg.rs:64-75) -------------- */
+/* Synchronous at return.  *jpeg is malloc'd by the callee; release with dmmt_free. */
+int dmmt_encode(dmmt_ctx *, const dmmt_image *, const dmmt_options *, uint8_t **jpeg, size_t *len);
+/* n independent images; image i is encoded on ctxs[i % nctx] (round-robin).
+ * Images sharing geometry+format on one context are encoded by ONE batched launch chain. */
+int dmmt_encode_batch(dmmt_ctx *const *ctxs, int nctx, const dmmt_image *imgs, int n,
+                      const dmmt_options *, uint8_t **jpegs, size_t *lens);
+/* One large image split by MCU rows over nctx devices of this process (single-process
+ * multi-device; the one-process-per-GPU variant is the dmmt_shard_* API below). */
+int dmmt_encode_sharded(dmmt_ctx *const *ctxs, int nctx, const dmmt_image *, const dmmt_options *,
+                        uint8_t **jpeg, size_t *len);
+void dmmt_free(void *);
+const char *dmmt_strerror(int code);
+const char *dmmt_last_cuda_error(void); /* thread-local text of the last CUDA failure */
+
+/* ---- plans: device-resident batched encode (what bench.py times) ------------------------- */
+int dmmt_plan_create(dmmt_ctx *, uint16_t width, uint16_t height, dmmt_fmt fmt, uint16_t max_value,
+                     const dmmt_options *, int n_images, dmmt_plan **out);
+void dmmt_plan_destroy(dmmt_plan *);
+size_t dmmt_plan_pixel_bytes(const dmmt_plan *);  /* bytes of ONE input image */
+size_t dmmt_plan_out_stride(const dmmt_plan *);   /* bytes reserved per image in the output arena */
+/* Scan capacity per image in bytes (default: 128 B per 8x8 block); worst case is
+ * dmmt_plan_worst_case_scan_bytes().  Reallocates scratch. */
+int dmmt_plan_set_scan_capacity(dmmt_plan *, size_t bytes_per_image);
+size_t dmmt_plan_worst_case_scan_bytes(const dmmt_plan *);
+/* Asynchronous on the context's stream.  d_pixels: n images back to back in device memory;
+ * d_out: n * out_stride bytes; d_lens: n u64 (file length per image; 0 + error flag on failure).
+ * Use dmmt_plan_status after synchronising to read the device-side error flags. */
+int dmmt_plan_encode_device(dmmt_plan *, const void *d_pixels, uint8_t *d_out, uint64_t *d_lens);
+int dmmt_plan_status(dmmt_plan *);                /* synchronises; first device-side error or 0 */
+/* Host-buffer end-to-end: H2D of the pixels, encode, D2H of lengths + bytes.  jpegs[i] malloc'd. */
+int dmmt_plan_encode_host(dmmt_plan *, const void *h_pixels, uint8_t **jpegs, size_t *lens);
+/* Same but into a caller-provided host arena (n * out_stride bytes, ideally pinned). */
+int dmmt_plan_encode_host_into(dmmt_plan *, const void *h_pixels, uint8_t *h_out, uint64_t *h_lens);
+
+/* per-kernel CUDA-event timings of the last dmmt_plan_encode_* call (profiling must be enabled
+ * first; it adds event records between the kernels).  ms[] order: DMMT_T_* */
+#define DMMT_T_K1_TRANSFORM 0 /* fused normalise/pad/YCbCr/subsample/DCT/quantise/zig-zag */
+#define DMMT_T_K2_HISTOGRAM 1
+#define DMMT_T_K2B_TABLES 2
+#define DMMT_T_K3_PACK 3      /* bit-length + decoupled look-back scan + pack (incl. scan zeroing) */
+#define DMMT_T_K4_STUFF 4
+#define DMMT_T_TOTAL 5
+#define DMMT_T_COUNT 6
+int dmmt_plan_set_profiling(dmmt_plan *, int enabled);
+int dmmt_plan_last_timings(dmmt_plan *, float *ms, int n);
+/* number of kernels launched by the last encode call on this plan */
+int dmmt_plan_last_launch_count(const dmmt_plan *);
+
+/* ---- test / measurement hooks (not part of the drop-in surface) --------------------------- */
+#define DMMT_FETCH_COEF 0      /* i16 [n_stream_blocks][64], zig-zag, MCU-interleaved stream order */
+#define DMMT_FETCH_HIST 1      /* u32 [4][256]: Y-DC, Y-AC, C-DC, C-AC */
+#define DMMT_FETCH_TABLES 2    /* u8  [4][2][256]: per table symbols[256] then lengths[256] in the reference's Vec<SymbolCodeLength> order; count via DMMT_FETCH_META */
+#define DMMT_FETCH_SCAN 3      /* unstuffed, 1-padded scan bytes */
+#define DMMT_FETCH_META 4      /* dmmt_image_meta */
+typedef struct {
+    uint64_t scan_bits;        /* entropy-coded bits before padding */
+    uint64_t out_len;          /* whole file length */
+    uint32_t header_len;
+    uint32_t n_symbols[4];
+    int32_t error;
+    uint32_t n_stream_blocks;
+    uint32_t reserved;
+} dmmt_image_meta;
+/* copies an intermediate of image `index` of the last encode to host memory */
+int dmmt_plan_fetch(dmmt_plan *, int what, int index, void *dst, size_t cap_bytes, size_t *got);
+/* pre-quantisation DCT coefficients (f32, natural order inside a block, stream order of blocks)
+ * of image `index`: runs the debug variant of K1 on d_pixels (device) and copies to host. */
+int dmmt_plan_debug_dct(dmmt_plan *, const void *d_pixels, int index, float *dst, size_t cap_floats);
+size_t dmmt_plan_stream_blocks(const dmmt_plan *);
+
+/* ---- one-process-per-GPU sharding of ONE image by MCU rows -------------------- */
+/* A shard plan covers MCU rows [mcu_row_begin, mcu_row_end) of a full_width x full_height image.
+ * The caller exchanges the small values between the phases with its own collective
+ * (torch.distributed / NCCL allgather + allreduce); every phase is synchronous at return. */
+typedef struct dmmt_shard dmmt_shard;
+int dmmt_shard_create(dmmt_ctx *, uint16_t full_width, uint16_t full_height, dmmt_fmt fmt,
+                      uint16_t max_value, const dmmt_options *, int mcu_row_begin, int mcu_row_end,
+                      dmmt_shard **out);
+void dmmt_shard_destroy(dmmt_shard *);
+int dmmt_shard_mcu_rows_total(uint16_t full_height, const dmmt_options *);
+size_t dmmt_shard_pixel_bytes(const dmmt_shard *);       /* bytes of this shard's pixel rows */
+size_t dmmt_shard_pixel_offset(const dmmt_shard *);      /* byte offset of those rows in the full image */
+/* phase 1: K1 on the shard's rows (device pointer). last_dc = quantised DC of the shard's last Y, Cb, Cr block. */
+int dmmt_shard_transform(dmmt_shard *, const void *d_pixels, int16_t last_dc[3]);
+/* phase 2: K2 with the previous shard's last DCs as predictors; hist = 4*256 u64 local counts. */
+int dmmt_shard_histogram(dmmt_shard *, const int16_t seed_dc[3], uint64_t hist[1024]);
+/* phase 3: K2b from the GLOBAL (all-reduced) histogram; returns this shard's entropy-coded bits. */
+int dmmt_shard_tables(dmmt_shard *, const uint64_t global_hist[1024], uint64_t *local_bits);
+/* phase 4: K3 at the shard's global bit offset. is_last: append the 1-padding.
+ * tail_bits/tail_nbits: the trailing partial byte of this shard (bits beyond the last whole
+ * byte boundary of the global stream), which the next shard must OR into its first byte. */
+int dmmt_shard_pack(dmmt_shard *, uint64_t global_bit_offset, int is_last, uint8_t *tail_byte,
+                    int *tail_nbits);
+/* phase 5: K4 on the bytes this shard owns (global bytes whose LAST bit lies in the shard),
+ * with the previous shard's tail byte OR-ed into the first one.  is_first: prepend the header;
+ * is_last: append EOI.  Result stays on the device: *d_bytes / *n_bytes. */
+int dmmt_shard_stuff(dmmt_shard *, uint8_t prev_tail_byte, int prev_tail_nbits, int is_first,
+                     int is_last, const uint8_t **d_bytes, uint64_t *n_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMMT_CUDA_H */
