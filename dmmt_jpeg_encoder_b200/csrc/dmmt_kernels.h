@@ -1,0 +1,74 @@
+// dmmt_kernels.h -- host launchers of the sm_100a kernels (k1_transform.cu, k2_entropy.cu),
+// called by the C-ABI layer (dmmt_api.cu).  Everything is asynchronous on the given stream.
+#pragma once
+
+#include "dmmt_common.cuh"
+
+namespace dmmt {
+
+// K1 (k1_transform.cu)
+cudaError_t launch_k1(const Geom& g, int fmt, float maxf, int check_max, const QuantF& qf,
+                      const void* d_pixels, size_t img_stride_bytes, int n_images, int16_t* d_coef,
+                      size_t coef_img_stride, float* d_dbg, ImgMeta* meta, cudaStream_t st);
+
+// K2 (k2_entropy.cu)
+cudaError_t launch_k2(const Geom& g, const int16_t* coef, size_t coef_img_stride, int n,
+                      unsigned int* hist, ImgMeta* meta, const int16_t* seed_dc, cudaStream_t st);
+
+struct K2bHostArgs {
+    const unsigned int* hist;         // [n][4][256] u32 local counts
+    const unsigned long long* ghist;  // optional [4][256] u64 global counts (sharded mode)
+    EncTables* enc;
+    LenTables* lens;
+    ImgMeta* meta;
+    uint8_t* out;
+    size_t out_stride;
+    unsigned long long scan_cap_bits;
+    int W, H, bits_per_channel;       // ORIGINAL size for SOF0
+    const uint8_t* qtab_luma;         // natural order
+    const uint8_t* qtab_chroma;
+    int write_header;
+};
+cudaError_t launch_k2b(const Geom& g, const K2bHostArgs& h, int n, cudaStream_t st);
+
+cudaError_t launch_zero_scan(uint32_t* scan, size_t stride_words, const ImgMeta* meta, int n,
+                             unsigned long long seed_bits, int blocks_per_image, cudaStream_t st);
+
+uint32_t k3_chunks(const Geom& g);
+uint32_t k4_max_chunks(size_t scan_cap_bytes);
+
+cudaError_t launch_k3(const Geom& g, const int16_t* coef, size_t coef_img_stride, int n,
+                      const EncTables* enc, ImgMeta* meta, unsigned long long* lb_state,
+                      unsigned int* ticket, uint32_t* scan, size_t scan_stride_words,
+                      const int16_t* seed_dc, unsigned long long seed_bits, int pad_ones,
+                      cudaStream_t st);
+
+struct K4HostArgs {
+    const uint8_t* scan;
+    size_t scan_stride_bytes;
+    ImgMeta* meta;
+    unsigned long long* lb_state;
+    unsigned int* ticket;
+    uint32_t max_chunks;
+    uint8_t* out;
+    size_t out_stride;
+    unsigned long long* out_lens;
+    unsigned long long first_byte;
+    long long n_bytes_override;
+    unsigned long long seed_bits;
+    int prepend_header, append_eoi;
+    uint8_t or_first_byte;
+};
+cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStream_t st);
+
+cudaError_t launch_last_dc(const Geom& g, const int16_t* coef, int16_t* d_out3, cudaStream_t st);
+
+// K5: packs the n files of an output arena ([n][out_stride]) back to back (16-byte aligned
+// starts) into `dense`; offsets[0..n) and offsets[n] (= end) are written on the device.  chained:
+// start at the value already stored in offsets[0] (end of the previous sub-batch).
+cudaError_t launch_k5_compact(const uint8_t* out, size_t out_stride, const unsigned long long* lens,
+                              int n, uint8_t* dense, unsigned long long dense_cap,
+                              unsigned long long* offsets, ImgMeta* meta, int chained,
+                              int* sticky_err, cudaStream_t st);
+
+}  // namespace dmmt

@@ -1,0 +1,358 @@
+// dmmt_shard.cu -- ONE image split by MCU rows over several devices / ranks (BASELINE config 5,
+// SURVEY 8e).  A shard owns MCU rows [begin, end): a contiguous range of the stream order of all
+// three components (block_fold_iterator.rs:125-148, block_entangler.rs:69-77), so K1 is local and
+// the entropy stage needs four tiny exchanges, which the caller performs with its own collective
+// (torch.distributed / NCCL all-gather + all-reduce in the one-process-per-GPU driver, plain host
+// code in dmmt_encode_sharded):
+//   1. last quantised DC of (Y, Cb, Cr) of every shard  -> predictor seeds (categorize.rs:157-161)
+//   2. sum of the 4 symbol histograms                   -> image-global tables (transformer.rs:201-217)
+//   3. entropy-coded bits of every shard                -> global bit offsets (binary_stream.rs:38-66)
+//   4. stuffed byte counts                              -> final byte offsets of the shard outputs
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "dmmt_internal.h"
+#include "dmmt_qtables.h"
+
+using namespace dmmt;
+
+struct dmmt_shard {
+    dmmt_plan* plan = nullptr;
+    int full_W = 0, full_H = 0;
+    int row_begin = 0, row_end = 0;  // MCU rows
+    int px_row_begin = 0, px_rows = 0;
+    unsigned long long local_bits = 0;
+    unsigned long long seed_bits = 0;
+    bool have_seed = false;
+    unsigned int* h_hist = nullptr;  // pinned [1024]
+};
+
+static int mcu_rows_of(int H, int subsampling) {
+    const int vr = subsampling == DMMT_P420 ? 2 : 1;
+    return (H + 8 * vr - 1) / (8 * vr);
+}
+
+extern "C" int dmmt_shard_mcu_rows_total(uint16_t full_height, const dmmt_options* opt) {
+    if (!opt || opt->subsampling > DMMT_P420 || full_height == 0) return DMMT_E_INVALID;
+    return mcu_rows_of(full_height, opt->subsampling);
+}
+
+extern "C" void dmmt_shard_destroy(dmmt_shard* s) {
+    if (!s) return;
+    if (s->plan) {
+        (void)cudaSetDevice(s->plan->ctx->device);
+        dmmt_plan_destroy(s->plan);
+    }
+    if (s->h_hist) (void)cudaFreeHost(s->h_hist);
+    delete s;
+}
+
+extern "C" int dmmt_shard_create(dmmt_ctx* ctx, uint16_t full_width, uint16_t full_height, dmmt_fmt fmt,
+                                 uint16_t max_value, const dmmt_options* opt, int mcu_row_begin, int mcu_row_end,
+                                 dmmt_shard** out) {
+    if (!ctx || !opt || !out || opt->subsampling > DMMT_P420 || full_width == 0 || full_height == 0)
+        return DMMT_E_INVALID;
+    *out = nullptr;
+    const int total = mcu_rows_of(full_height, opt->subsampling);
+    if (mcu_row_begin < 0 || mcu_row_end > total || mcu_row_begin >= mcu_row_end) return DMMT_E_INVALID;
+    const int vr = opt->subsampling == DMMT_P420 ? 2 : 1;
+    dmmt_shard* s = new (std::nothrow) dmmt_shard();
+    if (!s) return DMMT_E_NOMEM;
+    s->full_W = full_width, s->full_H = full_height;
+    s->row_begin = mcu_row_begin, s->row_end = mcu_row_end;
+    s->px_row_begin = mcu_row_begin * 8 * vr;
+    s->px_rows = std::min<int>(full_height, mcu_row_end * 8 * vr) - s->px_row_begin;  // >= 1
+    // the whole padded image must fit the reference's u16 model (padder.rs:6-7)
+    if (total * 8 * vr > 65535) {
+        delete s;
+        return DMMT_E_SIZE;
+    }
+    int rc = dmmt_plan_create_impl(ctx, full_width, s->px_rows, mcu_row_end - mcu_row_begin, full_width, full_height,
+                                   (int)fmt, fmt == DMMT_RGB_F32_NORM ? 1 : max_value, opt, 1, ctx->stream, false,
+                                   &s->plan);
+    if (rc == DMMT_OK && cudaHostAlloc(&s->h_hist, 1024 * sizeof(unsigned int), cudaHostAllocDefault) != cudaSuccess)
+        rc = DMMT_E_NOMEM;
+    if (rc != DMMT_OK) {
+        dmmt_shard_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return DMMT_OK;
+}
+
+extern "C" size_t dmmt_shard_pixel_bytes(const dmmt_shard* s) { return s ? s->plan->pixel_bytes : 0; }
+extern "C" size_t dmmt_shard_pixel_offset(const dmmt_shard* s) {
+    if (!s) return 0;
+    const size_t pb = s->plan->fmt == DMMT_RGB_U8 ? 3 : (s->plan->fmt == DMMT_RGB_U16 ? 6 : 12);
+    return (size_t)s->px_row_begin * s->full_W * pb;
+}
+
+// ---- phase 1 ---------------------------------------------------------------------------------
+static int shard_transform_launch(dmmt_shard* s, const void* d_pixels) {
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    DMMT_CUDA(cudaMemsetAsync(p->zero_region, 0, p->zero_bytes, p->stream));
+    const int check_max = (p->fmt == DMMT_RGB_U8 && p->max_value < 255) || (p->fmt == DMMT_RGB_U16 && p->max_value < 65535);
+    DMMT_CUDA(launch_k1(p->g, p->fmt, (float)p->max_value, check_max, p->qf, d_pixels, p->pixel_bytes, 1, p->coef,
+                        p->coef_stride, nullptr, p->meta, p->stream));
+    DMMT_CUDA(launch_last_dc(p->g, p->coef, p->d_last_dc, p->stream));
+    p->last_launches = 2;
+    p->last_n = 1;
+    return DMMT_OK;
+}
+static int shard_transform_collect(dmmt_shard* s, int16_t last_dc[3]) {
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    DMMT_CUDA(cudaMemcpyAsync(last_dc, p->d_last_dc, 3 * sizeof(int16_t), cudaMemcpyDeviceToHost, p->stream));
+    DMMT_CUDA(cudaStreamSynchronize(p->stream));
+    return DMMT_OK;
+}
+extern "C" int dmmt_shard_transform(dmmt_shard* s, const void* d_pixels, int16_t last_dc[3]) {
+    if (!s || !d_pixels || !last_dc) return DMMT_E_INVALID;
+    DMMT_TRY(shard_transform_launch(s, d_pixels));
+    return shard_transform_collect(s, last_dc);
+}
+
+// ---- phase 2 ---------------------------------------------------------------------------------
+static int shard_histogram_launch(dmmt_shard* s, const int16_t seed_dc[3]) {
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    DMMT_CUDA(cudaMemcpyAsync(p->d_seed_dc, seed_dc, 3 * sizeof(int16_t), cudaMemcpyHostToDevice, p->stream));
+    s->have_seed = true;
+    DMMT_CUDA(launch_k2(p->g, p->coef, p->coef_stride, 1, p->hist, p->meta, p->d_seed_dc, p->stream));
+    p->last_launches += 1;
+    DMMT_CUDA(cudaMemcpyAsync(s->h_hist, p->hist, 1024 * sizeof(unsigned int), cudaMemcpyDeviceToHost, p->stream));
+    return DMMT_OK;
+}
+static int shard_histogram_collect(dmmt_shard* s, uint64_t hist[1024]) {
+    DMMT_CUDA(cudaSetDevice(s->plan->ctx->device));
+    DMMT_CUDA(cudaStreamSynchronize(s->plan->stream));
+    for (int i = 0; i < 1024; i++) hist[i] = s->h_hist[i];
+    return DMMT_OK;
+}
+extern "C" int dmmt_shard_histogram(dmmt_shard* s, const int16_t seed_dc[3], uint64_t hist[1024]) {
+    if (!s || !seed_dc || !hist) return DMMT_E_INVALID;
+    DMMT_TRY(shard_histogram_launch(s, seed_dc));
+    return shard_histogram_collect(s, hist);
+}
+
+// ---- phase 3 ---------------------------------------------------------------------------------
+static int shard_tables_launch(dmmt_shard* s, const uint64_t global_hist[1024]) {
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    if (!p->d_out_own) DMMT_CUDA(cudaMalloc(&p->d_out_own, p->out_stride));
+    DMMT_CUDA(cudaMemcpyAsync(p->d_ghist, global_hist, 1024 * 8, cudaMemcpyHostToDevice, p->stream));
+    K2bHostArgs b{};
+    b.hist = p->hist, b.ghist = p->d_ghist, b.enc = p->enc, b.lens = p->lens, b.meta = p->meta;
+    b.out = p->d_out_own, b.out_stride = p->out_stride;
+    b.scan_cap_bits = (unsigned long long)p->scan_cap_bytes * 8 - 8;  // room for the seed bits
+    b.W = p->sof_W, b.H = p->sof_H, b.bits_per_channel = p->opt.bits_per_channel;
+    b.qtab_luma = kQuantPresets[p->opt.qtable_preset][0];
+    b.qtab_chroma = kQuantPresets[p->opt.qtable_preset][1];
+    b.write_header = 1;  // every shard writes the (identical) header into its arena; only the first one ships it
+    DMMT_CUDA(launch_k2b(p->g, b, 1, p->stream));
+    p->last_launches += 2;
+    return DMMT_OK;
+}
+static int shard_tables_collect(dmmt_shard* s, uint64_t* local_bits) {
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    ImgMeta m{};
+    DMMT_CUDA(cudaMemcpyAsync(&m, p->meta, sizeof m, cudaMemcpyDeviceToHost, p->stream));
+    DMMT_CUDA(cudaStreamSynchronize(p->stream));
+    if (m.error) return m.error;
+    s->local_bits = m.scan_bits;
+    *local_bits = m.scan_bits;
+    return DMMT_OK;
+}
+extern "C" int dmmt_shard_tables(dmmt_shard* s, const uint64_t global_hist[1024], uint64_t* local_bits) {
+    if (!s || !global_hist || !local_bits) return DMMT_E_INVALID;
+    DMMT_TRY(shard_tables_launch(s, global_hist));
+    return shard_tables_collect(s, local_bits);
+}
+
+// ---- phase 4 ---------------------------------------------------------------------------------
+static int shard_pack_launch(dmmt_shard* s, uint64_t global_bit_offset, int is_last) {
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    s->seed_bits = global_bit_offset & 7;  // the shard's buffer starts at the byte holding its first bit
+    const int zero_blocks = (int)std::min<size_t>(std::max<size_t>(p->scan_cap_bytes / 65536, 1), 1024);
+    DMMT_CUDA(launch_zero_scan(p->scan, p->scan_stride_words, p->meta, 1, s->seed_bits, zero_blocks, p->stream));
+    DMMT_CUDA(launch_k3(p->g, p->coef, p->coef_stride, 1, p->enc, p->meta, p->lb3, p->tk3, p->scan,
+                        p->scan_stride_words, s->have_seed ? p->d_seed_dc : nullptr, s->seed_bits, is_last ? 1 : 0,
+                        p->stream));
+    p->last_launches += 2;
+    return DMMT_OK;
+}
+static int shard_pack_collect(dmmt_shard* s, int is_last, uint8_t* tail_byte, int* tail_nbits) {
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    const unsigned long long end = s->seed_bits + s->local_bits;
+    *tail_byte = 0;
+    *tail_nbits = is_last ? 0 : (int)(end & 7);
+    if (*tail_nbits)
+        DMMT_CUDA(cudaMemcpyAsync(tail_byte, reinterpret_cast<const uint8_t*>(p->scan) + end / 8, 1,
+                                  cudaMemcpyDeviceToHost, p->stream));
+    DMMT_CUDA(cudaStreamSynchronize(p->stream));
+    return DMMT_OK;
+}
+extern "C" int dmmt_shard_pack(dmmt_shard* s, uint64_t global_bit_offset, int is_last, uint8_t* tail_byte,
+                               int* tail_nbits) {
+    if (!s || !tail_byte || !tail_nbits) return DMMT_E_INVALID;
+    DMMT_TRY(shard_pack_launch(s, global_bit_offset, is_last));
+    return shard_pack_collect(s, is_last, tail_byte, tail_nbits);
+}
+
+// ---- phase 5 ---------------------------------------------------------------------------------
+// Owned bytes: local bytes [0, floor(end / 8)) -- plus the padded last byte on the last shard.
+// Local byte 0 also carries the previous shard's tail bits (OR-ed in here).
+static int shard_stuff_launch(dmmt_shard* s, uint8_t prev_tail_byte, int is_first, int is_last) {
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    const unsigned long long end = s->seed_bits + s->local_bits;
+    const unsigned long long owned = is_last ? (end + 7) / 8 : end / 8;
+    K4HostArgs k{};
+    k.scan = reinterpret_cast<const uint8_t*>(p->scan), k.scan_stride_bytes = p->scan_stride_words * 4;
+    k.meta = p->meta, k.lb_state = p->lb4, k.ticket = p->tk4, k.max_chunks = p->max_chunks4;
+    k.out = p->d_out_own, k.out_stride = p->out_stride, k.out_lens = p->d_lens;
+    k.first_byte = 0, k.n_bytes_override = (long long)owned, k.seed_bits = s->seed_bits;
+    k.prepend_header = is_first, k.append_eoi = is_last;
+    k.or_first_byte = prev_tail_byte;
+    const uint32_t grid = std::max<uint32_t>(1, k4_max_chunks((size_t)owned));
+    DMMT_CUDA(launch_k4(k, 1, grid, p->stream));
+    p->last_launches += 1;
+    DMMT_CUDA(cudaMemcpyAsync(p->h_lens, p->d_lens, 8, cudaMemcpyDeviceToHost, p->stream));
+    return DMMT_OK;
+}
+static int shard_stuff_collect(dmmt_shard* s, const uint8_t** d_bytes, uint64_t* n_bytes) {
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    ImgMeta m{};
+    DMMT_CUDA(cudaMemcpyAsync(&m, p->meta, sizeof m, cudaMemcpyDeviceToHost, p->stream));
+    DMMT_CUDA(cudaStreamSynchronize(p->stream));
+    if (m.error) return m.error;
+    *d_bytes = p->d_out_own;
+    *n_bytes = p->h_lens[0];
+    return DMMT_OK;
+}
+extern "C" int dmmt_shard_stuff(dmmt_shard* s, uint8_t prev_tail_byte, int prev_tail_nbits, int is_first,
+                                int is_last, const uint8_t** d_bytes, uint64_t* n_bytes) {
+    if (!s || !d_bytes || !n_bytes) return DMMT_E_INVALID;
+    if ((unsigned long long)(prev_tail_nbits & 7) != s->seed_bits) return DMMT_E_INVALID;  // exchange out of step
+    DMMT_TRY(shard_stuff_launch(s, prev_tail_byte, is_first, is_last));
+    return shard_stuff_collect(s, d_bytes, n_bytes);
+}
+
+extern "C" int dmmt_shard_launch_count(const dmmt_shard* s) { return s ? s->plan->last_launches : 0; }
+
+// ---- single-process driver: shards on the given contexts (devices may repeat) ------------------
+extern "C" int dmmt_encode_sharded(dmmt_ctx* const* ctxs, int nctx, const dmmt_image* im, const dmmt_options* o,
+                                   uint8_t** jpeg, size_t* len) {
+    if (!ctxs || nctx <= 0 || !im || !o || !jpeg || !len || !im->pixels || o->subsampling > DMMT_P420)
+        return DMMT_E_INVALID;
+    *jpeg = nullptr, *len = 0;
+    if (im->width == 0 || im->height == 0) return DMMT_E_INVALID;
+    if (im->pixels_on_device) return DMMT_E_INVALID;  // the shards live on different devices: host pixels only
+    const int rows = mcu_rows_of(im->height, o->subsampling);
+    const int ns = std::min(nctx, rows);
+    std::vector<dmmt_shard*> sh((size_t)ns, nullptr);
+    std::vector<uint8_t*> d_px((size_t)ns, nullptr);
+    int rc = DMMT_OK;
+    auto cleanup = [&]() {
+        for (int i = 0; i < ns; i++) {
+            if (d_px[i]) {
+                (void)cudaSetDevice(ctxs[i]->device);
+                (void)cudaFree(d_px[i]);
+            }
+            dmmt_shard_destroy(sh[i]);
+        }
+    };
+#define SH_TRY(expr)            \
+    do {                        \
+        rc = (expr);            \
+        if (rc != DMMT_OK) {    \
+            cleanup();          \
+            return rc;          \
+        }                       \
+    } while (0)
+#define SH_CUDA(expr)                                            \
+    do {                                                         \
+        cudaError_t e__ = (expr);                                \
+        if (e__ != cudaSuccess) {                                \
+            dmmt_set_cuda_error(e__, #expr, __FILE__, __LINE__); \
+            cleanup();                                           \
+            return DMMT_E_CUDA;                                  \
+        }                                                        \
+    } while (0)
+    // MCU rows [r*rows/ns, (r+1)*rows/ns)
+    for (int r = 0; r < ns; r++) {
+        const int b = (int)((long long)r * rows / ns), e = (int)((long long)(r + 1) * rows / ns);
+        SH_TRY(dmmt_shard_create(ctxs[r], im->width, im->height, im->fmt, im->max_value, o, b, e, &sh[r]));
+        SH_CUDA(cudaSetDevice(ctxs[r]->device));
+        SH_CUDA(cudaMalloc(&d_px[r], dmmt_shard_pixel_bytes(sh[r])));
+        SH_CUDA(cudaMemcpyAsync(d_px[r], static_cast<const uint8_t*>(im->pixels) + dmmt_shard_pixel_offset(sh[r]),
+                                dmmt_shard_pixel_bytes(sh[r]), cudaMemcpyHostToDevice, ctxs[r]->stream));
+    }
+    // phase 1 on all shards, then exchange 1 (last DCs)
+    std::vector<int16_t> last_dc((size_t)ns * 3), seed((size_t)ns * 3, 0);
+    for (int r = 0; r < ns; r++) SH_TRY(shard_transform_launch(sh[r], d_px[r]));
+    for (int r = 0; r < ns; r++) SH_TRY(shard_transform_collect(sh[r], &last_dc[3 * r]));
+    for (int r = 1; r < ns; r++)
+        for (int c = 0; c < 3; c++) seed[3 * r + c] = last_dc[3 * (r - 1) + c];
+    // phase 2, exchange 2 (histogram sum)
+    std::vector<uint64_t> h((size_t)1024), g((size_t)1024, 0);
+    for (int r = 0; r < ns; r++) SH_TRY(shard_histogram_launch(sh[r], &seed[3 * r]));
+    for (int r = 0; r < ns; r++) {
+        SH_TRY(shard_histogram_collect(sh[r], h.data()));
+        for (int i = 0; i < 1024; i++) g[i] += h[i];
+    }
+    // phase 3, exchange 3 (bit counts -> global bit offsets)
+    std::vector<uint64_t> bits((size_t)ns), bit_off((size_t)ns + 1, 0);
+    for (int r = 0; r < ns; r++) SH_TRY(shard_tables_launch(sh[r], g.data()));
+    for (int r = 0; r < ns; r++) SH_TRY(shard_tables_collect(sh[r], &bits[r]));
+    for (int r = 0; r < ns; r++) bit_off[r + 1] = bit_off[r] + bits[r];
+    // phase 4 (+ tails)
+    std::vector<uint8_t> tail((size_t)ns, 0);
+    std::vector<int> tail_n((size_t)ns, 0);
+    for (int r = 0; r < ns; r++) SH_TRY(shard_pack_launch(sh[r], bit_off[r], r == ns - 1));
+    for (int r = 0; r < ns; r++) SH_TRY(shard_pack_collect(sh[r], r == ns - 1, &tail[r], &tail_n[r]));
+    // a shard that does not complete a byte hands its predecessor's bits on
+    for (int r = 1; r < ns; r++)
+        if (r < ns - 1 && (bit_off[r] & 7) + bits[r] < 8) tail[r] |= tail[r - 1];
+    // phase 5, exchange 4 (byte counts)
+    std::vector<const uint8_t*> d_bytes((size_t)ns, nullptr);
+    std::vector<uint64_t> n_bytes((size_t)ns, 0);
+    for (int r = 0; r < ns; r++) SH_TRY(shard_stuff_launch(sh[r], r ? tail[r - 1] : 0, r == 0, r == ns - 1));
+    for (int r = 0; r < ns; r++) SH_TRY(shard_stuff_collect(sh[r], &d_bytes[r], &n_bytes[r]));
+    uint64_t total = 0;
+    for (int r = 0; r < ns; r++) total += n_bytes[r];
+    uint8_t* buf = static_cast<uint8_t*>(malloc(total ? total : 1));
+    if (!buf) {
+        cleanup();
+        return DMMT_E_NOMEM;
+    }
+    uint64_t at = 0;
+    for (int r = 0; r < ns; r++) {
+        cudaError_t e = cudaSetDevice(ctxs[r]->device);
+        if (e == cudaSuccess && n_bytes[r])
+            e = cudaMemcpyAsync(buf + at, d_bytes[r], n_bytes[r], cudaMemcpyDeviceToHost, ctxs[r]->stream);
+        if (e != cudaSuccess) {
+            dmmt_set_cuda_error(e, "gather of the shard outputs", __FILE__, __LINE__);
+            free(buf);
+            cleanup();
+            return DMMT_E_CUDA;
+        }
+        at += n_bytes[r];
+    }
+    for (int r = 0; r < ns; r++) {
+        (void)cudaSetDevice(ctxs[r]->device);
+        (void)cudaStreamSynchronize(ctxs[r]->stream);
+    }
+    cleanup();
+    *jpeg = buf, *len = (size_t)total;
+    return DMMT_OK;
+#undef SH_TRY
+#undef SH_CUDA
+}

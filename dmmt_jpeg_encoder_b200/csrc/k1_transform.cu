@@ -22,7 +22,7 @@
 //            the Arai flow graph without any transpose, IEEE division by the quantiser, round half
 //            away from zero, zig-zag by register renaming, 8 x 16-byte stores of the block.
 // Output: int16 [n_mcus][blocks_per_mcu][64] in MCU-interleaved STREAM order, zig-zag inside a block.
-#include "dmmt_common.cuh"
+#include "dmmt_kernels.h"
 
 namespace dmmt {
 
@@ -128,7 +128,7 @@ struct Px<DMMT_RGB_F32_NORM> {
 template <int FMT>
 __device__ __forceinline__ void load_strip_row(const uint8_t* __restrict__ row_base, int x0, int W,
                                                bool row_valid, bool vec_ok, float maxf,
-                                               float (&n)[48]) {
+                                               float (&n)[48], bool check_max, bool& bad) {
     constexpr int PB = Px<FMT>::kBytes;
     if (!row_valid) {
 #pragma unroll
@@ -165,8 +165,7 @@ __device__ __forceinline__ void load_strip_row(const uint8_t* __restrict__ row_b
                 n[4 * i + 2] = __uint_as_float(v.z), n[4 * i + 3] = __uint_as_float(v.w);
             }
         }
-        return;
-    }
+    } else {
     // ragged edge / unaligned pitch: scalar, bounds-checked
 #pragma unroll
     for (int px = 0; px < 16; px++) {
@@ -186,6 +185,14 @@ __device__ __forceinline__ void load_strip_row(const uint8_t* __restrict__ row_b
             n[3 * px + c] = v;
         }
     }
+    }
+    if constexpr (FMT != DMMT_RGB_F32_NORM) {
+        // color.rs:62-65: a component above max panics in the reference.  v > max <=> v/max > 1.
+        if (check_max) {
+#pragma unroll
+            for (int i = 0; i < 48; i++) bad |= n[i] > 1.0f;
+        }
+    }
 }
 
 struct K1Args {
@@ -198,6 +205,8 @@ struct K1Args {
     int16_t* coef;               // [n][n_blocks][64]
     size_t coef_img_stride;      // elements between images
     float* dbg;                  // optional pre-quant coefficients [n_blocks][64] natural order (image 0 of launch)
+    int check_max;               // samples may exceed max_value: flag DMMT_E_INVALID (color.rs:62-65)
+    ImgMeta* meta;               // [n] error flags
     QuantF qf;
 };
 
@@ -223,6 +232,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_transform(const __grid_constant
     {
         const int sx = threadIdx.x & 15, sy = threadIdx.x >> 4;  // sy in [0,8)
         const int x0 = tile_x * TILE_W + sx * 16;
+        bool bad = false;
         float cbs[16], crs[16];  // running chroma window sums (x outer, y inner: subsampling.rs:108-122)
 #pragma unroll
         for (int r = 0; r < VR; r++) {
@@ -230,7 +240,8 @@ __global__ void __launch_bounds__(K1_THREADS) k1_transform(const __grid_constant
             const int y = mrow * ROWS + yl;
             const bool row_valid = (y < a.H) && (x0 < a.W);
             float n[48];
-            load_strip_row<FMT>(pix + (size_t)y * pitch, x0, a.W, row_valid, a.vec_ok != 0, a.maxf, n);
+            load_strip_row<FMT>(pix + (size_t)y * pitch, x0, a.W, row_valid, a.vec_ok != 0, a.maxf, n,
+                                a.check_max != 0, bad);
             float yv[16], cb[16], cr[16];
 #pragma unroll
             for (int p = 0; p < 16; p++) rgb_to_ycbcr(n[3 * p], n[3 * p + 1], n[3 * p + 2], yv[p], cb[p], cr[p]);
@@ -288,6 +299,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_transform(const __grid_constant
                 sCr[sy][c][sx] = make_float4(crs[4 * c], crs[4 * c + 1], crs[4 * c + 2], crs[4 * c + 3]);
             }
         }
+        if (bad) atomicCAS(&a.meta[img].error, 0, DMMT_E_INVALID);
     }
     __syncthreads();
 
@@ -393,9 +405,9 @@ cudaError_t launch_sub(const K1Args& a, dim3 grid, int fmt, bool dbg, cudaStream
 
 // Host launcher.  n_images equally sized images; dbg != nullptr selects the variant that also
 // writes the pre-quantisation coefficients of image 0.
-cudaError_t launch_k1(const Geom& g, int fmt, float maxf, const QuantF& qf, const void* d_pixels,
-                      size_t img_stride_bytes, int n_images, int16_t* d_coef,
-                      size_t coef_img_stride, float* d_dbg, cudaStream_t st) {
+cudaError_t launch_k1(const Geom& g, int fmt, float maxf, int check_max, const QuantF& qf,
+                      const void* d_pixels, size_t img_stride_bytes, int n_images, int16_t* d_coef,
+                      size_t coef_img_stride, float* d_dbg, ImgMeta* meta, cudaStream_t st) {
     K1Args a;
     a.pixels = static_cast<const uint8_t*>(d_pixels);
     a.img_stride_bytes = img_stride_bytes;
@@ -409,6 +421,8 @@ cudaError_t launch_k1(const Geom& g, int fmt, float maxf, const QuantF& qf, cons
     a.coef = d_coef;
     a.coef_img_stride = coef_img_stride;
     a.dbg = d_dbg;
+    a.check_max = check_max;
+    a.meta = meta;
     a.qf = qf;
     const int pw = g.mcus_x * 8 * g.hr;
     dim3 grid((pw + TILE_W - 1) / TILE_W, g.mcus_y, n_images);

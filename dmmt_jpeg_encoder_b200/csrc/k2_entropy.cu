@@ -12,7 +12,7 @@
 // XOR swizzle (chunk c of block b at slot c ^ (b & 7)), so the coalesced global loads AND the
 // thread-per-block 128-bit shared loads are both conflict-free; each thread then walks only the
 // NON-ZERO coefficients of its block (64-bit occupancy mask + ffs).
-#include "dmmt_common.cuh"
+#include "dmmt_kernels.h"
 
 namespace dmmt {
 
@@ -680,6 +680,16 @@ __global__ void __launch_bounds__(K4_THREADS) k4_stuff(const K4Args a) {
         s_prefix = lookback_exclusive(a.lb_state + (size_t)img * a.max_chunks, (int)chunk, chunk_ff);
     __syncthreads();
     unsigned long long o = hdr + base + s_prefix + ff_before;
+    if (o + (unsigned long long)nvalid + nff + 2ull > a.out_stride) {
+        // Error::FailedToWriteImageData: the image's slot of the output arena is too small.
+        // Offsets are monotonic, so the owner of the last byte sees the overflow as well.
+        if (nvalid > 0) atomicCAS(&meta->error, 0, DMMT_E_WRITE);
+        if (chunk == n_chunks - 1 && nvalid > 0 && base + nvalid == total_bytes) {
+            meta->out_len = 0ull;
+            if (a.out_lens) a.out_lens[img] = 0ull;
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
 #pragma unroll
@@ -710,6 +720,83 @@ __global__ void k_last_dc(const int16_t* coef, uint32_t n_blocks, int ypm, int b
     }
 }
 
+// =========================================== K5 ===========================================
+// Packs the files of the strided output arena back to back (16-byte aligned starts) so that the
+// host needs ONE device-to-host copy per batch.  k5_offsets: one CTA, exclusive scan of the
+// aligned lengths; k5_copy: 128-bit copies.
+__global__ void __launch_bounds__(1024) k5_offsets(unsigned long long* lens, int n,
+                                                   unsigned long long dense_cap,
+                                                   unsigned long long* offsets, ImgMeta* meta,
+                                                   int chained, int* sticky_err) {
+    __shared__ unsigned long long s_w[33];
+    __shared__ unsigned long long s_run;
+    // chained: offsets[0] already holds the end of the previous sub-batch (or 0)
+    if (threadIdx.x == 0) s_run = chained ? offsets[0] : 0ull;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        unsigned long long len = 0ull;
+        if (i < n) {
+            const int err = meta[i].error;
+            if (err == 0) len = lens[i];
+            else {
+                lens[i] = 0ull;
+                if (sticky_err) atomicCAS(sticky_err, 0, err);  // survives the reuse of this slot's meta
+            }
+        }
+        const unsigned long long al = (len + 15ull) & ~15ull;
+        unsigned long long inc = al;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned long long w = s_w[lane];
+            unsigned long long winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= d) winc += t;
+            }
+            s_w[lane] = winc - w;
+            if (lane == 31) s_w[32] = winc;
+        }
+        __syncthreads();
+        const unsigned long long off = s_run + s_w[wid] + inc - al;
+        if (i < n) {
+            if (off + al > dense_cap) {  // dense arena too small: Error::FailedToWriteImageData
+                if (len) {
+                    atomicCAS(&meta[i].error, 0, DMMT_E_WRITE);
+                    if (sticky_err) atomicCAS(sticky_err, 0, DMMT_E_WRITE);
+                }
+                lens[i] = 0ull;
+            }
+            offsets[i] = off;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += s_w[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n] = s_run;
+}
+
+__global__ void __launch_bounds__(256) k5_copy(const uint8_t* __restrict__ out, size_t out_stride,
+                                               const unsigned long long* __restrict__ lens,
+                                               const unsigned long long* __restrict__ offsets,
+                                               uint8_t* __restrict__ dense) {
+    const int img = blockIdx.y;
+    const unsigned long long nq = (lens[img] + 15ull) >> 4;
+    const uint4* src = reinterpret_cast<const uint4*>(out + (size_t)img * out_stride);
+    uint4* dst = reinterpret_cast<uint4*>(dense + offsets[img]);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nq;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -721,21 +808,6 @@ cudaError_t launch_k2(const Geom& g, const int16_t* coef, size_t coef_img_stride
     k2_histogram<<<grid, EB, 0, st>>>(a);
     return cudaGetLastError();
 }
-
-struct K2bHostArgs {
-    const unsigned int* hist;
-    const unsigned long long* ghist;
-    EncTables* enc;
-    LenTables* lens;
-    ImgMeta* meta;
-    uint8_t* out;
-    size_t out_stride;
-    unsigned long long scan_cap_bits;
-    int W, H, bits_per_channel;
-    const uint8_t* qtab_luma;    // natural order
-    const uint8_t* qtab_chroma;
-    int write_header;
-};
 
 cudaError_t launch_k2b(const Geom& g, const K2bHostArgs& h, int n, cudaStream_t st) {
     K2bArgs a;
@@ -784,23 +856,6 @@ cudaError_t launch_k3(const Geom& g, const int16_t* coef, size_t coef_img_stride
     return cudaGetLastError();
 }
 
-struct K4HostArgs {
-    const uint8_t* scan;
-    size_t scan_stride_bytes;
-    ImgMeta* meta;
-    unsigned long long* lb_state;
-    unsigned int* ticket;
-    uint32_t max_chunks;
-    uint8_t* out;
-    size_t out_stride;
-    unsigned long long* out_lens;
-    unsigned long long first_byte;
-    long long n_bytes_override;
-    unsigned long long seed_bits;
-    int prepend_header, append_eoi;
-    uint8_t or_first_byte;
-};
-
 cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStream_t st) {
     K4Args a{h.scan, h.scan_stride_bytes, h.meta, h.lb_state, h.ticket, h.max_chunks, h.out, h.out_stride,
              h.out_lens, h.first_byte, h.n_bytes_override, h.seed_bits, h.prepend_header, h.append_eoi,
@@ -812,6 +867,18 @@ cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStre
 
 cudaError_t launch_last_dc(const Geom& g, const int16_t* coef, int16_t* d_out3, cudaStream_t st) {
     k_last_dc<<<1, 32, 0, st>>>(coef, g.n_blocks, g.ypm, g.bpm, d_out3);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k5_compact(const uint8_t* out, size_t out_stride, const unsigned long long* lens,
+                              int n, uint8_t* dense, unsigned long long dense_cap,
+                              unsigned long long* offsets, ImgMeta* meta, int chained,
+                              int* sticky_err, cudaStream_t st) {
+    k5_offsets<<<1, 1024, 0, st>>>(const_cast<unsigned long long*>(lens), n, dense_cap, offsets, meta,
+                                   chained, sticky_err);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k5_copy<<<dim3(8, n), 256, 0, st>>>(out, out_stride, lens, offsets, dense);
     return cudaGetLastError();
 }
 

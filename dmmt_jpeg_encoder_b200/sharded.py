@@ -1,0 +1,182 @@
+"""One image, MCU-row shards, one process per GPU (BASELINE config 5).
+
+Rank r owns MCU rows [r*M/N, (r+1)*M/N).  The kernels run through the dmmt_shard_* C ABI; the four
+small exchanges run over torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests):
+
+  1. all_gather of the last quantised DC of (Y, Cb, Cr)     -> DC predictor seeds
+  2. all_reduce(sum) of the 4 symbol histograms (1024 x i64) -> image-global Huffman tables
+  3. all_gather of the entropy-coded bit counts + tail bits  -> global bit offsets
+  4. all_gather of the stuffed byte counts                   -> byte offsets; send/recv to rank 0
+
+`ShardBackend` is the seam: `CudaShardBackend` is the product; the CPU tests plug in a simulator so
+the exchange arithmetic is covered without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _ffi as F
+from .encoder import Context, Options
+
+
+def shard_rows(total_mcu_rows: int, world: int, rank: int) -> tuple[int, int]:
+    return rank * total_mcu_rows // world, (rank + 1) * total_mcu_rows // world
+
+
+def mcu_rows_total(height: int, options: Options) -> int:
+    vr = 2 if options.subsampling == F.P420 else 1
+    return (height + 8 * vr - 1) // (8 * vr)
+
+
+def pixel_row_range(height: int, options: Options, row_begin: int, row_end: int) -> tuple[int, int]:
+    vr = 2 if options.subsampling == F.P420 else 1
+    return row_begin * 8 * vr, min(height, row_end * 8 * vr)
+
+
+class ShardBackend:
+    """The five local phases of one shard."""
+
+    def transform(self) -> np.ndarray: ...                                   # -> last_dc i16[3]
+    def histogram(self, seed_dc: np.ndarray) -> np.ndarray: ...              # -> u64[1024]
+    def tables(self, global_hist: np.ndarray) -> int: ...                    # -> local bits
+    def pack(self, global_bit_offset: int, is_last: bool) -> tuple[int, int]: ...  # -> tail byte, nbits
+    def stuff(self, prev_tail: int, prev_nbits: int, is_first: bool, is_last: bool) -> torch.Tensor: ...
+
+
+class _DevPtr:
+    """Zero-copy view of device memory owned by the C library as a torch tensor."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+class CudaShardBackend(ShardBackend):
+    def __init__(self, ctx: Context, d_pixels: int, full_width: int, full_height: int, fmt: int, max_value: int,
+                 options: Options, row_begin: int, row_end: int):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        o = options.c()
+        F.check(F.lib().dmmt_shard_create(ctx.handle, full_width, full_height, fmt, max_value, C.byref(o),
+                                          row_begin, row_end, C.byref(self._h)), "dmmt_shard_create")
+        self.d_pixels = d_pixels
+
+    @property
+    def pixel_bytes(self) -> int:
+        return F.lib().dmmt_shard_pixel_bytes(self._h)
+
+    @property
+    def pixel_offset(self) -> int:
+        return F.lib().dmmt_shard_pixel_offset(self._h)
+
+    def launch_count(self) -> int:
+        return F.lib().dmmt_shard_launch_count(self._h)
+
+    def transform(self):
+        out = (C.c_int16 * 3)()
+        F.check(F.lib().dmmt_shard_transform(self._h, C.c_void_p(self.d_pixels), out), "dmmt_shard_transform")
+        return np.array(out[:], np.int16)
+
+    def histogram(self, seed_dc):
+        seed = (C.c_int16 * 3)(*[int(v) for v in seed_dc])
+        h = np.zeros(1024, np.uint64)
+        F.check(F.lib().dmmt_shard_histogram(self._h, seed, h.ctypes.data_as(F._U64P)), "dmmt_shard_histogram")
+        return h
+
+    def tables(self, global_hist):
+        g = np.ascontiguousarray(global_hist, np.uint64)
+        bits = C.c_uint64()
+        F.check(F.lib().dmmt_shard_tables(self._h, g.ctypes.data_as(F._U64P), C.byref(bits)), "dmmt_shard_tables")
+        return bits.value
+
+    def pack(self, global_bit_offset, is_last):
+        tb, tn = C.c_uint8(), C.c_int()
+        F.check(F.lib().dmmt_shard_pack(self._h, global_bit_offset, int(is_last), C.byref(tb), C.byref(tn)),
+                "dmmt_shard_pack")
+        return tb.value, tn.value
+
+    def stuff(self, prev_tail, prev_nbits, is_first, is_last):
+        p, n = C.c_void_p(), C.c_uint64()
+        F.check(F.lib().dmmt_shard_stuff(self._h, prev_tail, prev_nbits, int(is_first), int(is_last),
+                                         C.byref(p), C.byref(n)), "dmmt_shard_stuff")
+        if n.value == 0:
+            return torch.empty(0, dtype=torch.uint8, device=f"cuda:{self.ctx.device}")
+        return torch.as_tensor(_DevPtr(p.value, n.value), device=f"cuda:{self.ctx.device}")
+
+    def close(self):
+        if self._h:
+            F.lib().dmmt_shard_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def encode_sharded(backend: ShardBackend, device: torch.device, group=None, dst: int = 0,
+                   timings: dict | None = None) -> bytes | None:
+    """Runs the phases of this rank's shard with the four exchanges; returns the file on `dst`."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    is_first, is_last = rank == 0, rank == world - 1
+
+    # phase 1 + exchange 1: DC predictor seeds (categorize.rs:157-161 never resets the chain)
+    last_dc = torch.from_numpy(backend.transform().astype(np.int64)).to(device)
+    all_dc = [torch.empty_like(last_dc) for _ in range(world)]
+    dist.all_gather(all_dc, last_dc, group=group)
+    seed = all_dc[rank - 1].cpu().numpy().astype(np.int16) if rank else np.zeros(3, np.int16)
+
+    # phase 2 + exchange 2: image-global histograms (transformer.rs:201-217)
+    hist = torch.from_numpy(backend.histogram(seed).astype(np.int64)).to(device)
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+
+    # phase 3 + exchange 3: bit offsets
+    bits = backend.tables(hist.cpu().numpy().astype(np.uint64))
+    t = torch.tensor([bits], dtype=torch.int64, device=device)
+    all_bits = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(all_bits, t, group=group)
+    all_bits = [int(x.item()) for x in all_bits]
+    bit_off = [0]
+    for b in all_bits:
+        bit_off.append(bit_off[-1] + b)
+
+    # phase 4 + exchange of the trailing partial bytes
+    tail_byte, tail_nbits = backend.pack(bit_off[rank], is_last)
+    t = torch.tensor([tail_byte, tail_nbits], dtype=torch.int64, device=device)
+    all_tail = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(all_tail, t, group=group)
+    tails = [int(x[0].item()) for x in all_tail]
+    # a shard that does not complete a byte hands its predecessor's bits on
+    for r in range(1, world - 1):
+        if (bit_off[r] & 7) + all_bits[r] < 8:
+            tails[r] |= tails[r - 1]
+    prev_tail = tails[rank - 1] if rank else 0
+    prev_nbits = bit_off[rank] & 7
+
+    # phase 5 + exchange 4: byte counts, then the bytes travel to dst
+    mine = backend.stuff(prev_tail, prev_nbits, is_first, is_last)
+    t = torch.tensor([mine.numel()], dtype=torch.int64, device=device)
+    all_n = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(all_n, t, group=group)
+    all_n = [int(x.item()) for x in all_n]
+    if timings is not None:
+        timings["bytes"] = all_n
+        timings["bits"] = all_bits
+    if rank == dst:
+        out = torch.empty(sum(all_n), dtype=torch.uint8, device=device)
+        off = 0
+        for r in range(world):
+            if all_n[r]:
+                if r == rank:
+                    out[off:off + all_n[r]].copy_(mine)
+                else:
+                    dist.recv(out[off:off + all_n[r]], src=r, group=group)
+            off += all_n[r]
+        return out.cpu().numpy().tobytes()
+    if mine.numel():
+        dist.send(mine.contiguous(), dst=dst, group=group)
+    return None

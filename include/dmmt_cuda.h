@@ -98,7 +98,7 @@ void dmmt_free(void *);
 const char *dmmt_strerror(int code);
 const char *dmmt_last_cuda_error(void); /* thread-local text of the last CUDA failure */
 
-/* ---- plans: device-resident batched encode (what bench.py times) ------------------------- */
+/* ---- plans: fixed geometry, device-resident launch chain over up to n_images images ------- */
 int dmmt_plan_create(dmmt_ctx *, uint16_t width, uint16_t height, dmmt_fmt fmt, uint16_t max_value,
                      const dmmt_options *, int n_images, dmmt_plan **out);
 void dmmt_plan_destroy(dmmt_plan *);
@@ -108,15 +108,51 @@ size_t dmmt_plan_out_stride(const dmmt_plan *);   /* bytes reserved per image in
  * dmmt_plan_worst_case_scan_bytes().  Reallocates scratch. */
 int dmmt_plan_set_scan_capacity(dmmt_plan *, size_t bytes_per_image);
 size_t dmmt_plan_worst_case_scan_bytes(const dmmt_plan *);
-/* Asynchronous on the context's stream.  d_pixels: n images back to back in device memory;
- * d_out: n * out_stride bytes; d_lens: n u64 (file length per image; 0 + error flag on failure).
- * Use dmmt_plan_status after synchronising to read the device-side error flags. */
-int dmmt_plan_encode_device(dmmt_plan *, const void *d_pixels, uint8_t *d_out, uint64_t *d_lens);
+/* Asynchronous on the plan's stream.  d_pixels: n_images (<= plan size) images back to back in
+ * device memory; d_out: n_images * out_stride bytes; d_lens: n_images u64 (file length per
+ * image; 0 + error flag on failure).  Use dmmt_plan_status after synchronising to read the
+ * device-side error flags. */
+int dmmt_plan_encode_device(dmmt_plan *, const void *d_pixels, int n_images, uint8_t *d_out,
+                            uint64_t *d_lens);
 int dmmt_plan_status(dmmt_plan *);                /* synchronises; first device-side error or 0 */
-/* Host-buffer end-to-end: H2D of the pixels, encode, D2H of lengths + bytes.  jpegs[i] malloc'd. */
-int dmmt_plan_encode_host(dmmt_plan *, const void *h_pixels, uint8_t **jpegs, size_t *lens);
-/* Same but into a caller-provided host arena (n * out_stride bytes, ideally pinned). */
-int dmmt_plan_encode_host_into(dmmt_plan *, const void *h_pixels, uint8_t *h_out, uint64_t *h_lens);
+/* Host-buffer end-to-end: H2D of the pixels, encode, D2H of lengths + bytes.  jpegs[i] malloc'd
+ * (release with dmmt_free).  Grows the scan capacity and retries once on DMMT_E_OVERFLOW. */
+int dmmt_plan_encode_host(dmmt_plan *, const void *h_pixels, int n_images, uint8_t **jpegs,
+                          size_t *lens);
+/* Same, but the files are packed back to back (16-byte aligned starts) into the caller's host
+ * arena (ideally pinned, see dmmt_host_alloc): file i = h_out[h_offsets[i] .. + h_lens[i]). */
+int dmmt_plan_encode_host_into(dmmt_plan *, const void *h_pixels, int n_images, uint8_t *h_out,
+                               uint64_t out_cap, uint64_t *h_offsets, uint64_t *h_lens);
+
+/* ---- batches: many equally sized images, pipelined in sub-batches over `depth` streams ------ */
+/* This is the throughput path (BASELINE config 4): sub-batch k runs on slot k % depth, so the
+ * H2D copy, the kernel chain and the D2H copy of neighbouring sub-batches overlap. */
+typedef struct dmmt_batch dmmt_batch;
+int dmmt_batch_create(dmmt_ctx *, uint16_t width, uint16_t height, dmmt_fmt fmt, uint16_t max_value,
+                      const dmmt_options *, int sub_batch, int depth, dmmt_batch **out);
+void dmmt_batch_destroy(dmmt_batch *);
+/* Inputs resident in device memory (n images back to back), outputs stay in device memory:
+ * files packed back to back into d_dense (file i at d_offsets[i], length d_lens[i];
+ * d_offsets has n + 1 entries, the last one is the total).  Asynchronous; follow with
+ * dmmt_batch_status. */
+int dmmt_batch_encode_device(dmmt_batch *, const void *d_pixels, int n, uint8_t *d_dense,
+                             uint64_t dense_cap, uint64_t *d_offsets, uint64_t *d_lens);
+/* Host pixels (ideally pinned) -> host files, packed into h_out like
+ * dmmt_plan_encode_host_into.  Synchronous at return. */
+int dmmt_batch_encode_host(dmmt_batch *, const void *h_pixels, int n, uint8_t *h_out, uint64_t out_cap,
+                           uint64_t *h_offsets, uint64_t *h_lens);
+int dmmt_batch_status(dmmt_batch *);              /* synchronises all slots; first error or 0 */
+/* scan capacity of every slot (see dmmt_plan_set_scan_capacity); use after DMMT_E_OVERFLOW */
+int dmmt_batch_set_scan_capacity(dmmt_batch *, size_t bytes_per_image);
+size_t dmmt_batch_worst_case_scan_bytes(const dmmt_batch *);
+int dmmt_batch_last_launch_count(const dmmt_batch *);
+/* per-kernel timings (DMMT_T_*) summed over the sub-batches of the last dmmt_batch_encode_device
+ * call; profiling serialises the slots. */
+int dmmt_batch_set_profiling(dmmt_batch *, int enabled);
+int dmmt_batch_last_timings(dmmt_batch *, float *ms, int n);
+/* page-locked host memory for the host-buffer paths */
+int dmmt_host_alloc(size_t bytes, void **out);
+void dmmt_host_free(void *);
 
 /* per-kernel CUDA-event timings of the last dmmt_plan_encode_* call (profiling must be enabled
  * first; it adds event records between the kernels).  ms[] order: DMMT_T_* */
@@ -125,8 +161,9 @@ int dmmt_plan_encode_host_into(dmmt_plan *, const void *h_pixels, uint8_t *h_out
 #define DMMT_T_K2B_TABLES 2
 #define DMMT_T_K3_PACK 3      /* bit-length + decoupled look-back scan + pack (incl. scan zeroing) */
 #define DMMT_T_K4_STUFF 4
-#define DMMT_T_TOTAL 5
-#define DMMT_T_COUNT 6
+#define DMMT_T_K5_COMPACT 5 /* packing of the output arena (0 when not run) */
+#define DMMT_T_TOTAL 6
+#define DMMT_T_COUNT 7
 int dmmt_plan_set_profiling(dmmt_plan *, int enabled);
 int dmmt_plan_last_timings(dmmt_plan *, float *ms, int n);
 /* number of kernels launched by the last encode call on this plan */
@@ -135,7 +172,7 @@ int dmmt_plan_last_launch_count(const dmmt_plan *);
 /* ---- test / measurement hooks (not part of the drop-in surface) --------------------------- */
 #define DMMT_FETCH_COEF 0      /* i16 [n_stream_blocks][64], zig-zag, MCU-interleaved stream order */
 #define DMMT_FETCH_HIST 1      /* u32 [4][256]: Y-DC, Y-AC, C-DC, C-AC */
-#define DMMT_FETCH_TABLES 2    /* u8  [4][2][256]: per table symbols[256] then lengths[256] in the reference's Vec<SymbolCodeLength> order; count via DMMT_FETCH_META */
+#define DMMT_FETCH_TABLES 2    /* u8  [2][4][256]: symbols[4][256] then lengths[4][256], each table in the reference's Vec<SymbolCodeLength> order; counts via DMMT_FETCH_META */
 #define DMMT_FETCH_SCAN 3      /* unstuffed, 1-padded scan bytes */
 #define DMMT_FETCH_META 4      /* dmmt_image_meta */
 typedef struct {
@@ -182,6 +219,8 @@ int dmmt_shard_pack(dmmt_shard *, uint64_t global_bit_offset, int is_last, uint8
  * is_last: append EOI.  Result stays on the device: *d_bytes / *n_bytes. */
 int dmmt_shard_stuff(dmmt_shard *, uint8_t prev_tail_byte, int prev_tail_nbits, int is_first,
                      int is_last, const uint8_t **d_bytes, uint64_t *n_bytes);
+
+int dmmt_shard_launch_count(const dmmt_shard *);  /* kernels launched by the phases so far */
 
 #ifdef __cplusplus
 }

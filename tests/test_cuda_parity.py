@@ -1,0 +1,396 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the
+committed golden files.  Bit-exact for every integer/byte stage; the pre-quantisation DCT
+coefficients are checked at the north-star tolerance (1e-4 relative) AND for bit equality.
+
+Run with `pytest -m gpu` on a B200 (gpurun); skipped by `-m "not gpu"`.
+"""
+import ctypes as C
+import hashlib
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, GOLDEN, PRESETS, load_fixture, synth_image
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def D():
+    import dmmt_jpeg_encoder_b200 as d
+
+    if d._ffi.lib().dmmt_device_count() < 1:
+        pytest.fail("no CUDA device: the CUDA path cannot run and there is no fallback")
+    return d
+
+
+@pytest.fixture(scope="module")
+def ctx(D):
+    c = D.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+
+    return oracle
+
+
+SHA = json.load(open(os.path.join(GOLDEN, "expected_sha256.json")))
+
+
+def stream_map(r):
+    """(component, raster block index) of every stream block."""
+    hr, vr = {0: (1, 1), 1: (2, 1), 2: (2, 2)}[r.preset]
+    bw = r.padded_width // 8
+    cbw = bw // hr
+    mcus_x, mcus_y = r.padded_width // (8 * hr), r.padded_height // (8 * vr)
+    out = []
+    for my in range(mcus_y):
+        for mx in range(mcus_x):
+            for dy in range(vr):
+                for dx in range(hr):
+                    out.append((0, (my * vr + dy) * bw + mx * hr + dx))
+            out.append((1, my * cbw + mx))
+            out.append((2, my * cbw + mx))
+    return out
+
+
+def oracle_encode(O, px, mx=255, preset=2, q=0, bits=8, keep=False):
+    r = O.encode(px, mx, preset, bits, q, keep_planes=keep)
+    r.preset = preset
+    return r
+
+
+# ------------------------------------------------------------------------------- whole files
+@pytest.mark.parametrize("name", FIXTURES)
+@pytest.mark.parametrize("pname", list(PRESETS))
+def test_golden_files_byte_identical(D, ctx, name, pname):
+    """BASELINE configs 1+2: tests/*.ppm x {P444,P422,P420} byte-identical to the golden files."""
+    _, px, mx = load_fixture(name)
+    got = ctx.encode(px, mx, D.Options(PRESETS[pname], 8, 0))
+    key = f"{name}_{pname}"
+    assert hashlib.sha256(got).hexdigest() == SHA[key]
+    assert got == open(os.path.join(GOLDEN, "jpeg", key + ".jpg"), "rb").read()
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_reference_api_convert_ppm_to_jpeg(D, tmp_path, name):
+    """The reference's public entry point (lib.rs:59-77) on the P3 text of the fixtures."""
+    text, _, _ = load_fixture(name)
+    src, dst = tmp_path / f"{name}.ppm", tmp_path / f"{name}.jpg"
+    src.write_bytes(text)
+    args = D.CLIParser.default().parse(["dmmt-jpeg-encoder", str(src), str(dst)])
+    D.convert_ppm_to_jpeg(args)
+    assert dst.read_bytes() == open(os.path.join(GOLDEN, "jpeg", f"{name}_P420.jpg"), "rb").read()
+
+
+def test_jpeg_image_writer_f32_image_equals_sample_image(D, O):
+    """Image<f32> (already normalised dots) and raw samples + max give the same bytes."""
+    px = synth_image("photo", 77, 45, 5)
+    opts = D.JpegTransformationOptions()
+    a, b = io.BytesIO(), io.BytesIO()
+    D.JpegImageWriter(a, D.Image(77, 45, samples=px, max_value=255), opts).write_image()
+    dots = px.astype(np.float32) / np.float32(255)
+    D.JpegImageWriter(b, D.Image(77, 45, dots), opts).write_image()
+    assert a.getvalue() == b.getvalue() == O.encode(px, 255, O.P420).jpeg
+
+
+# ------------------------------------------------------------------------------- stage by stage
+@pytest.mark.parametrize("pname", list(PRESETS))
+@pytest.mark.parametrize("kind,w,h", [("photo", 203, 117), ("uniform", 64, 48), ("grad", 500, 260)])
+def test_every_stage_matches_oracle(D, ctx, O, pname, kind, w, h):
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    preset = PRESETS[pname]
+    px = synth_image(kind, w, h, 7)
+    r = oracle_encode(O, px, preset=preset, keep=True)
+    plan = D.Plan(ctx, w, h, F.FMT_U8, 255, D.Options(preset, 8, 0), 1)
+    d_px = torch.from_numpy(px).cuda()
+    d_out = torch.empty(plan.out_stride, dtype=torch.uint8, device="cuda")
+    d_len = torch.zeros(1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    plan.encode_device(d_px.data_ptr(), 1, d_out.data_ptr(), d_len.data_ptr())
+    plan.status()
+    assert plan.stream_blocks == r.n_stream_blocks
+    # K1: quantised zig-zag coefficients in stream order -- bit exact
+    coef = plan.fetch(F.FETCH_COEF)
+    np.testing.assert_array_equal(coef, r.stream)
+    # K1 debug variant: pre-quantisation DCT coefficients
+    dct = plan.debug_dct(d_px.data_ptr())
+    planes = (r.dct_y, r.dct_cb, r.dct_cr)
+    want = np.stack([planes[c][i] for c, i in stream_map(r)])
+    scale = np.maximum(np.abs(want), 1.0)
+    assert np.max(np.abs(dct - want) / scale) <= 1e-4          # north-star tolerance
+    assert np.array_equal(dct == 0, want == 0) and np.array_equal(dct[want != 0], want[want != 0])  # and bit equality
+    # K2: histograms
+    hist = plan.fetch(F.FETCH_HIST)
+    np.testing.assert_array_equal(hist.astype(np.uint64), r.hist)
+    # K2b: length tables in the reference's Vec<SymbolCodeLength> order
+    sym, ln = plan.fetch(F.FETCH_TABLES)
+    meta = plan.fetch(F.FETCH_META)
+    for t in range(4):
+        n = meta.n_symbols[t]
+        assert n == len(r.tables[t][0])
+        assert list(sym[t][:n]) == r.tables[t][0]
+        assert list(ln[t][:n]) == r.tables[t][1]
+    assert meta.scan_bits == r.scan_bits and meta.header_len == r.header_bytes
+    # K3: unstuffed scan; K4: the file
+    n_out = int(d_len.item())
+    got = bytes(d_out[:n_out].cpu().numpy())
+    assert got == r.jpeg
+    scan = plan.fetch(F.FETCH_SCAN)
+    assert len(scan) == r.scan_bytes_unstuffed
+    assert O.stuff_bytes(bytes(scan)) == r.jpeg[r.header_bytes:-2]
+    plan.close()
+
+
+@pytest.mark.parametrize("q", range(7))
+def test_all_quantisation_presets(D, ctx, O, q):
+    px = synth_image("photo", 120, 72, q)
+    for preset in (0, 1, 2):
+        assert ctx.encode(px, 255, D.Options(preset, 8, q)) == O.encode(px, 255, preset, 8, q).jpeg
+
+
+@pytest.mark.parametrize("bits", [8, 16, 32])
+def test_bits_per_channel_only_changes_sof(D, ctx, O, bits):
+    px = synth_image("grad", 40, 40)
+    assert ctx.encode(px, 255, D.Options(2, bits, 0)) == O.encode(px, 255, 2, bits, 0).jpeg
+
+
+def test_input_formats(D, ctx, O):
+    """u8, u16 (max 255 / 1023 / 65535) and normalised f32 inputs, incl. unaligned row pitches."""
+    rng = np.random.default_rng(3)
+    for w, h in [(33, 21), (64, 16), (16, 64), (1, 1), (2, 2), (8, 8), (17, 7), (255, 3)]:
+        px = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = O.encode(px, 255, O.P420).jpeg
+        assert ctx.encode(px, 255) == want
+        assert ctx.encode(px.astype(np.uint16), 255) == want
+        assert ctx.encode(px.astype(np.float32) / np.float32(255), 1) == want
+    for mx in (1023, 65535, 17734, 15):
+        px = rng.integers(0, mx + 1, (37, 53, 3)).astype(np.uint16)
+        for preset in (0, 1, 2):
+            assert ctx.encode(px, mx, D.Options(preset, 8, 0)) == O.encode(px, mx, preset).jpeg
+    px = rng.integers(0, 16, (20, 20, 3)).astype(np.uint8)
+    assert ctx.encode(px, 15) == O.encode(px, 15, O.P420).jpeg
+
+
+@pytest.mark.parametrize("pname", list(PRESETS))
+def test_ragged_sizes_sweep(D, ctx, O, pname):
+    """Edge padding (padder.rs:12-42): every residue of W and H modulo the MCU, plus tile edges."""
+    rng = np.random.default_rng(11)
+    sizes = [(w, h) for w in (1, 7, 8, 9, 15, 16, 17, 31) for h in (1, 7, 9, 16, 17)]
+    sizes += [(255, 9), (256, 9), (257, 9), (271, 33), (513, 17), (1030, 5)]
+    for w, h in sizes:
+        px = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        got = ctx.encode(px, 255, D.Options(PRESETS[pname], 8, 0))
+        assert got == O.encode(px, 255, PRESETS[pname]).jpeg, (w, h)
+
+
+def test_uniform_noise_reaches_16_bit_codes(D, ctx, O):
+    px = synth_image("uniform", 256, 256, 0)
+    r = O.encode(px, 255, O.P420)
+    assert max(max(l) for _, l in r.tables) == 16          # 15 + the '+1' quirk (symbol_counting.rs:88)
+    assert ctx.encode(px, 255) == r.jpeg
+
+
+def test_constant_and_extreme_images(D, ctx, O):
+    for val in (0, 255, 128):
+        px = np.full((40, 56, 3), val, np.uint8)
+        assert ctx.encode(px, 255) == O.encode(px, 255, O.P420).jpeg
+    # black/white checkerboard at pixel level: largest AC magnitudes
+    y, x = np.mgrid[0:64, 0:64]
+    px = (((x + y) & 1) * 255).astype(np.uint8)[..., None].repeat(3, -1)
+    for preset in (0, 1, 2):
+        assert ctx.encode(px, 255, D.Options(preset, 8, 1)) == O.encode(px, 255, preset, 8, 1).jpeg
+
+
+def test_all_ff_scan_stuffing(D, ctx, O):
+    """Images whose scans contain many 0xFF bytes exercise K4's compaction."""
+    rng = np.random.default_rng(5)
+    found = 0
+    for seed in range(6):
+        px = synth_image("uniform", 96, 80, seed)
+        r = O.encode(px, 255, O.P444, 8, 1)
+        found += r.scan_bytes_stuffed - r.scan_bytes_unstuffed
+        assert ctx.encode(px, 255, D.Options(0, 8, 1)) == r.jpeg
+    assert found > 0
+
+
+# ------------------------------------------------------------------------------- errors
+def test_sample_above_max_is_rejected(D, ctx):
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    px = np.full((16, 16, 3), 200, np.uint8)
+    with pytest.raises(D.DmmtError) as e:
+        ctx.encode(px, 100)
+    assert e.value.code == F.E_INVALID
+
+
+def test_scan_overflow_is_detected_and_retried(D, ctx, O):
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    px = synth_image("uniform", 128, 128, 1)
+    want = O.encode(px, 255, O.P444, 8, 1).jpeg
+    plan = D.Plan(ctx, 128, 128, F.FMT_U8, 255, D.Options(0, 8, 1), 1)
+    plan.set_scan_capacity(1024)
+    d_px = torch.from_numpy(px).cuda()
+    d_out = torch.zeros(plan.out_stride, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    plan.encode_device(d_px.data_ptr(), 1, d_out.data_ptr())
+    with pytest.raises(D.DmmtError) as e:
+        plan.status()
+    assert e.value.code == F.E_OVERFLOW
+    # the host path grows the capacity to the worst case and retries
+    assert plan.encode_host(px[None]) == [want]
+    plan.close()
+
+
+def test_invalid_arguments(D, ctx):
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    with pytest.raises(D.DmmtError) as e:
+        D.Plan(ctx, 16, 16, F.FMT_U8, 255, D.Options(3, 8, 0), 1)
+    assert e.value.code == F.E_INVALID
+    with pytest.raises(D.DmmtError) as e:
+        D.Plan(ctx, 16, 16, F.FMT_U8, 255, D.Options(2, 8, 9), 1)
+    assert e.value.code == F.E_INVALID
+    with pytest.raises(D.DmmtError) as e:
+        D.Plan(ctx, 65535, 16, F.FMT_U8, 255, D.Options(2, 8, 0), 1)   # padded width 65536 wraps u16
+    assert e.value.code == F.E_SIZE
+
+
+# ------------------------------------------------------------------------------- batches
+@pytest.mark.parametrize("pname", list(PRESETS))
+def test_plan_batch_of_images(D, ctx, O, pname):
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    n, w, h = 7, 150, 90
+    px = np.stack([synth_image(("photo", "uniform", "grad")[i % 3], w, h, i) for i in range(n)])
+    plan = D.Plan(ctx, w, h, F.FMT_U8, 255, D.Options(PRESETS[pname], 8, 0), n)
+    got = plan.encode_host(px)
+    for i in range(n):
+        assert got[i] == O.encode(px[i], 255, PRESETS[pname]).jpeg, i
+    # fewer images than the plan holds
+    got = plan.encode_host(px[:3])
+    assert got == [O.encode(px[i], 255, PRESETS[pname]).jpeg for i in range(3)]
+    plan.close()
+
+
+@pytest.mark.parametrize("sub,depth", [(4, 3), (5, 2), (16, 1), (1, 4)])
+def test_pipelined_batch_host_and_device(D, ctx, O, sub, depth):
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    n, w, h = 13, 200, 120
+    px = np.stack([synth_image(("photo", "grad", "uniform")[i % 3], w, h, 100 + i) for i in range(n)])
+    want = [O.encode(px[i], 255, O.P420).jpeg for i in range(n)]
+    b = D.Batch(ctx, w, h, F.FMT_U8, 255, D.Options(), sub, depth)
+    assert b.encode(px) == want
+    assert b.encode(px) == want                      # slots are reusable
+    # device-resident path: packed arena + offsets + lens stay on the device
+    s = torch.cuda.Stream()
+    c2 = D.Context(0, s.cuda_stream)
+    b2 = D.Batch(c2, w, h, F.FMT_U8, 255, D.Options(), sub, depth)
+    d_px = torch.from_numpy(px).cuda()
+    cap = px.nbytes
+    d_dense = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    d_off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    d_len = torch.zeros(n, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(2):
+        b2.encode_device(d_px.data_ptr(), n, d_dense.data_ptr(), cap, d_off.data_ptr(), d_len.data_ptr())
+        b2.status()
+        off, ln, dense = d_off.cpu().numpy(), d_len.cpu().numpy(), d_dense.cpu().numpy()
+        assert off[0] == 0 and off[n] == sum((l + 15) // 16 * 16 for l in ln)
+        for i in range(n):
+            assert dense[off[i]: off[i] + ln[i]].tobytes() == want[i], i
+    assert b2.last_launch_count() > 0
+    b.close(), b2.close(), c2.close()
+
+
+def test_generic_encode_batch_mixed_geometries(D, ctx, O):
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    imgs = [synth_image("photo", 40 + 9 * i, 30 + 5 * i, i) for i in range(5)]
+    arr = (F.Image * 5)(*[F.Image(im.shape[1], im.shape[0], 255, F.FMT_U8, im.ctypes.data, 0) for im in imgs])
+    ctxs = (C.c_void_p * 2)(ctx.handle, ctx.handle)
+    outs, lens = (F._U8P * 5)(), (C.c_size_t * 5)()
+    o = D.Options().c()
+    F.check(F.lib().dmmt_encode_batch(ctxs, 2, arr, 5, C.byref(o), outs, lens))
+    for i in range(5):
+        assert C.string_at(outs[i], lens[i]) == O.encode(imgs[i], 255, O.P420).jpeg
+        F.lib().dmmt_free(outs[i])
+
+
+# ------------------------------------------------------------------------------- shards
+@pytest.mark.parametrize("pname", list(PRESETS))
+@pytest.mark.parametrize("n_shards", [2, 3, 8])
+def test_mcu_row_shards_stitch_to_the_same_file(D, ctx, O, pname, n_shards):
+    """BASELINE config 5 at test size: MCU-row shards with DC seeds, global histograms and
+    bit-offset stitching reproduce the unsharded file byte for byte (here all shards on one GPU)."""
+    px = synth_image("photo", 210, 333, 42)
+    want = O.encode(px, 255, PRESETS[pname]).jpeg
+    assert ctx.encode_sharded(px, n_shards, 255, D.Options(PRESETS[pname], 8, 0)) == want
+
+
+def test_shards_with_tiny_bit_counts(D, ctx, O):
+    """One MCU per row, constant colour: a shard holds only a handful of bits, so shards may not
+    complete a byte and must hand their predecessor's tail on."""
+    for preset in (0, 1, 2):
+        px = np.full((72, 8, 3), 77, np.uint8)
+        want = O.encode(px, 255, preset).jpeg
+        for n in (2, 3, 4, 9):
+            assert ctx.encode_sharded(px, n, 255, D.Options(preset, 8, 0)) == want, (preset, n)
+
+
+# ------------------------------------------------------------------------------- full sizes
+def test_4k_frame_matches_oracle_and_decodes(D, ctx, O):
+    """BASELINE config 3 geometry (3840x2160)."""
+    from PIL import Image
+
+    px = synth_image("photo", 3840, 2160, 0)
+    got = ctx.encode(px, 255)
+    assert got == O.encode(px, 255, O.P420, nthreads=8).jpeg
+    im = np.asarray(Image.open(io.BytesIO(got)).convert("RGB")).astype(np.float64)
+    mse = ((im - px.astype(np.float64)) ** 2).mean()
+    assert 10 * np.log10(255 ** 2 / mse) > 30.0
+
+
+def test_1080p_batch_properties(D, ctx, O):
+    """BASELINE config 4 geometry (1920x1080 -> padded 1088): a batch of 24 frames; two of them
+    against the oracle, all of them for structural invariants (markers, sizes, decodability of one)."""
+    from PIL import Image
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    n = 24
+    px = np.stack([synth_image("grad" if i % 2 else "uniform", 1920, 1080, i) for i in range(n)])
+    b = D.Batch(ctx, 1920, 1080, F.FMT_U8, 255, D.Options(), 8, 3)
+    files = b.encode(px)
+    for i in (0, 13):
+        assert files[i] == O.encode(px[i], 255, O.P420, nthreads=8).jpeg
+    for f in files:
+        assert f[:2] == b"\xff\xd8" and f[-2:] == b"\xff\xd9"
+        body = f[f.index(b"\xff\xda") + 14:-2]
+        assert b"\xff" not in body.replace(b"\xff\x00", b"")      # every 0xFF is stuffed
+    assert Image.open(io.BytesIO(files[1])).size == (1920, 1080)
+    # same image -> same file wherever it sits in the batch (no cross-image state)
+    px2 = px[::-1].copy()
+    assert b.encode(px2) == files[::-1]
+    b.close()
+
+
+def test_large_image_sharded_equals_unsharded(D, ctx, O):
+    """Config 5 property at 8192x4096 (the oracle would need minutes): N-shard output is
+    independent of N and equal to the single-launch-chain output."""
+    px = synth_image("grad", 8192, 4096)
+    whole = ctx.encode(px, 255)
+    assert ctx.encode_sharded(px, 4, 255) == whole
+    assert ctx.encode_sharded(px, 7, 255) == whole
+    assert whole[:2] == b"\xff\xd8" and whole[-2:] == b"\xff\xd9"
