@@ -194,11 +194,12 @@ def test_ragged_sizes_sweep(D, ctx, O, pname):
         assert got == O.encode(px, 255, PRESETS[pname]).jpeg, (w, h)
 
 
-def test_uniform_noise_reaches_16_bit_codes(D, ctx, O):
-    px = synth_image("uniform", 256, 256, 0)
-    r = O.encode(px, 255, O.P420)
-    assert max(max(l) for _, l in r.tables) == 16          # 15 + the '+1' quirk (symbol_counting.rs:88)
-    assert ctx.encode(px, 255) == r.jpeg
+def test_noise_reaches_16_bit_codes(D, ctx, O):
+    for kind, preset in (("photo", 2), ("uniform", 0)):
+        px = synth_image(kind, 512, 512, 0)
+        r = O.encode(px, 255, preset)
+        assert max(max(l) for _, l in r.tables) == 16      # 15 + the '+1' quirk (symbol_counting.rs:88)
+        assert ctx.encode(px, 255, D.Options(preset, 8, 0)) == r.jpeg
 
 
 def test_constant_and_extreme_images(D, ctx, O):
@@ -360,7 +361,9 @@ def test_4k_frame_matches_oracle_and_decodes(D, ctx, O):
     assert got == O.encode(px, 255, O.P420, nthreads=8).jpeg
     im = np.asarray(Image.open(io.BytesIO(got)).convert("RGB")).astype(np.float64)
     mse = ((im - px.astype(np.float64)) ** 2).mean()
-    assert 10 * np.log10(255 ** 2 / mse) > 30.0
+    # per-channel independent noise with a 3 px correlation length mostly lives in the chroma that
+    # 4:2:0 + Annex K quantisation discard: ~20.7 dB is what libjpeg reconstructs from these bytes
+    assert 10 * np.log10(255 ** 2 / mse) > 18.0
 
 
 def test_1080p_batch_properties(D, ctx, O):
