@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- encoded MPixel/s of the B200 encode path on BASELINE.json's batched workload.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): a batch of 1024
+synthetic 1920x1080 RGB frames, 4:2:0, Annex-K tables; image i belongs to rank i mod N (round-robin,
+no data-path collective).  A "step" = one pass of the whole encode path (K1..K5: colour/pad/
+subsample/DCT/quantise -> histogram -> per-image Huffman tables -> bit pack -> byte stuffing ->
+packed files) over the rank's share of the batch.
+
+  value : whole-job MPixel/s (original pixels), inputs resident in HBM, outputs left in HBM,
+          CUDA events on the launching stream, max over ranks.
+  e2e   : the same through the host-buffer C-ABI call (dmmt_batch_encode_host): pinned host
+          pixels -> H2D -> encode -> D2H of the files, every step.
+  roofline / kernels : per-kernel CUDA-event times of one extra profiled pass (slots serialised),
+          algorithmic bytes per launch / time vs MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline : the C oracle (restatement of the reference; the Rust crate cannot be built in
+          this image) on the host cores, on a bounded sample of the same images.
+
+`--impl reference` times only that CPU arm (rank 0), with the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import socket
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "encoded MPixel/s"
+UNIT = "MPixel/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=1024, help="global batch (images)")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--kind", default="photo", choices=["photo", "grad", "uniform"])
+    ap.add_argument("--sub-batch", type=int, default=32)
+    ap.add_argument("--depth", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=64, help="images of the batch timed on the CPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def hbm_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU while the timed region runs (pynvml)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml as N
+
+            N.nvmlInit()
+            self.N = N
+            self.h = N.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM)
+        except Exception:
+            self.N = None
+
+    def _loop(self):
+        N = self.N
+        names = {
+            getattr(N, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(N, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(N, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(N, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM))
+                try:
+                    r = N.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def start(self):
+        if self.N is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "nvml unavailable"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def cpu_arm(args, indices, steps, warmup):
+    """Times the oracle (C restatement of the reference) on `indices` of the synthetic batch with
+    one image per host thread (the reference is one image per process, src/lib.rs:59-77; a batch
+    user runs one process per core).  Returns (MPixel/s, cores, sample description, ms per step)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from dmmt_jpeg_encoder_b200 import synth
+    from oracle import oracle as O
+
+    O.build()
+    cores = os.cpu_count() or 1
+    imgs = [synth.make(args.kind, i, args.height, args.width).numpy() for i in indices]
+
+    def one(px):
+        return len(O.encode(px, 255, O.P420, 8, 0, nthreads=1).jpeg)
+
+    def step():
+        with ThreadPoolExecutor(cores) as ex:
+            return sum(ex.map(one, imgs))
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    mpix = len(imgs) * args.width * args.height * steps / dt / 1e6
+    sample = (f"{len(imgs)} of the {args.images} {args.width}x{args.height} '{args.kind}' frames per step, "
+              f"{steps} step(s), one frame per host thread ({cores} threads), C restatement of the reference "
+              f"(oracle/, gcc -O2 -ffp-contract=off); timed region = JpegImageWriter::write_image equivalent")
+    return mpix, cores, sample, dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = min(args.cpu_sample, args.images)
+    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    mpix, cores, sample, ms = cpu_arm(args, list(range(n)), steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": f"synthetic ({args.kind}, int-hash generator, seeds 1234+i)",
+        "config": {"workload": f"batch of {args.images} synthetic {args.width}x{args.height} RGB u8 frames -> baseline "
+                               f"JPEG 4:2:0, Annex-K tables, per-image optimal Huffman tables (bounded CPU sample: "
+                               f"{n} frames per step)"},
+        "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is Rust-only and no Rust toolchain exists in this image: this arm is the C oracle "
+                "(oracle/dmmt_oracle.c), a restatement of the reference's algorithm, not the Rust binary",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import dmmt_jpeg_encoder_b200 as D
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+    from dmmt_jpeg_encoder_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or F.lib().dmmt_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the encode path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def reduce(v, op):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    W, H, K, WU = args.width, args.height, args.steps, max(args.warmup, 0)
+    mine = list(range(rank, args.images, world))           # round-robin: image i -> rank i mod N
+    n = len(mine)
+    img_bytes = W * H * 3
+    pW, pH = (W + 15) // 16 * 16, (H + 15) // 16 * 16
+
+    # ---- synthetic inputs, generated on the device (not timed)
+    d_px = torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev)
+    for j, i in enumerate(mine):
+        d_px[j] = synth.make(args.kind, i, H, W, dev)
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream(device=dev)
+    ctx = D.Context(local, stream.cuda_stream)
+    batch = D.Batch(ctx, W, H, F.FMT_U8, 255, D.Options(F.P420, 8, 0), min(args.sub_batch, n), args.depth)
+    dense_cap = n * (img_bytes // 4)
+    d_dense = torch.empty(dense_cap, dtype=torch.uint8, device=dev)
+    d_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    d_len = torch.zeros(n, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        batch.encode_device(d_px.data_ptr(), n, d_dense.data_ptr(), dense_cap, d_off.data_ptr(), d_len.data_ptr())
+
+    for _ in range(max(WU, 1)):
+        step()
+    batch.status()                                          # raises on any device-side error
+    lens = d_len.cpu().numpy().astype(np.int64)
+    offs = d_off.cpu().numpy().astype(np.int64)
+    file_bytes = int(lens.sum())
+
+    # ---- the checker (outside every timed region): image 0 of this rank byte-identical to the oracle
+    verified = None
+    if rank == 0:
+        from oracle import oracle as O
+
+        got = d_dense[offs[0]: offs[0] + lens[0]].cpu().numpy().tobytes()
+        want = O.encode(d_px[0].cpu().numpy(), 255, O.P420).jpeg
+        if got != want:
+            raise SystemExit("bench: CUDA output of image 0 differs from the oracle -- numbers would be meaningless")
+        verified = "image 0 byte-identical to oracle"
+
+    # ---- value: device-resident, CUDA events on the context's stream
+    sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(K):
+            step()
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    batch.status()
+    ms_total = reduce(ev0.elapsed_time(ev1), dist.ReduceOp.MAX if world > 1 else None)
+    launches = reduce(float(batch.last_launch_count() * K), dist.ReduceOp.SUM if world > 1 else None)
+    total_px = args.images * W * H
+    value = total_px * K / (ms_total / 1e3) / 1e6
+
+    # ---- e2e: host buffers through dmmt_batch_encode_host, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_in = D.PinnedBuffer(n * img_bytes)
+        h_out_cap = max(file_bytes * 2, 1 << 20)
+        h_out = D.PinnedBuffer(h_out_cap)
+        torch.from_numpy(h_in.array).view(n, H, W, 3).copy_(d_px)      # stage the inputs on the host once
+        torch.cuda.synchronize()
+        h_offs, h_lens = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        batch_h = D.Batch(ctx, W, H, F.FMT_U8, 255, D.Options(F.P420, 8, 0), min(args.sub_batch, n), args.depth)
+
+        def estep():
+            batch_h.encode_host(h_in.ptr, n, h_out.ptr, h_out_cap, h_offs, h_lens)
+
+        for _ in range(max(min(WU, 2), 1)):
+            estep()
+        assert int(h_lens.sum()) == file_bytes
+        if rank == 0:
+            assert h_out.array[int(h_offs[0]): int(h_offs[0] + h_lens[0])].tobytes() == want
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            estep()                                         # synchronous at return
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        dt = reduce(dt, dist.ReduceOp.MAX if world > 1 else None)
+        d2h = reduce(float(int(h_offs[-1] + (h_lens[-1] + 15) // 16 * 16) + 16 * n + 8 * (n + (n + args.sub_batch - 1) // args.sub_batch)),
+                     dist.ReduceOp.SUM if world > 1 else None)
+        e2e = {"value": total_px * K / dt / 1e6, "unit": UNIT, "ms_per_step": dt / K * 1e3,
+               "h2d_bytes_per_step": int(reduce(float(n * img_bytes), dist.ReduceOp.SUM if world > 1 else None)),
+               "d2h_bytes_per_step": int(d2h),
+               "api": "dmmt_batch_encode_host (pinned host pixels -> packed host files), all ranks"}
+        batch_h.close()
+        h_in.close(), h_out.close()
+
+    # ---- per-kernel pass (slots serialised, events between kernels) -> roofline
+    peak, peak_src = hbm_peak()
+    batch.set_profiling(True)
+    step()
+    batch.status()
+    tm = batch.last_timings()
+    batch.set_profiling(False)
+    n_sub = (n + batch.sub_batch - 1) // batch.sub_batch
+    coef_bytes = 2 * (pW * pH * 3 // 2)                     # i16 coefficients per image, 4:2:0
+    scan_b = (file_bytes / n) - 330.0                       # ~ stuffed scan bytes per image
+    n_blocks = (pW // 8) * (pH // 8) * 3 // 2
+    alg = {                                                 # algorithmic bytes per IMAGE
+        "k1_transform": img_bytes + coef_bytes,
+        "k2_histogram": coef_bytes,
+        "k3_pack": coef_bytes + scan_b + 4 * n_blocks / 256.0,
+        "k4_stuff": 2 * scan_b,
+        "k5_compact": 2 * (file_bytes / n),
+    }
+    kernels = {}
+    for name, per_img in alg.items():
+        ms = tm[name]
+        if ms <= 0:
+            continue
+        gbs = per_img * n / (ms / 1e3) / 1e9
+        kernels[name] = {"ms_per_step": ms, "launches_per_step": n_sub * (2 if name in ("k3_pack", "k5_compact") else 1),
+                         "avg_launch_ms": ms / n_sub, "algorithmic_bytes_per_launch": per_img * n / n_sub,
+                         "achieved_gbs": gbs, "frac": gbs / peak}
+    kernels["k2b_tables"] = {"ms_per_step": tm["k2b_tables"], "launches_per_step": 2 * n_sub}
+    dom = max((k for k in kernels if "achieved_gbs" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "share_of_step": kernels[dom]["ms_per_step"] / tm["total"] if tm["total"] > 0 else None,
+                "k1_frac": kernels.get("k1_transform", {}).get("frac")}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        m, cores, sample, _ = cpu_arm(args, mine[: min(args.cpu_sample, n)], 2, 1)
+        cpu = {"value": m, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": WU,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": f"synthetic ({args.kind}, int-hash generator, seeds 1234+i, generated on device)",
+            "config": {"workload": f"batch of {args.images} synthetic {W}x{H} RGB u8 frames -> baseline JPEG 4:2:0, "
+                                   f"Annex-K tables, per-image optimal Huffman tables; image i on rank i mod N",
+                       "images_per_rank": n, "sub_batch": batch.sub_batch, "streams": batch.depth,
+                       "l2": f"inputs larger than L2 ({n * img_bytes / 1e6:.0f} MB of pixels per rank per step, no reuse)",
+                       "bytes_per_pixel_out": file_bytes / (n * W * H), "verified": verified},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "kernels": kernels, "kernel_pass_total_ms": tm["total"],
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    batch.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
