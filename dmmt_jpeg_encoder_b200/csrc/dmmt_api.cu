@@ -212,10 +212,7 @@ int dmmt_plan_create_impl(dmmt_ctx* ctx, int W, int H_rows, int mcus_y_override,
     p->pixel_bytes = (size_t)W * H_rows * fmt_bytes(fmt);
     p->coef_stride = (size_t)g.n_blocks * 64;
     p->n_chunks3 = k3_chunks(g);
-    for (int i = 0; i < 64; i++) {
-        p->qf.q[0][i] = (float)kQuantPresets[opt->qtable_preset][0][i];  // `q as f32` (quantizer.rs:60)
-        p->qf.q[1][i] = (float)kQuantPresets[opt->qtable_preset][1][i];
-    }
+    make_k1_consts(fmt, max_value, kQuantPresets[opt->qtable_preset][0], kQuantPresets[opt->qtable_preset][1], &p->k1c);
     int rc = DMMT_OK;
     auto fail = [&](int code) {
         plan_free_scratch(p);
@@ -301,7 +298,7 @@ int dmmt_plan_chain(dmmt_plan* p, const void* d_pixels, int n, uint8_t* d_out, u
     DMMT_CUDA(mark(0));
     const int check_max = (p->fmt == DMMT_RGB_U8 && p->max_value < 255) ||
                           (p->fmt == DMMT_RGB_U16 && p->max_value < 65535);
-    DMMT_CUDA(launch_k1(p->g, p->fmt, (float)p->max_value, check_max, p->qf, d_pixels, p->pixel_bytes, n,
+    DMMT_CUDA(launch_k1(p->g, p->fmt, p->k1c, check_max, d_pixels, p->pixel_bytes, n,
                         p->coef, p->coef_stride, nullptr, p->meta, st));
     launches += 1;
     DMMT_CUDA(mark(1));
@@ -595,7 +592,7 @@ extern "C" int dmmt_plan_debug_dct(dmmt_plan* p, const void* d_pixels, int index
     float* d_dbg = nullptr;
     DMMT_CUDA(cudaMalloc(&d_dbg, p->coef_stride * sizeof(float)));
     const uint8_t* px = static_cast<const uint8_t*>(d_pixels) + (size_t)index * p->pixel_bytes;
-    cudaError_t e = launch_k1(p->g, p->fmt, (float)p->max_value, 0, p->qf, px, p->pixel_bytes, 1,
+    cudaError_t e = launch_k1(p->g, p->fmt, p->k1c, 0, px, p->pixel_bytes, 1,
                               p->coef + (size_t)index * p->coef_stride, p->coef_stride, d_dbg, p->meta + index,
                               p->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dst, d_dbg, p->coef_stride * sizeof(float), cudaMemcpyDeviceToHost, p->stream);

@@ -48,7 +48,7 @@ struct dmmt_plan {
     size_t out_stride = 0;
     size_t coef_stride = 0;         // int16 elements per image
     uint32_t n_chunks3 = 0, max_chunks4 = 0;
-    dmmt::QuantF qf{};
+    dmmt::K1Consts k1c{};
 
     // device scratch
     int16_t* coef = nullptr;

@@ -7,9 +7,15 @@
 namespace dmmt {
 
 // K1 (k1_transform.cu)
-cudaError_t launch_k1(const Geom& g, int fmt, float maxf, int check_max, const QuantF& qf,
-                      const void* d_pixels, size_t img_stride_bytes, int n_images, int16_t* d_coef,
-                      size_t coef_img_stride, float* d_dbg, ImgMeta* meta, cudaStream_t st);
+struct K1Consts {
+    float maxf, r_hi, r_lo;  // max value and 1/max split in two f32
+    int exact;               // 1: use the IEEE-division kernels (fast forms not proven for this plan)
+    QuantF qf, rq_hi, rq_lo; // divisors and 1/q split in two f32
+};
+void make_k1_consts(int fmt, int max_value, const uint8_t* q_luma, const uint8_t* q_chroma, K1Consts* c);
+cudaError_t launch_k1(const Geom& g, int fmt, const K1Consts& c, int check_max, const void* d_pixels,
+                      size_t img_stride_bytes, int n_images, int16_t* d_coef, size_t coef_img_stride,
+                      float* d_dbg, ImgMeta* meta, cudaStream_t st);
 
 // K2 (k2_entropy.cu)
 cudaError_t launch_k2(const Geom& g, const int16_t* coef, size_t coef_img_stride, int n,

@@ -95,7 +95,7 @@ static int shard_transform_launch(dmmt_shard* s, const void* d_pixels) {
     DMMT_CUDA(cudaSetDevice(p->ctx->device));
     DMMT_CUDA(cudaMemsetAsync(p->zero_region, 0, p->zero_bytes, p->stream));
     const int check_max = (p->fmt == DMMT_RGB_U8 && p->max_value < 255) || (p->fmt == DMMT_RGB_U16 && p->max_value < 65535);
-    DMMT_CUDA(launch_k1(p->g, p->fmt, (float)p->max_value, check_max, p->qf, d_pixels, p->pixel_bytes, 1, p->coef,
+    DMMT_CUDA(launch_k1(p->g, p->fmt, p->k1c, check_max, d_pixels, p->pixel_bytes, 1, p->coef,
                         p->coef_stride, nullptr, p->meta, p->stream));
     DMMT_CUDA(launch_last_dc(p->g, p->coef, p->d_last_dc, p->stream));
     p->last_launches = 2;

@@ -98,100 +98,91 @@ __device__ __forceinline__ void rgb_to_ycbcr(float r, float g, float b, float& y
                    255.0f);
 }
 
-// quantizer.rs:60 : (d / q as f32).round() as i16  (IEEE divide, half away from zero, saturate)
-__device__ __forceinline__ int quantize(float d, float q) {
-    const float x = __fdiv_rn(d, q);
-    // round half away from zero: trunc(x + copysign(pred(0.5), x)) is exact for |x| < 2^23
+// quantizer.rs:60 : (d / q as f32).round() as i16  (IEEE divide, half away from zero, saturate).
+// Fast exact form: d / q == fma(d, rq_hi, d * rq_lo) with rq_hi = fl(1/q), rq_lo = fl(1/q - rq_hi):
+// tools/exhaustive_div.cu proves on all 2^32 bit patterns of d and every q in 1..255 that the
+// rounded+saturated i16 is identical (the only exceptions are d = +-inf, which need EXACT).
+template <bool EXACT>
+__device__ __forceinline__ uint32_t quantize(float d, float q, float rq_hi, float rq_lo) {
+    float x;
+    if constexpr (EXACT) x = __fdiv_rn(d, q);
+    else x = __fmaf_rn(d, rq_hi, __fmul_rn(d, rq_lo));
+    // round half away from zero: trunc(x + copysign(pred(0.5), x)); cvt.rzi.s16 saturates, NaN -> 0
     const float h = __int_as_float((__float_as_int(x) & 0x80000000) | 0x3EFFFFFF);
-    int r = __float2int_rz(__fadd_rn(x, h));
-    r = max(-32768, min(32767, r));
-    return r;
+    unsigned short r;
+    asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(r) : "f"(__fadd_rn(x, h)));
+    return (uint32_t)r;
 }
 
 template <int FMT>
 struct Px;
 template <>
 struct Px<DMMT_RGB_U8> {
-    static constexpr int kBytes = 3;
+    static constexpr int kBytes = 3, kWords = 12;   // words per 16-pixel strip row
 };
 template <>
 struct Px<DMMT_RGB_U16> {
-    static constexpr int kBytes = 6;
+    static constexpr int kBytes = 6, kWords = 24;
 };
 template <>
 struct Px<DMMT_RGB_F32_NORM> {
-    static constexpr int kBytes = 12;
+    static constexpr int kBytes = 12, kWords = 48;
 };
 
-// Loads one 16-pixel strip row, normalised (color.rs:45-53), into n[48] (r,g,b interleaved).
-// fast: the row segment is fully inside the image and 16-byte aligned -> 128-bit loads.
+// Raw samples of one 16-pixel strip row.  Three cases per thread: fully inside + 16-byte aligned
+// (128-bit loads), fully outside the image (black: padder.rs:18,27-38), ragged (bounds-checked
+// scalar loads).  Samples outside the image are 0, which normalises to exactly 0.0.
 template <int FMT>
 __device__ __forceinline__ void load_strip_row(const uint8_t* __restrict__ row_base, int x0, int W,
-                                               bool row_valid, bool vec_ok, float maxf,
-                                               float (&n)[48], bool check_max, bool& bad) {
-    constexpr int PB = Px<FMT>::kBytes;
-    if (!row_valid) {
+                                               bool row_valid, bool vec_ok,
+                                               uint32_t (&w)[Px<FMT>::kWords]) {
+    constexpr int PB = Px<FMT>::kBytes, NW = Px<FMT>::kWords;
+    if (row_valid && vec_ok && x0 + 16 <= W) {
+        const uint4* p = reinterpret_cast<const uint4*>(row_base + (size_t)x0 * PB);
 #pragma unroll
-        for (int i = 0; i < 48; i++) n[i] = 0.0f;  // padder.rs:18,27-38 black
+        for (int i = 0; i < NW / 4; i++) {
+            const uint4 v = __ldg(p + i);
+            w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+        }
         return;
     }
-    if (vec_ok && x0 + 16 <= W) {
-        const uint4* p = reinterpret_cast<const uint4*>(row_base + (size_t)x0 * PB);
-        if constexpr (FMT == DMMT_RGB_U8) {
-            uint32_t w[12];
 #pragma unroll
-            for (int i = 0; i < 3; i++) {
-                uint4 v = __ldg(p + i);
-                w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
-            }
+    for (int i = 0; i < NW; i++) w[i] = 0u;
+    if (!row_valid || x0 >= W) return;
+    // ragged edge / unaligned pitch
+    const int nval = min(16, W - x0) * 3;  // samples available
+    if constexpr (FMT == DMMT_RGB_U8) {
+        const uint8_t* q = row_base + (size_t)x0 * 3;
 #pragma unroll
-            for (int i = 0; i < 48; i++)
-                n[i] = __fdiv_rn((float)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu), maxf);
-        } else if constexpr (FMT == DMMT_RGB_U16) {
-            uint32_t w[24];
+        for (int i = 0; i < 48; i++)
+            if (i < nval) w[i >> 2] |= (uint32_t)q[i] << (8 * (i & 3));
+    } else if constexpr (FMT == DMMT_RGB_U16) {
+        const uint16_t* q = reinterpret_cast<const uint16_t*>(row_base) + (size_t)x0 * 3;
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
-                uint4 v = __ldg(p + i);
-                w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
-            }
-#pragma unroll
-            for (int i = 0; i < 48; i++)
-                n[i] = __fdiv_rn((float)((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu), maxf);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 12; i++) {
-                uint4 v = __ldg(p + i);
-                n[4 * i] = __uint_as_float(v.x), n[4 * i + 1] = __uint_as_float(v.y);
-                n[4 * i + 2] = __uint_as_float(v.z), n[4 * i + 3] = __uint_as_float(v.w);
-            }
-        }
+        for (int i = 0; i < 48; i++)
+            if (i < nval) w[i >> 1] |= (uint32_t)q[i] << (16 * (i & 1));
     } else {
-    // ragged edge / unaligned pitch: scalar, bounds-checked
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(row_base) + (size_t)x0 * 3;
 #pragma unroll
-    for (int px = 0; px < 16; px++) {
-        const bool in = (x0 + px) < W;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            float v = 0.0f;
-            if (in) {
-                const uint8_t* q = row_base + ((size_t)(x0 + px) * 3 + c) * (PB / 3);
-                if constexpr (FMT == DMMT_RGB_U8)
-                    v = __fdiv_rn((float)(*q), maxf);
-                else if constexpr (FMT == DMMT_RGB_U16)
-                    v = __fdiv_rn((float)(*reinterpret_cast<const uint16_t*>(q)), maxf);
-                else
-                    v = *reinterpret_cast<const float*>(q);
-            }
-            n[3 * px + c] = v;
-        }
+        for (int i = 0; i < 48; i++)
+            if (i < nval) w[i] = q[i];
     }
-    }
-    if constexpr (FMT != DMMT_RGB_F32_NORM) {
-        // color.rs:62-65: a component above max panics in the reference.  v > max <=> v/max > 1.
-        if (check_max) {
-#pragma unroll
-            for (int i = 0; i < 48; i++) bad |= n[i] > 1.0f;
-        }
+}
+
+// sample i (0..47) of the strip row as the reference's normalised f32 (color.rs:45-53).
+// v / max == fma(v, r_hi, v * r_lo) for every v <= max <= 65535 (exhaustively verified on the host
+// at plan creation, dmmt_api.cu; tools/exhaustive_div.cu checks all max); `exact` selects IEEE division.
+template <int FMT, bool EXACT>
+__device__ __forceinline__ float sample_norm(const uint32_t (&w)[Px<FMT>::kWords], int i, float maxf,
+                                             float r_hi, float r_lo) {
+    if constexpr (FMT == DMMT_RGB_F32_NORM) {
+        return __uint_as_float(w[i]);
+    } else {
+        float v;
+        if constexpr (FMT == DMMT_RGB_U8) v = (float)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+        else v = (float)((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+        if constexpr (EXACT) return __fdiv_rn(v, maxf);
+        else return __fmaf_rn(v, r_hi, __fmul_rn(v, r_lo));
     }
 }
 
@@ -201,17 +192,23 @@ struct K1Args {
     int W, H;                    // original size (pad region is synthesised)
     int mcus_x;                  // MCUs per row
     float maxf;                  // max_value as f32
+    float r_hi, r_lo;            // 1/max split in two f32 (see sample_norm)
     int vec_ok;                  // row pitch and base are 16-byte aligned
     int16_t* coef;               // [n][n_blocks][64]
     size_t coef_img_stride;      // elements between images
     float* dbg;                  // optional pre-quant coefficients [n_blocks][64] natural order (image 0 of launch)
     int check_max;               // samples may exceed max_value: flag DMMT_E_INVALID (color.rs:62-65)
+    uint32_t max_rep;            // max_value replicated into every u8 / u16 lane of a word
     ImgMeta* meta;               // [n] error flags
-    QuantF qf;
+    QuantF qf;                   // divisors
+    QuantF rq_hi, rq_lo;         // 1/q split in two f32 (see quantize)
 };
 
-template <int HR, int VR, int FMT, bool DBG>
-__global__ void __launch_bounds__(K1_THREADS) k1_transform(const __grid_constant__ K1Args a) {
+// EXACT: IEEE divisions everywhere (fallback when the host-side proof of the fast normalisation
+// fails, and for tiles of f32 input that contain non-finite / out-of-range samples).
+template <int HR, int VR, int FMT, bool DBG, bool EXACT>
+__device__ __forceinline__ void k1_tile(const K1Args& a, float4 (*sY)[4][16], float4 (*sCb)[(HR == 2) ? 2 : 4][16],
+                                        float4 (*sCr)[(HR == 2) ? 2 : 4][16], int* s_flag) {
     constexpr int ROWS = 8 * VR;
     constexpr int CCH = (HR == 2) ? 2 : 4;     // 16-byte chunks per strip in a chroma plane row
     constexpr int YPM = HR * VR, BPM = YPM + 2;
@@ -219,10 +216,6 @@ __global__ void __launch_bounds__(K1_THREADS) k1_transform(const __grid_constant
     constexpr int NYU = 32 * VR;               // Y blocks per tile
     constexpr int NCU = (HR == 2) ? 16 : 32;   // blocks per chroma plane per tile
     constexpr int NUNITS = NYU + 2 * NCU;
-
-    __shared__ float4 sY[ROWS][4][16];
-    __shared__ float4 sCb[8][CCH][16];
-    __shared__ float4 sCr[8][CCH][16];
 
     const int tile_x = blockIdx.x, mrow = blockIdx.y, img = blockIdx.z;
     const uint8_t* __restrict__ pix = a.pixels + (size_t)img * a.img_stride_bytes;
@@ -233,18 +226,33 @@ __global__ void __launch_bounds__(K1_THREADS) k1_transform(const __grid_constant
         const int sx = threadIdx.x & 15, sy = threadIdx.x >> 4;  // sy in [0,8)
         const int x0 = tile_x * TILE_W + sx * 16;
         bool bad = false;
-        float cbs[16], crs[16];  // running chroma window sums (x outer, y inner: subsampling.rs:108-122)
-#pragma unroll
+        float cbs[16], crs[16];  // chroma of row 0, then the window sums (x outer, y inner: subsampling.rs:108-122)
+#pragma unroll 1
         for (int r = 0; r < VR; r++) {
             const int yl = sy * VR + r;
             const int y = mrow * ROWS + yl;
-            const bool row_valid = (y < a.H) && (x0 < a.W);
-            float n[48];
-            load_strip_row<FMT>(pix + (size_t)y * pitch, x0, a.W, row_valid, a.vec_ok != 0, a.maxf, n,
-                                a.check_max != 0, bad);
+            uint32_t w[Px<FMT>::kWords];
+            load_strip_row<FMT>(pix + (size_t)y * pitch, x0, a.W, y < a.H, a.vec_ok != 0, w);
+            if constexpr (FMT != DMMT_RGB_F32_NORM) {
+                // color.rs:62-65: a component above max panics in the reference (SIMD-in-word compare)
+                if (a.check_max) {
+#pragma unroll
+                    for (int i = 0; i < Px<FMT>::kWords; i++)
+                        bad |= (FMT == DMMT_RGB_U8 ? __vcmpgtu4(w[i], a.max_rep) : __vcmpgtu2(w[i], a.max_rep)) != 0u;
+                }
+            }
             float yv[16], cb[16], cr[16];
 #pragma unroll
-            for (int p = 0; p < 16; p++) rgb_to_ycbcr(n[3 * p], n[3 * p + 1], n[3 * p + 2], yv[p], cb[p], cr[p]);
+            for (int p = 0; p < 16; p++) {
+                const float nr = sample_norm<FMT, EXACT>(w, 3 * p, a.maxf, a.r_hi, a.r_lo);
+                const float ng = sample_norm<FMT, EXACT>(w, 3 * p + 1, a.maxf, a.r_hi, a.r_lo);
+                const float nb = sample_norm<FMT, EXACT>(w, 3 * p + 2, a.maxf, a.r_hi, a.r_lo);
+                if constexpr (FMT == DMMT_RGB_F32_NORM) {
+                    // the fast quantiser is proven for finite coefficients only: fence off wild input
+                    bad |= !(fabsf(nr) <= 1024.0f) | !(fabsf(ng) <= 1024.0f) | !(fabsf(nb) <= 1024.0f);
+                }
+                rgb_to_ycbcr(nr, ng, nb, yv[p], cb[p], cr[p]);
+            }
 #pragma unroll
             for (int c = 0; c < 4; c++)
                 sY[yl][c][sx] = make_float4(yv[4 * c], yv[4 * c + 1], yv[4 * c + 2], yv[4 * c + 3]);
@@ -253,12 +261,11 @@ __global__ void __launch_bounds__(K1_THREADS) k1_transform(const __grid_constant
                 for (int p = 0; p < 16; p++) cbs[p] = cb[p], crs[p] = cr[p];
             } else {
                 // second row of the window: only reachable for VR == 2.  Window order is
-                // (x,y),(x,y+1),(x+1,y),(x+1,y+1): keep per-column partial sums apart until the
+                // (x,y),(x,y+1),(x+1,y),(x+1,y+1): keep per-column values apart until the
                 // horizontal combine so the additions happen in exactly that order.
 #pragma unroll
                 for (int p = 0; p < 16; p += 2) {
-                    // ((c00 + c10) + c01) + c11
-                    float sb = __fadd_rn(cbs[p], cb[p]);
+                    float sb = __fadd_rn(cbs[p], cb[p]);       // ((c00 + c10) + c01) + c11
                     sb = __fadd_rn(sb, cbs[p + 1]);
                     sb = __fadd_rn(sb, cb[p + 1]);
                     cbs[p >> 1] = sb;
@@ -299,7 +306,10 @@ __global__ void __launch_bounds__(K1_THREADS) k1_transform(const __grid_constant
                 sCr[sy][c][sx] = make_float4(crs[4 * c], crs[4 * c + 1], crs[4 * c + 2], crs[4 * c + 3]);
             }
         }
-        if (bad) atomicCAS(&a.meta[img].error, 0, DMMT_E_INVALID);
+        if (bad) {
+            if constexpr (FMT == DMMT_RGB_F32_NORM) *s_flag = 1;
+            else if (a.check_max) atomicCAS(&a.meta[img].error, 0, DMMT_E_INVALID);
+        }
     }
     __syncthreads();
 
@@ -370,34 +380,63 @@ __global__ void __launch_bounds__(K1_THREADS) k1_transform(const __grid_constant
     }
 
     // quantise (natural-order table) and emit in zig-zag order
+    bool exact = EXACT;
+    if constexpr (FMT == DMMT_RGB_F32_NORM && !EXACT) exact = *s_flag != 0;
     uint32_t w[32];
+    if (exact) {
+#pragma unroll 4
+        for (int i = 0; i < 32; i++) {
+            const int n0 = zz_at(2 * i), n1 = zz_at(2 * i + 1);
+            w[i] = quantize<true>(d[n0], a.qf.q[comp][n0], 0.f, 0.f) |
+                   (quantize<true>(d[n1], a.qf.q[comp][n1], 0.f, 0.f) << 16);
+        }
+    } else {
 #pragma unroll
-    for (int i = 0; i < 32; i++) {
-        const int n0 = zz_at(2 * i), n1 = zz_at(2 * i + 1);
-        const int q0 = quantize(d[n0], a.qf.q[comp][n0]);
-        const int q1 = quantize(d[n1], a.qf.q[comp][n1]);
-        w[i] = ((uint32_t)q0 & 0xFFFFu) | ((uint32_t)q1 << 16);
+        for (int i = 0; i < 32; i++) {
+            const int n0 = zz_at(2 * i), n1 = zz_at(2 * i + 1);
+            const uint32_t q0 = quantize<false>(d[n0], 0.f, a.rq_hi.q[comp][n0], a.rq_lo.q[comp][n0]);
+            const uint32_t q1 = quantize<false>(d[n1], 0.f, a.rq_hi.q[comp][n1], a.rq_lo.q[comp][n1]);
+            w[i] = __byte_perm(q0, q1, 0x5410);
+        }
     }
     uint4* out = reinterpret_cast<uint4*>(a.coef + (size_t)img * a.coef_img_stride + sblk * 64);
 #pragma unroll
     for (int i = 0; i < 8; i++) out[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
 }
 
+template <int HR, int VR, int FMT, bool DBG, bool EXACT>
+__global__ void __launch_bounds__(K1_THREADS, 4) k1_transform(const __grid_constant__ K1Args a) {
+    constexpr int ROWS = 8 * VR;
+    constexpr int CCH = (HR == 2) ? 2 : 4;
+    __shared__ float4 sY[ROWS][4][16];
+    __shared__ float4 sCb[8][CCH][16];
+    __shared__ float4 sCr[8][CCH][16];
+    __shared__ int s_flag;
+    if constexpr (FMT == DMMT_RGB_F32_NORM) {
+        if (threadIdx.x == 0) s_flag = 0;
+        __syncthreads();
+    }
+    k1_tile<HR, VR, FMT, DBG, EXACT>(a, sY, sCb, sCr, &s_flag);
+}
+
 template <int HR, int VR, int FMT>
-cudaError_t launch_fmt(const K1Args& a, dim3 grid, bool dbg, cudaStream_t st) {
-    if (dbg)
-        k1_transform<HR, VR, FMT, true><<<grid, K1_THREADS, 0, st>>>(a);
-    else
-        k1_transform<HR, VR, FMT, false><<<grid, K1_THREADS, 0, st>>>(a);
+cudaError_t launch_fmt(const K1Args& a, dim3 grid, bool dbg, bool exact, cudaStream_t st) {
+    if (dbg) {
+        if (exact) k1_transform<HR, VR, FMT, true, true><<<grid, K1_THREADS, 0, st>>>(a);
+        else k1_transform<HR, VR, FMT, true, false><<<grid, K1_THREADS, 0, st>>>(a);
+    } else {
+        if (exact) k1_transform<HR, VR, FMT, false, true><<<grid, K1_THREADS, 0, st>>>(a);
+        else k1_transform<HR, VR, FMT, false, false><<<grid, K1_THREADS, 0, st>>>(a);
+    }
     return cudaGetLastError();
 }
 
 template <int HR, int VR>
-cudaError_t launch_sub(const K1Args& a, dim3 grid, int fmt, bool dbg, cudaStream_t st) {
+cudaError_t launch_sub(const K1Args& a, dim3 grid, int fmt, bool dbg, bool exact, cudaStream_t st) {
     switch (fmt) {
-        case DMMT_RGB_U8: return launch_fmt<HR, VR, DMMT_RGB_U8>(a, grid, dbg, st);
-        case DMMT_RGB_U16: return launch_fmt<HR, VR, DMMT_RGB_U16>(a, grid, dbg, st);
-        default: return launch_fmt<HR, VR, DMMT_RGB_F32_NORM>(a, grid, dbg, st);
+        case DMMT_RGB_U8: return launch_fmt<HR, VR, DMMT_RGB_U8>(a, grid, dbg, exact, st);
+        case DMMT_RGB_U16: return launch_fmt<HR, VR, DMMT_RGB_U16>(a, grid, dbg, exact, st);
+        default: return launch_fmt<HR, VR, DMMT_RGB_F32_NORM>(a, grid, dbg, exact, st);
     }
 }
 
@@ -405,16 +444,18 @@ cudaError_t launch_sub(const K1Args& a, dim3 grid, int fmt, bool dbg, cudaStream
 
 // Host launcher.  n_images equally sized images; dbg != nullptr selects the variant that also
 // writes the pre-quantisation coefficients of image 0.
-cudaError_t launch_k1(const Geom& g, int fmt, float maxf, int check_max, const QuantF& qf,
-                      const void* d_pixels, size_t img_stride_bytes, int n_images, int16_t* d_coef,
-                      size_t coef_img_stride, float* d_dbg, ImgMeta* meta, cudaStream_t st) {
+cudaError_t launch_k1(const Geom& g, int fmt, const K1Consts& c, int check_max, const void* d_pixels,
+                      size_t img_stride_bytes, int n_images, int16_t* d_coef, size_t coef_img_stride,
+                      float* d_dbg, ImgMeta* meta, cudaStream_t st) {
     K1Args a;
     a.pixels = static_cast<const uint8_t*>(d_pixels);
     a.img_stride_bytes = img_stride_bytes;
     a.W = g.W;
     a.H = g.H;
     a.mcus_x = g.mcus_x;
-    a.maxf = maxf;
+    a.maxf = c.maxf;
+    a.r_hi = c.r_hi;
+    a.r_lo = c.r_lo;
     const size_t pb = (fmt == DMMT_RGB_U8) ? 3 : (fmt == DMMT_RGB_U16 ? 6 : 12);
     a.vec_ok = ((reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0) && (((size_t)g.W * pb) % 16 == 0) &&
                (img_stride_bytes % 16 == 0);
@@ -422,14 +463,50 @@ cudaError_t launch_k1(const Geom& g, int fmt, float maxf, int check_max, const Q
     a.coef_img_stride = coef_img_stride;
     a.dbg = d_dbg;
     a.check_max = check_max;
+    const uint32_t mv = (uint32_t)c.maxf;
+    a.max_rep = fmt == DMMT_RGB_U8 ? (mv & 0xFFu) * 0x01010101u : (mv & 0xFFFFu) * 0x00010001u;
     a.meta = meta;
-    a.qf = qf;
+    a.qf = c.qf;
+    a.rq_hi = c.rq_hi;
+    a.rq_lo = c.rq_lo;
     const int pw = g.mcus_x * 8 * g.hr;
     dim3 grid((pw + TILE_W - 1) / TILE_W, g.mcus_y, n_images);
     const bool dbg = d_dbg != nullptr;
-    if (g.hr == 2 && g.vr == 2) return launch_sub<2, 2>(a, grid, fmt, dbg, st);
-    if (g.hr == 2 && g.vr == 1) return launch_sub<2, 1>(a, grid, fmt, dbg, st);
-    return launch_sub<1, 1>(a, grid, fmt, dbg, st);
+    const bool exact = c.exact != 0;
+    if (g.hr == 2 && g.vr == 2) return launch_sub<2, 2>(a, grid, fmt, dbg, exact, st);
+    if (g.hr == 2 && g.vr == 1) return launch_sub<2, 1>(a, grid, fmt, dbg, exact, st);
+    return launch_sub<1, 1>(a, grid, fmt, dbg, exact, st);
+}
+
+// Builds the per-plan constants and PROVES the fast normalisation for this max value: for every
+// v in [0, max] fma(v, r_hi, v * r_lo) must equal the IEEE quotient v / max (color.rs:45-53);
+// otherwise the plan uses the exact-division kernels.
+void make_k1_consts(int fmt, int max_value, const uint8_t* q_luma, const uint8_t* q_chroma, K1Consts* c) {
+    c->maxf = (float)max_value;
+    const double r = 1.0 / (double)max_value;
+    c->r_hi = (float)r;
+    c->r_lo = (float)(r - (double)c->r_hi);
+    c->exact = 0;
+    if (fmt != DMMT_RGB_F32_NORM) {
+        const int top = fmt == DMMT_RGB_U8 ? 255 : 65535;
+        for (int v = 0; v <= top && v <= max_value; v++) {
+            const volatile float ref = (float)v / c->maxf;
+            const volatile float fast = fmaf((float)v, c->r_hi, (float)v * c->r_lo);
+            if (ref != fast) {
+                c->exact = 1;
+                break;
+            }
+        }
+    }
+    for (int t = 0; t < 2; t++)
+        for (int i = 0; i < 64; i++) {
+            const int q = t ? q_chroma[i] : q_luma[i];
+            c->qf.q[t][i] = (float)q;  // `q as f32` (quantizer.rs:60)
+            const double rq = 1.0 / (double)(q ? q : 1);
+            c->rq_hi.q[t][i] = (float)rq;
+            c->rq_lo.q[t][i] = (float)(rq - (double)c->rq_hi.q[t][i]);
+            if (q == 0) c->exact = 1;  // no preset has a zero divisor; IEEE division handles it like the reference
+        }
 }
 
 }  // namespace dmmt
