@@ -590,9 +590,14 @@ __global__ void __launch_bounds__(EB) k3_pack(const K3Args a) {
 }
 
 // =========================================== K4 ===========================================
-// Byte stuffing as scan + compaction: each thread owns 32 consecutive unstuffed bytes, counts its
-// 0xFF bytes, a block scan + decoupled look-back gives its output offset, then it writes its
-// bytes with the inserted zeros.  The CTA that owns the last byte also writes EOI and the length.
+// Byte stuffing (segment_marker_injector.rs:13-30) as scan + compaction.  A CTA takes 8 KB chunks of
+// the unstuffed scan by ticket (so a waiting chunk's predecessors are always running or done):
+//   1. coalesced 128-bit loads into a padded shared tile, thread = 32 consecutive bytes
+//   2. per-thread 0xFF count (SIMD-in-word compare), CTA scan, decoupled look-back over chunks
+//   3. every thread ORs its bytes (plus the inserted zeros) into a zeroed shared output tile laid out
+//      congruent (mod 16) to the destination, word by word with 64-bit shifts
+//   4. 128-bit copies of the tile to the file, byte stores only at the ragged head/tail
+// The owner of the last byte also writes EOI (encoder.rs:164-167) and the file length.
 struct K4Args {
     const uint8_t* scan;           // [n][scan_img_stride_bytes]
     size_t scan_img_stride_bytes;
@@ -612,14 +617,19 @@ struct K4Args {
     uint8_t or_first_byte;         // previous shard's tail bits, OR-ed into the first owned byte
 };
 
+constexpr int K4_ROW = K4_BYTES_PER_THREAD + 16;              // padded row: conflict-free 128-bit access
+constexpr int K4_OUT_WORDS = (2 * K4_CHUNK + 16 + 16) / 4;    // worst case: every byte is 0xFF
+
 __global__ void __launch_bounds__(K4_THREADS) k4_stuff(const K4Args a) {
+    __shared__ __align__(16) uint8_t s_in[K4_THREADS * K4_ROW];
+    __shared__ __align__(16) uint32_t s_out[K4_OUT_WORDS];
     __shared__ uint32_t s_warp[K4_THREADS / 32 + 1];
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned int s_chunk;
-    const int img = blockIdx.y;
+    const int img = blockIdx.y, tid = threadIdx.x;
     ImgMeta* meta = a.meta + img;
     if (meta->error) {
-        if (blockIdx.x == 0 && threadIdx.x == 0 && a.out_lens) a.out_lens[img] = 0ull;
+        if (blockIdx.x == 0 && tid == 0 && a.out_lens) a.out_lens[img] = 0ull;
         return;
     }
     const unsigned long long total_bytes =
@@ -629,7 +639,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_stuff(const K4Args a) {
     const uint32_t hdr = a.prepend_header ? meta->header_len : 0u;
     uint8_t* out = a.out + (size_t)img * a.out_stride;
     if (n_chunks == 0) {  // nothing owned (possible for a shard); still terminate the file
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (blockIdx.x == 0 && tid == 0) {
             unsigned long long len = hdr;
             if (a.append_eoi) out[len] = 0xFF, out[len + 1] = 0xD9, len += 2;
             meta->out_len = len;
@@ -637,76 +647,140 @@ __global__ void __launch_bounds__(K4_THREADS) k4_stuff(const K4Args a) {
         }
         return;
     }
-    if (threadIdx.x == 0) s_chunk = atomicAdd(&a.ticket[img], 1u);
-    __syncthreads();
-    const uint32_t chunk = s_chunk;
-    if (chunk >= n_chunks) return;
-
     const uint8_t* __restrict__ src = a.scan + (size_t)img * a.scan_img_stride_bytes + a.first_byte;
-    const unsigned long long base = (unsigned long long)chunk * K4_CHUNK + (unsigned long long)threadIdx.x * K4_BYTES_PER_THREAD;
-    // load up to 32 bytes (the scan buffer is padded, reading past total_bytes is safe but masked)
-    uint32_t w[8];
-    int nvalid = 0;
-    if (base < total_bytes) {
-        const unsigned long long rem = total_bytes - base;
-        nvalid = rem < K4_BYTES_PER_THREAD ? (int)rem : K4_BYTES_PER_THREAD;
-        const uint8_t* p = src + base;
-        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-            const uint4 v0 = *reinterpret_cast<const uint4*>(p), v1 = *reinterpret_cast<const uint4*>(p + 16);
+    const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+
+    while (true) {
+        __syncthreads();  // previous iteration's tiles are free
+        if (tid == 0) s_chunk = atomicAdd(&a.ticket[img], 1u);
+        __syncthreads();
+        const uint32_t chunk = s_chunk;
+        if (chunk >= n_chunks) return;
+        const unsigned long long cbase = (unsigned long long)chunk * K4_CHUNK;
+        const uint32_t cvalid = (uint32_t)min((unsigned long long)K4_CHUNK, total_bytes - cbase);
+
+        // 1. stage the chunk (reads may run past cvalid inside the padded scan buffer; masked below)
+#pragma unroll
+        for (int i = 0; i < K4_CHUNK / 16 / K4_THREADS; i++) {
+            const int j = i * K4_THREADS + tid;  // 16-byte unit of the chunk
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if ((uint32_t)j * 16 < cvalid) {
+                const uint8_t* p = src + cbase + (size_t)j * 16;
+                if (src_aligned) v = *reinterpret_cast<const uint4*>(p);
+                else {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        w[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) |
+                               ((uint32_t)p[4 * k + 3] << 24);
+                    v = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            *reinterpret_cast<uint4*>(s_in + (j >> 1) * K4_ROW + (j & 1) * 16) = v;
+        }
+        for (int i = tid; i < K4_OUT_WORDS / 4; i += K4_THREADS) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+
+        // 2. thread = 32 consecutive bytes
+        uint32_t w[8];
+        {
+            const uint4 v0 = *reinterpret_cast<const uint4*>(s_in + tid * K4_ROW);
+            const uint4 v1 = *reinterpret_cast<const uint4*>(s_in + tid * K4_ROW + 16);
             w[0] = v0.x, w[1] = v0.y, w[2] = v0.z, w[3] = v0.w, w[4] = v1.x, w[5] = v1.y, w[6] = v1.z, w[7] = v1.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                w[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) |
-                       ((uint32_t)p[4 * i + 3] << 24);
         }
-        if (base == 0 && a.or_first_byte) w[0] |= a.or_first_byte;
-    } else {
+        const int tbase = tid * K4_BYTES_PER_THREAD;
+        const int nvalid = max(0, min(K4_BYTES_PER_THREAD, (int)cvalid - tbase));
+        if (chunk == 0 && tid == 0 && a.or_first_byte) w[0] |= a.or_first_byte;
+        uint32_t nff = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) w[i] = 0;
-    }
-    uint32_t nff = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        // bytes beyond nvalid are ignored
-        uint32_t eq = __vcmpeq4(w[i], 0xFFFFFFFFu);  // 0xFF per matching byte
-        const int valid_in_word = nvalid - 4 * i;
-        if (valid_in_word < 4) eq &= valid_in_word <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - valid_in_word)));
-        nff += __popc(eq) >> 3;
-    }
-    uint32_t chunk_ff;
-    const uint32_t ff_before = block_exclusive_scan<K4_THREADS>(nff, s_warp, &chunk_ff);
-    if (threadIdx.x == 0)
-        s_prefix = lookback_exclusive(a.lb_state + (size_t)img * a.max_chunks, (int)chunk, chunk_ff);
-    __syncthreads();
-    unsigned long long o = hdr + base + s_prefix + ff_before;
-    if (o + (unsigned long long)nvalid + nff + 2ull > a.out_stride) {
-        // Error::FailedToWriteImageData: the image's slot of the output arena is too small.
-        // Offsets are monotonic, so the owner of the last byte sees the overflow as well.
-        if (nvalid > 0) atomicCAS(&meta->error, 0, DMMT_E_WRITE);
-        if (chunk == n_chunks - 1 && nvalid > 0 && base + nvalid == total_bytes) {
-            meta->out_len = 0ull;
-            if (a.out_lens) a.out_lens[img] = 0ull;
+        for (int i = 0; i < 8; i++) {
+            const int vw = nvalid - 4 * i;  // valid bytes in this word
+            if (vw < 4) w[i] &= vw <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - vw)));  // bytes past the end: 0 (never 0xFF)
+            nff += __popc(__vcmpeq4(w[i], 0xFFFFFFFFu)) >> 3;
         }
-        return;
-    }
+        uint32_t chunk_ff;
+        const uint32_t ff_before = block_exclusive_scan<K4_THREADS>(nff, s_warp, &chunk_ff);
+        if (tid == 0) s_prefix = lookback_exclusive(a.lb_state + (size_t)img * a.max_chunks, (int)chunk, chunk_ff);
+        __syncthreads();
+        const unsigned long long gs = hdr + cbase + s_prefix;  // file offset of the chunk's first output byte
+        const uint32_t n_out = cvalid + chunk_ff;
+        const bool last = chunk == n_chunks - 1;
+        if (gs + n_out + 2ull > a.out_stride) {
+            // Error::FailedToWriteImageData: the image's slot of the output arena is too small
+            if (tid == 0) {
+                atomicCAS(&meta->error, 0, DMMT_E_WRITE);
+                if (last) {
+                    meta->out_len = 0ull;
+                    if (a.out_lens) a.out_lens[img] = 0ull;
+                }
+            }
+            continue;
+        }
+        const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(out) + gs) & 15);  // tile congruent to the file mod 16
+
+        // 3. OR the bytes (little-endian words) into the zeroed tile
+        uint32_t pos = mis + tbase + ff_before;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < 8; i++) {
+            const int vw = nvalid - 4 * i;
+            if (vw <= 0) break;
+            const uint32_t eq = __vcmpeq4(w[i], 0xFFFFFFFFu);
+            unsigned long long v;
+            uint32_t adv;
+            if (eq == 0u) {
+                v = w[i];
+                adv = (uint32_t)min(vw, 4);
+            } else {
+                // spread the bytes: after every 0xFF a 0x00 (already zero in the tile)
+                v = 0ull;
+                adv = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (4 * i + j < nvalid) {
-                const uint8_t v = (uint8_t)(w[i] >> (8 * j));
-                out[o++] = v;
-                if (v == 0xFF) out[o++] = 0x00;
+                for (int b = 0; b < 4; b++) {
+                    if (b < vw) {
+                        const uint32_t byte = (w[i] >> (8 * b)) & 0xFFu;
+                        v |= (unsigned long long)byte << (8 * adv);
+                        adv += byte == 0xFFu ? 2u : 1u;
+                    }
+                }
+            }
+            // v holds up to 8 bytes; shifted to the byte lane of `pos` it spans up to 3 words
+            const uint32_t sh = 8 * (pos & 3);
+            const unsigned long long vs = v << sh;
+            const uint32_t w0 = (uint32_t)vs, w1 = (uint32_t)(vs >> 32);
+            const uint32_t w2 = sh ? (uint32_t)(v >> (64 - sh)) : 0u;
+            if (w0) atomicOr(&s_out[pos >> 2], w0);
+            if (w1) atomicOr(&s_out[(pos >> 2) + 1], w1);
+            if (w2) atomicOr(&s_out[(pos >> 2) + 2], w2);
+            pos += adv;
+        }
+        __syncthreads();
+
+        // 4. tile -> file
+        {
+            const uint8_t* tile = reinterpret_cast<const uint8_t*>(s_out);
+            uint8_t* dst = out + gs - mis;          // 16-byte aligned
+            const uint32_t beg = mis, end = mis + n_out;
+            const uint32_t abeg = (beg + 15) & ~15u, aend = end & ~15u;
+            if (abeg <= aend) {
+                for (uint32_t o = abeg + tid * 16; o < aend; o += K4_THREADS * 16)
+                    *reinterpret_cast<uint4*>(dst + o) = *reinterpret_cast<const uint4*>(tile + o);
+                if (tid < 16) {
+                    const uint32_t o = beg + tid;
+                    if (o < abeg && o < end) dst[o] = tile[o];
+                } else if (tid < 32) {
+                    const uint32_t o = aend + (tid - 16);
+                    if (o >= abeg && o < end) dst[o] = tile[o];
+                }
+            } else {  // the whole chunk output lies inside one 16-byte unit
+                if (tid < 16 && beg + tid < end) dst[beg + tid] = tile[beg + tid];
             }
         }
-    }
-    if (chunk == n_chunks - 1 && nvalid > 0 && base + nvalid == total_bytes) {
-        // owner of the last byte: EOI (encoder.rs:164-167) + file length
-        unsigned long long len = o;
-        if (a.append_eoi) out[len] = 0xFF, out[len + 1] = 0xD9, len += 2;
-        meta->out_len = len;
-        if (a.out_lens) a.out_lens[img] = len;
+        if (last && tid == 0) {
+            unsigned long long len = gs + n_out;
+            if (a.append_eoi) out[len] = 0xFF, out[len + 1] = 0xD9, len += 2;
+            meta->out_len = len;
+            if (a.out_lens) a.out_lens[img] = len;
+        }
     }
 }
 
@@ -860,8 +934,13 @@ cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStre
     K4Args a{h.scan, h.scan_stride_bytes, h.meta, h.lb_state, h.ticket, h.max_chunks, h.out, h.out_stride,
              h.out_lens, h.first_byte, h.n_bytes_override, h.seed_bits, h.prepend_header, h.append_eoi,
              h.or_first_byte};
+    // CTAs take chunks by ticket, so the grid only has to keep the device busy: about 8 CTAs per SM
+    // over all images, never more than the chunks an image can have
+    uint32_t per_image = (uint32_t)((148 * 8 + n - 1) / n);
+    if (per_image < 8) per_image = 8;
     if (grid_chunks == 0) grid_chunks = 1;
-    k4_stuff<<<dim3(grid_chunks, n), K4_THREADS, 0, st>>>(a);
+    if (per_image > grid_chunks) per_image = grid_chunks;
+    k4_stuff<<<dim3(per_image, n), K4_THREADS, 0, st>>>(a);
     return cudaGetLastError();
 }
 
