@@ -123,6 +123,8 @@ static void plan_free_scratch(dmmt_plan* p) {
     (void)cudaFree(p->enc), p->enc = nullptr;
     (void)cudaFree(p->lens), p->lens = nullptr;
     (void)cudaFree(p->scan), p->scan = nullptr;
+    (void)cudaFree(p->tb.tok), p->tb.tok = nullptr;
+    (void)cudaFree(p->tb.ntok), p->tb.ntok = nullptr;
     (void)cudaFree(p->d_lens), p->d_lens = nullptr;
     (void)cudaFree(p->d_offsets), p->d_offsets = nullptr;
     (void)cudaFree(p->d_seed_dc), p->d_seed_dc = nullptr;
@@ -138,6 +140,8 @@ static void plan_free_scratch(dmmt_plan* p) {
 // (re)allocates everything whose size depends on the scan capacity
 static int plan_alloc_scan(dmmt_plan* p, size_t scan_cap_bytes) {
     (void)cudaFree(p->scan), p->scan = nullptr;
+    (void)cudaFree(p->tb.tok), p->tb.tok = nullptr;
+    (void)cudaFree(p->tb.ntok), p->tb.ntok = nullptr;
     (void)cudaFree(p->zero_region), p->zero_region = nullptr;
     (void)cudaFree(p->d_out_own), p->d_out_own = nullptr;
     (void)cudaFree(p->d_dense), p->d_dense = nullptr;
@@ -147,6 +151,14 @@ static int plan_alloc_scan(dmmt_plan* p, size_t scan_cap_bytes) {
     p->out_stride = align_up(1024 + p->scan_cap_bytes + p->scan_cap_bytes / 8 + 64, 16);
     p->max_chunks4 = k4_max_chunks(p->scan_cap_bytes + 8);
     DMMT_CUDA(cudaMalloc(&p->scan, (size_t)p->n * p->scan_stride_words * 4));
+    // token stream: 32 tokens per block by default (the bytes of the coefficient stream); the worst
+    // case is 65 (DC + 63 AC + EOB never coexist with 63 AC, but 65 bounds it) once the scan capacity
+    // has been grown to the worst case as well
+    const bool worst = p->scan_cap_bytes >= (size_t)p->g.n_blocks * 209;
+    p->tb.chunk_cap = tok_blocks_per_chunk() * (worst ? 68u : 32u);
+    p->tb.img_stride_words = (size_t)p->n_chunks3 * p->tb.chunk_cap;
+    DMMT_CUDA(cudaMalloc(&p->tb.tok, (size_t)p->n * p->tb.img_stride_words * 4));
+    DMMT_CUDA(cudaMalloc(&p->tb.ntok, (size_t)p->n * p->n_chunks3 * 4));
     // one zero-initialised region per run: hist | meta | lb3 | lb4 | tk3 | tk4
     const size_t o_hist = 0;
     const size_t o_meta = o_hist + align_up((size_t)p->n * 1024 * sizeof(unsigned int), 16);
@@ -302,7 +314,7 @@ int dmmt_plan_chain(dmmt_plan* p, const void* d_pixels, int n, uint8_t* d_out, u
                         p->coef, p->coef_stride, nullptr, p->meta, st));
     launches += 1;
     DMMT_CUDA(mark(1));
-    DMMT_CUDA(launch_k2(p->g, p->coef, p->coef_stride, n, p->hist, p->meta, nullptr, st));
+    DMMT_CUDA(launch_k2(p->g, p->coef, p->coef_stride, n, p->hist, p->meta, nullptr, p->tb, st));
     launches += 1;
     DMMT_CUDA(mark(2));
     K2bHostArgs b{};
@@ -318,8 +330,7 @@ int dmmt_plan_chain(dmmt_plan* p, const void* d_pixels, int n, uint8_t* d_out, u
     DMMT_CUDA(mark(3));
     const int zero_blocks = (int)std::min<size_t>(std::max<size_t>(p->scan_cap_bytes / 65536, 1), 128);
     DMMT_CUDA(launch_zero_scan(p->scan, p->scan_stride_words, p->meta, n, 0ull, zero_blocks, st));
-    DMMT_CUDA(launch_k3(p->g, p->coef, p->coef_stride, n, p->enc, p->meta, p->lb3, p->tk3, p->scan,
-                        p->scan_stride_words, nullptr, 0ull, 1, st));
+    DMMT_CUDA(launch_k3(p->g, n, p->tb, p->enc, p->meta, p->lb3, p->tk3, p->scan, p->scan_stride_words, 0ull, 1, st));
     launches += 2;
     DMMT_CUDA(mark(4));
     K4HostArgs k{};

@@ -63,6 +63,7 @@ struct dmmt_plan {
     dmmt::EncTables* enc = nullptr;
     dmmt::LenTables* lens = nullptr;
     uint32_t* scan = nullptr;
+    dmmt::TokBuf tb{};                        // K2 -> K3 token stream
     unsigned long long* d_lens = nullptr;     // [n]
     unsigned long long* d_offsets = nullptr;  // [n + 1]
     int16_t* d_seed_dc = nullptr;             // [3] shard predictors

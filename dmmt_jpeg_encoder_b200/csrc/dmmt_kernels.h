@@ -17,9 +17,18 @@ cudaError_t launch_k1(const Geom& g, int fmt, const K1Consts& c, int check_max, 
                       size_t img_stride_bytes, int n_images, int16_t* d_coef, size_t coef_img_stride,
                       float* d_dbg, ImgMeta* meta, cudaStream_t st);
 
-// K2 (k2_entropy.cu)
+// K2 (k2_entropy.cu): tokens of chunk c (256 stream blocks) of image i live at
+// tok + i * img_stride_words + c * chunk_cap; ntok[i * n_chunks + c] of them are valid.
+struct TokBuf {
+    uint32_t* tok;
+    size_t img_stride_words;
+    uint32_t chunk_cap;        // tokens per chunk (multiple of 4)
+    uint32_t* ntok;
+};
+uint32_t tok_blocks_per_chunk();
 cudaError_t launch_k2(const Geom& g, const int16_t* coef, size_t coef_img_stride, int n,
-                      unsigned int* hist, ImgMeta* meta, const int16_t* seed_dc, cudaStream_t st);
+                      unsigned int* hist, ImgMeta* meta, const int16_t* seed_dc, const TokBuf& tb,
+                      cudaStream_t st);
 
 struct K2bHostArgs {
     const unsigned int* hist;         // [n][4][256] u32 local counts
@@ -43,11 +52,9 @@ cudaError_t launch_zero_scan(uint32_t* scan, size_t stride_words, const ImgMeta*
 uint32_t k3_chunks(const Geom& g);
 uint32_t k4_max_chunks(size_t scan_cap_bytes);
 
-cudaError_t launch_k3(const Geom& g, const int16_t* coef, size_t coef_img_stride, int n,
-                      const EncTables* enc, ImgMeta* meta, unsigned long long* lb_state,
-                      unsigned int* ticket, uint32_t* scan, size_t scan_stride_words,
-                      const int16_t* seed_dc, unsigned long long seed_bits, int pad_ones,
-                      cudaStream_t st);
+cudaError_t launch_k3(const Geom& g, int n, const TokBuf& tb, const EncTables* enc, ImgMeta* meta,
+                      unsigned long long* lb_state, unsigned int* ticket, uint32_t* scan, size_t scan_stride_words,
+                      unsigned long long seed_bits, int pad_ones, cudaStream_t st);
 
 struct K4HostArgs {
     const uint8_t* scan;

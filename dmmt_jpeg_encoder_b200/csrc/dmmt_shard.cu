@@ -121,7 +121,7 @@ static int shard_histogram_launch(dmmt_shard* s, const int16_t seed_dc[3]) {
     DMMT_CUDA(cudaSetDevice(p->ctx->device));
     DMMT_CUDA(cudaMemcpyAsync(p->d_seed_dc, seed_dc, 3 * sizeof(int16_t), cudaMemcpyHostToDevice, p->stream));
     s->have_seed = true;
-    DMMT_CUDA(launch_k2(p->g, p->coef, p->coef_stride, 1, p->hist, p->meta, p->d_seed_dc, p->stream));
+    DMMT_CUDA(launch_k2(p->g, p->coef, p->coef_stride, 1, p->hist, p->meta, p->d_seed_dc, p->tb, p->stream));
     p->last_launches += 1;
     DMMT_CUDA(cudaMemcpyAsync(s->h_hist, p->hist, 1024 * sizeof(unsigned int), cudaMemcpyDeviceToHost, p->stream));
     return DMMT_OK;
@@ -180,9 +180,8 @@ static int shard_pack_launch(dmmt_shard* s, uint64_t global_bit_offset, int is_l
     s->seed_bits = global_bit_offset & 7;  // the shard's buffer starts at the byte holding its first bit
     const int zero_blocks = (int)std::min<size_t>(std::max<size_t>(p->scan_cap_bytes / 65536, 1), 1024);
     DMMT_CUDA(launch_zero_scan(p->scan, p->scan_stride_words, p->meta, 1, s->seed_bits, zero_blocks, p->stream));
-    DMMT_CUDA(launch_k3(p->g, p->coef, p->coef_stride, 1, p->enc, p->meta, p->lb3, p->tk3, p->scan,
-                        p->scan_stride_words, s->have_seed ? p->d_seed_dc : nullptr, s->seed_bits, is_last ? 1 : 0,
-                        p->stream));
+    DMMT_CUDA(launch_k3(p->g, 1, p->tb, p->enc, p->meta, p->lb3, p->tk3, p->scan, p->scan_stride_words, s->seed_bits,
+                        is_last ? 1 : 0, p->stream));
     p->last_launches += 2;
     return DMMT_OK;
 }

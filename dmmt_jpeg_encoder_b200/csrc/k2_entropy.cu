@@ -1,17 +1,24 @@
 // k2_entropy.cu -- the entropy stage of the sm_100a encode path:
-//   K2  symbol histogram                     (categorize.rs:153-169, symbol_counting.rs:55-74)
+//   K2  tokenise (DC diff / RLE / category) + symbol histogram
+//                                            (categorize.rs:21-169, symbol_counting.rs:55-74)
 //   K2b Huffman table construction + headers (symbol_counting.rs:85-94, huffman/length_limited.rs:37-134,
 //                                             huffman/encoder.rs:37-157, jpeg/encoder.rs:137-262)
-//   K3  bit-length pass -> decoupled look-back exclusive scan -> bit packing
+//   K3  token bit lengths -> decoupled look-back exclusive scan -> bit packing, one lane per token
 //                                            (jpeg/encoder.rs:264-404, binary_stream.rs:38-96)
 //   K4  0xFF byte stuffing as a scan-compaction (segment_marker_injector.rs:13-30) + EOI
 // All file:line citations are relative to /root/reference/src.
 //
 // Input is K1's coefficient stream: int16 [n_blocks][64], zig-zag inside a block, MCU-interleaved
-// stream order.  K2 and K3 stage 256 blocks (32 KB) per CTA into shared memory with a 16-byte-chunk
-// XOR swizzle (chunk c of block b at slot c ^ (b & 7)), so the coalesced global loads AND the
+// stream order.  K2 stages 256 blocks (32 KB) per CTA into shared memory with a 16-byte-chunk XOR
+// swizzle (chunk c of block b at slot c ^ (b & 7)), so the coalesced global loads AND the
 // thread-per-block 128-bit shared loads are both conflict-free; each thread then walks only the
-// NON-ZERO coefficients of its block (64-bit occupancy mask + ffs).
+// NON-ZERO coefficients of its block (occupancy mask + ffs) ONCE, emitting one 32-bit token per
+// coded coefficient (the reference's CategorizedBlock, categorize.rs:101-104, flattened) and counting
+// symbols.  K3 never sees coefficients: it maps one lane to one token, so the serial, divergent walk
+// happens once per image and the bit packing is perfectly balanced.
+//
+// Token word: bits 0-7 symbol, 8-9 table (T_*), 10-11 number of ZRL (0xF0) codes that precede the
+// symbol (categorize.rs:139-142), 16-31 the category's extra bits.  bits 0-9 index the encoder LUT.
 #include "dmmt_kernels.h"
 
 namespace dmmt {
@@ -44,24 +51,6 @@ __device__ __forceinline__ int s_coef_at(const uint4* s_coef, int b, int pos) {
     return p[pos & 7];
 }
 
-// 64-bit occupancy mask of the thread's own block (bit i set <=> zig-zag coefficient i != 0)
-__device__ __forceinline__ unsigned long long block_mask(const uint4* s_coef, int b) {
-    unsigned long long m = 0ull;
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-        const uint4 v = s_coef[b * 8 + (c ^ (b & 7))];
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        uint32_t bits = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            bits |= ((w[j] & 0xFFFFu) != 0u ? 1u : 0u) << (2 * j);
-            bits |= ((w[j] >> 16) != 0u ? 1u : 0u) << (2 * j + 1);
-        }
-        m |= (unsigned long long)bits << (8 * c);
-    }
-    return m;
-}
-
 // previous block of the same component in stream order (categorize.rs:157-161 runs one DC chain
 // per component over the entangled/stream order); -1 => first block of the component
 __device__ __forceinline__ long long prev_block_same_comp(uint32_t s, int ypm, int bpm) {
@@ -80,73 +69,113 @@ __device__ __forceinline__ void cat_bits(int v, int& cat, uint32_t& bits) {
     bits = (uint32_t)(v > 0 ? v : v - 1) & ((1u << cat) - 1u);
 }
 
-// Walks the tokens of block `b` (thread-private).  emit(table, symbol, extra_bits, extra_len).
-// DC: categorize.rs:159-160; AC: categorize.rs:132-151 (ZRL 0xF0 while run > 15, EOB 0x00).
-template <class Emit>
-__device__ __forceinline__ bool walk_block(const uint4* s_coef, int b, unsigned long long mask,
-                                           int dc_pred, int comp_tables, Emit&& emit) {
-    bool ok = true;
-    {
-        const int dc = s_coef_at(s_coef, b, 0);
-        const int diff = (int)(int16_t)(dc - dc_pred);
-        int cat = 0;
-        uint32_t bits = 0;
-        if (diff != 0) cat_bits(diff, cat, bits);
-        ok &= cat <= 15;
-        emit(comp_tables, cat, bits, cat);
-    }
-    unsigned long long m = mask & ~1ull;
-    int prev = 0;
-    while (m) {
-        const int pos = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        int run = pos - prev - 1;
-        prev = pos;
-        while (run > 15) {
-            emit(comp_tables + 1, 0xF0, 0u, 0);
-            run -= 16;
-        }
-        const int v = s_coef_at(s_coef, b, pos);
-        int cat;
-        uint32_t bits;
-        cat_bits(v, cat, bits);
-        ok &= cat <= 15;
-        emit(comp_tables + 1, (run << 4) | (cat & 15), bits, cat);
-    }
-    if (prev != 63) emit(comp_tables + 1, 0x00, 0u, 0);
-    return ok;
-}
-
 // =========================================== K2 ===========================================
 struct K2Args {
     const int16_t* coef;
     size_t coef_img_stride;
     uint32_t n_blocks;
+    uint32_t n_chunks;
     int ypm, bpm;
     unsigned int* hist;        // [n][4][256]
     ImgMeta* meta;             // [n]
     const int16_t* seed_dc;    // optional [3] predictors for the first block of each component (shards)
+    TokBuf tb;
 };
 
-__global__ void __launch_bounds__(EB) k2_histogram(const K2Args a) {
+// 64-bit occupancy mask of the thread's own block (bit i set <=> zig-zag coefficient i != 0)
+__device__ __forceinline__ void block_mask32(const uint4* s_coef, int b, uint32_t& lo, uint32_t& hi) {
+    uint32_t m[2] = {0u, 0u};
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const uint4 v = s_coef[b * 8 + (c ^ (b & 7))];
+        // per word: 0xFFFF in each non-zero half -> pick one byte of each half of two words -> 4 flag bytes
+        const uint32_t f01 = __byte_perm(__vcmpne2(v.x, 0u), __vcmpne2(v.y, 0u), 0x6420);
+        const uint32_t f23 = __byte_perm(__vcmpne2(v.z, 0u), __vcmpne2(v.w, 0u), 0x6420);
+        // bytes (0xFF / 0x00) -> bits 0..3 via a multiply that sums the masked bytes into the top byte
+        const uint32_t b01 = ((f01 & 0x08040201u) * 0x01010101u) >> 24;
+        const uint32_t b23 = ((f23 & 0x08040201u) * 0x01010101u) >> 24;
+        m[c >> 2] |= (b01 | (b23 << 4)) << (8 * (c & 3));
+    }
+    lo = m[0], hi = m[1];
+}
+
+__device__ __forceinline__ uint32_t make_token(int table, int sym, int nzrl, uint32_t extra) {
+    return (uint32_t)sym | ((uint32_t)table << 8) | ((uint32_t)nzrl << 10) | (extra << 16);
+}
+
+__global__ void __launch_bounds__(EB) k2_tokenize(const K2Args a) {
     __shared__ uint4 s_coef[EB * 8];
     __shared__ unsigned int s_hist[4 * 256];
+    __shared__ uint32_t s_warp[EB / 32 + 1];
     const int img = blockIdx.y;
     const int16_t* __restrict__ coef = a.coef + (size_t)img * a.coef_img_stride;
-    const uint32_t first = blockIdx.x * EB;
+    const uint32_t chunk = blockIdx.x, first = chunk * EB;
     for (int i = threadIdx.x; i < 1024; i += EB) s_hist[i] = 0;
     stage_chunk(s_coef, coef, first, a.n_blocks);
     __syncthreads();
     const uint32_t s = first + threadIdx.x;
-    if (s < a.n_blocks) {
-        const int b = threadIdx.x;
+    const bool active = s < a.n_blocks;
+    const int b = threadIdx.x;
+    uint32_t mlo = 0, mhi = 0, cnt = 0;
+    if (active) {
+        block_mask32(s_coef, b, mlo, mhi);
+        // tokens of the block: DC + one per non-zero AC (ZRLs ride on it) + EOB unless coefficient 63 != 0
+        cnt = 1u + __popc(mlo & ~1u) + __popc(mhi) + ((mhi >> 31) ? 0u : 1u);
+    }
+    uint32_t total;
+    uint32_t off = block_exclusive_scan<EB>(cnt, s_warp, &total);
+    const bool fits = total <= a.tb.chunk_cap;
+    if (threadIdx.x == 0) {
+        a.tb.ntok[(size_t)img * a.n_chunks + chunk] = fits ? total : 0u;
+        if (!fits) atomicCAS(&a.meta[img].error, 0, DMMT_E_OVERFLOW);  // host retries with the worst-case capacity
+    }
+    if (active) {
+        uint32_t* __restrict__ tok = a.tb.tok + (size_t)img * a.tb.img_stride_words + (size_t)chunk * a.tb.chunk_cap;
         const uint32_t m_idx = s / a.bpm, k = s - m_idx * a.bpm;
         const int comp = (int)k < a.ypm ? 0 : ((int)k == a.ypm ? 1 : 2);
+        const int tdc = comp ? T_CDC : T_YDC, tac = tdc + 1;
         const long long pb = prev_block_same_comp(s, a.ypm, a.bpm);
         const int dc_pred = pb >= 0 ? (int)coef[(size_t)pb * 64] : (a.seed_dc ? (int)a.seed_dc[comp] : 0);
-        const unsigned long long mask = block_mask(s_coef, b);
-        const bool ok = walk_block(s_coef, b, mask, dc_pred, comp ? T_CDC : T_YDC,
-                                   [&](int t, int sym, uint32_t, int) { atomicAdd(&s_hist[t * 256 + sym], 1u); });
+        bool ok = true;
+        {   // DC: categorize.rs:159-160
+            const int dc = s_coef_at(s_coef, b, 0);
+            const int diff = (int)(int16_t)(dc - dc_pred);
+            int cat = 0;
+            uint32_t bits = 0;
+            if (diff != 0) cat_bits(diff, cat, bits);
+            ok &= cat <= 15;
+            atomicAdd(&s_hist[tdc * 256 + (cat & 15)], 1u);
+            if (fits) tok[off] = make_token(tdc, cat & 15, 0, bits);
+            ++off;
+        }
+        // AC: categorize.rs:132-151 (run of zeros; 0xF0 per 16 zeros; EOB 0x00 when the tail is zero)
+        int prev = 0;
+        uint32_t nzrl_total = 0;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            uint32_t m = half ? mhi : (mlo & ~1u);
+            while (m) {
+                const int pos = 32 * half + __ffs((int)m) - 1;
+                m &= m - 1;
+                const int run = pos - prev - 1;
+                prev = pos;
+                const int v = s_coef_at(s_coef, b, pos);
+                int cat;
+                uint32_t bits;
+                cat_bits(v, cat, bits);
+                ok &= cat <= 15;
+                const int sym = ((run & 15) << 4) | (cat & 15);
+                nzrl_total += (uint32_t)(run >> 4);
+                atomicAdd(&s_hist[tac * 256 + sym], 1u);
+                if (fits) tok[off] = make_token(tac, sym, run >> 4, bits);
+                ++off;
+            }
+        }
+        if (nzrl_total) atomicAdd(&s_hist[tac * 256 + 0xF0], nzrl_total);
+        if (prev != 63) {
+            atomicAdd(&s_hist[tac * 256], 1u);
+            if (fits) tok[off] = make_token(tac, 0x00, 0, 0u);
+        }
         if (!ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_RANGE);
     }
     __syncthreads();
@@ -427,164 +456,208 @@ __global__ void k_zero_scan(uint32_t* scan, size_t scan_img_stride_words, const 
 
 // =========================================== K3 ===========================================
 struct K3Args {
-    const int16_t* coef;
-    size_t coef_img_stride;
-    uint32_t n_blocks;
     uint32_t n_chunks;
-    int ypm, bpm;
+    TokBuf tb;
     const EncTables* enc;          // [n]
     ImgMeta* meta;                 // [n]
     unsigned long long* lb_state;  // [n][n_chunks]  zero-initialised per run
     unsigned int* ticket;          // [n]            zero-initialised per run
     uint32_t* scan;                // [n][scan_img_stride_words] big-endian bit stream, zero-initialised by k_zero_scan
     size_t scan_img_stride_words;
-    const int16_t* seed_dc;        // optional [3]
     unsigned long long seed_bits;  // bit offset of this shard's first bit inside its first byte/word (< 32)
     int pad_ones;                  // append the 1-padding after the last block (binary_stream.rs:89-96)
 };
 
-// bit sink: OR `len` bits (right-aligned in `code`) at absolute bit position *pos of a big-endian
-// word stream; Shared = 32-bit shared-memory atomics, else global atomics on byte-swapped words.
+// code bits of one token: ZRL codes + symbol code + category bits (encoder.rs:356-404)
+__device__ __forceinline__ uint32_t token_bits(uint32_t t, uint32_t e, uint32_t zl_y, uint32_t zl_c) {
+    const uint32_t nz = (t >> 10) & 3u;
+    return (e >> 16) + (t & 15u) + nz * ((t & 0x200u) ? zl_c : zl_y);
+}
+
+// ORs `len` (<= 32) bits, right-aligned in `v`, at bit position `pos` of a big-endian word stream.
 template <bool Shared>
-struct BitSink {
-    uint32_t* words;
-    unsigned long long acc;  // left-aligned pending bits
-    int fill;                // valid bits in acc (< 32 between appends)
-    unsigned long long wpos;
-    __device__ __forceinline__ void init(uint32_t* w, unsigned long long bitpos) {
-        words = w;
-        acc = 0ull;
-        fill = (int)(bitpos & 31);
-        wpos = bitpos >> 5;
+__device__ __forceinline__ void or_bits(uint32_t* words, unsigned long long pos, uint32_t v, uint32_t len) {
+    const uint32_t sh = (uint32_t)(pos & 31);
+    const unsigned long long x = (unsigned long long)v << (64u - len - sh);  // len + sh <= 63
+    const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+    uint32_t* w = words + (pos >> 5);
+    if (Shared) {
+        if (hi) atomicOr(w, hi);
+        if (lo) atomicOr(w + 1, lo);
+    } else {
+        if (hi) atomicOr(w, bswap32(hi));
+        if (lo) atomicOr(w + 1, bswap32(lo));
     }
-    __device__ __forceinline__ void or_word(uint32_t v) {
-        if (v == 0u) return;
-        if (Shared) atomicOr(&words[wpos], v);
-        else atomicOr(&words[wpos], bswap32(v));
+}
+
+constexpr int K3_RUN = 8;                    // consecutive tokens per lane and step
+constexpr int K3_STEP = 32 * K3_RUN;         // tokens per warp step
+
+// tokens [base, base + 8) into registers; tokens at or beyond `end` read as 0
+__device__ __forceinline__ void load_run(const uint32_t* __restrict__ tok, uint32_t base, uint32_t end,
+                                         uint32_t (&t)[K3_RUN]) {
+    if (base + K3_RUN <= end) {
+        const uint4* p = reinterpret_cast<const uint4*>(tok + base);  // chunk bases and `base` are multiples of 8
+        const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
+        t[0] = v0.x, t[1] = v0.y, t[2] = v0.z, t[3] = v0.w, t[4] = v1.x, t[5] = v1.y, t[6] = v1.z, t[7] = v1.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < K3_RUN; i++) t[i] = (base + i < end) ? __ldg(tok + base + i) : 0u;
     }
-    __device__ __forceinline__ void put(uint32_t code, int len) {  // len <= 31
-        acc |= (unsigned long long)code << (64 - fill - len);
-        fill += len;
-        if (fill >= 32) {
-            or_word((uint32_t)(acc >> 32));
-            ++wpos;
-            acc <<= 32;
-            fill -= 32;
+}
+
+// A warp walks its token range 256 tokens per step, every lane owning a RUN of 8 consecutive tokens
+// (2 x 128-bit loads): the bit lengths are scanned inside the warp and each lane then appends its
+// run into a 64-bit accumulator, ORing finished 32-bit words into the bit buffer -- only the first
+// and last word of a run are shared with the neighbouring lanes, so the atomics rarely collide.
+template <bool Shared>
+__device__ __forceinline__ void emit_range(const uint32_t* __restrict__ tok, uint32_t begin, uint32_t end,
+                                           const uint32_t* s_enc, uint32_t zl_y, uint32_t zl_c, uint32_t* words,
+                                           unsigned long long bitpos) {
+    const int lane = threadIdx.x & 31;
+    for (uint32_t wbase = begin; wbase < end; wbase += K3_STEP) {
+        const uint32_t base = wbase + lane * K3_RUN;
+        uint32_t t[K3_RUN], e[K3_RUN];
+        load_run(tok, base, end, t);
+        uint32_t nb = 0;
+#pragma unroll
+        for (int i = 0; i < K3_RUN; i++) {
+            e[i] = s_enc[t[i] & 0x3FFu];
+            if (base + i < end) nb += token_bits(t[i], e[i], zl_y, zl_c);
         }
-    }
-    __device__ __forceinline__ void flush() {
-        if (fill > 0) or_word((uint32_t)(acc >> 32));
-    }
-};
-
-__global__ void __launch_bounds__(EB) k3_pack(const K3Args a) {
-    __shared__ uint4 s_coef[EB * 8];
-    __shared__ uint32_t s_out[K3_OUT_WORDS];
-    __shared__ uint32_t s_enc[4 * 256];
-    __shared__ uint32_t s_warp[EB / 32 + 1];
-    __shared__ unsigned long long s_prefix;
-    __shared__ unsigned int s_chunk;
-
-    const int img = blockIdx.y;
-    // chunk index in START order, so a waiting CTA's predecessors are always running or done.
-    // Images flagged by K2/K2b (range / capacity) are skipped; the flag is read once per CTA
-    // (K3 itself may set it concurrently, so it must not be re-read per thread).
-    if (threadIdx.x == 0) {
-        const int err = *reinterpret_cast<volatile int32_t*>(&a.meta[img].error);
-        s_chunk = (err == 0 || err == DMMT_E_SYMBOL) ? atomicAdd(&a.ticket[img], 1u) : 0xFFFFFFFFu;
-    }
-    for (int i = threadIdx.x; i < 1024; i += EB) s_enc[i] = a.enc[img].e[i >> 8][i & 255];
-    __syncthreads();
-    const uint32_t chunk = s_chunk;
-    if (chunk == 0xFFFFFFFFu) return;
-    const int16_t* __restrict__ coef = a.coef + (size_t)img * a.coef_img_stride;
-    const uint32_t first = chunk * EB;
-    stage_chunk(s_coef, coef, first, a.n_blocks);
-    __syncthreads();
-
-    const uint32_t s = first + threadIdx.x;
-    const bool active = s < a.n_blocks;
-    const int b = threadIdx.x;
-    unsigned long long mask = 0ull;
-    int dc_pred = 0, tbl = 0;
-    uint32_t nbits = 0;
-    bool ok = true, sym_ok = true;
-    if (active) {
-        const uint32_t m_idx = s / a.bpm, k = s - m_idx * a.bpm;
-        const int comp = (int)k < a.ypm ? 0 : ((int)k == a.ypm ? 1 : 2);
-        tbl = comp ? T_CDC : T_YDC;
-        const long long pb = prev_block_same_comp(s, a.ypm, a.bpm);
-        dc_pred = pb >= 0 ? (int)coef[(size_t)pb * 64] : (a.seed_dc ? (int)a.seed_dc[comp] : 0);
-        mask = block_mask(s_coef, b);
-        // pass 1: bit length of the block
-        ok = walk_block(s_coef, b, mask, dc_pred, tbl, [&](int t, int sym, uint32_t, int extra) {
-            const uint32_t e = s_enc[t * 256 + sym];
-            if ((e >> 16) == 0u) sym_ok = false;  // Error::HuffmanSymbolNotPresentInTranslator
-            nbits += (e >> 16) + (uint32_t)extra;
-        });
-    }
-    uint32_t chunk_bits;
-    const uint32_t off = block_exclusive_scan<EB>(nbits, s_warp, &chunk_bits);
-    if (threadIdx.x == 0)
-        s_prefix = lookback_exclusive(a.lb_state + (size_t)img * a.n_chunks, (int)chunk, chunk_bits);
-    __syncthreads();
-    const unsigned long long g0 = a.seed_bits + s_prefix;        // global bit position of the chunk
-    const unsigned long long gw0 = g0 >> 5;                      // first global word touched
-    const uint32_t phase = (uint32_t)(g0 & 31);
-    const bool last_chunk = (chunk == a.n_chunks - 1);
-    uint32_t pad = 0;
-    if (last_chunk && a.pad_ones) pad = (uint32_t)((8 - ((g0 + chunk_bits) & 7)) & 7);
-    const uint32_t span_bits = phase + chunk_bits + pad;
-    const uint32_t n_words = (span_bits + 31) >> 5;
-    uint32_t* gscan = a.scan + (size_t)img * a.scan_img_stride_words;
-    if (!ok || !sym_ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_SYMBOL);
-
-    if (n_words <= K3_OUT_WORDS) {
-        // fast path: assemble the chunk's bits in shared memory, then one coalesced flush
-        for (uint32_t i = threadIdx.x; i < n_words; i += EB) s_out[i] = 0u;
-        __syncthreads();
-        if (active) {
-            BitSink<true> sink;
-            sink.init(s_out, phase + off);
-            walk_block(s_coef, b, mask, dc_pred, tbl, [&](int t, int sym, uint32_t bits, int extra) {
-                const uint32_t e = s_enc[t * 256 + sym];
-                const int len = (int)(e >> 16);
-                sink.put(((e & 0xFFFFu) << extra) | bits, len + extra);
-            });
-            sink.flush();
+        uint32_t inc = nb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += u;
         }
-        if (pad && threadIdx.x == 0) {
-            BitSink<true> sink;
-            sink.init(s_out, phase + chunk_bits);
-            sink.put((1u << pad) - 1u, (int)pad);
-            sink.flush();
-        }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n_words; i += EB) {
-            const uint32_t v = bswap32(s_out[i]);
-            if (i == 0 || i == n_words - 1) {  // words shared with the neighbouring chunks
-                if (v) atomicOr(&gscan[gw0 + i], v);
-            } else {
-                gscan[gw0 + i] = v;
+        if (nb) {
+            const unsigned long long pos = bitpos + (inc - nb);
+            uint32_t* w = words + (pos >> 5);
+            unsigned long long acc = 0ull;     // left-aligned pending bits
+            int fill = (int)(pos & 31);        // valid bits in acc (< 32 between appends)
+            auto put = [&](uint32_t code, int len) {  // len <= 31
+                acc |= (unsigned long long)code << (64 - fill - len);
+                fill += len;
+                if (fill >= 32) {
+                    const uint32_t v = (uint32_t)(acc >> 32);
+                    if (v) atomicOr(w, Shared ? v : bswap32(v));
+                    ++w;
+                    acc <<= 32;
+                    fill -= 32;
+                }
+            };
+#pragma unroll
+            for (int i = 0; i < K3_RUN; i++) {
+                if (base + i < end) {
+                    uint32_t nz = (t[i] >> 10) & 3u;
+                    if (nz) {  // ZRL codes first (categorize.rs:139-142)
+                        const uint32_t z = s_enc[(t[i] & 0x300u) | 0xF0u];
+                        for (; nz; --nz) put(z & 0xFFFFu, (int)(z >> 16));
+                    }
+                    const int cat = (int)(t[i] & 15u);
+                    put(((e[i] & 0xFFFFu) << cat) | (t[i] >> 16), (int)(e[i] >> 16) + cat);
+                }
+            }
+            if (fill > 0) {
+                const uint32_t v = (uint32_t)(acc >> 32);
+                if (v) atomicOr(w, Shared ? v : bswap32(v));
             }
         }
-    } else {
-        // dense chunk (> 24 KB of code): OR straight into the zeroed global stream
-        if (active) {
-            BitSink<false> sink;
-            sink.init(gscan, g0 + off);
-            walk_block(s_coef, b, mask, dc_pred, tbl, [&](int t, int sym, uint32_t bits, int extra) {
-                const uint32_t e = s_enc[t * 256 + sym];
-                const int len = (int)(e >> 16);
-                sink.put(((e & 0xFFFFu) << extra) | bits, len + extra);
-            });
-            sink.flush();
+        bitpos += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+__global__ void __launch_bounds__(EB) k3_pack(const K3Args a) {
+    __shared__ uint32_t s_out[K3_OUT_WORDS];
+    __shared__ uint32_t s_enc[4 * 256];
+    __shared__ uint32_t s_wsum[EB / 32];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_chunk;
+    __shared__ int s_err;
+
+    const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // Images flagged by K1/K2/K2b (range / capacity) are skipped; the flag is read once per CTA
+    // (K3 itself may set it concurrently, so it must not be re-read later).
+    if (tid == 0) s_err = *reinterpret_cast<volatile int32_t*>(&a.meta[img].error);
+    for (int i = tid; i < 1024; i += EB) s_enc[i] = a.enc[img].e[i >> 8][i & 255];
+    __syncthreads();
+    if (s_err != 0 && s_err != DMMT_E_SYMBOL) return;
+    const uint32_t zl_y = s_enc[T_YAC * 256 + 0xF0] >> 16, zl_c = s_enc[T_CAC * 256 + 0xF0] >> 16;
+    uint32_t* gscan = a.scan + (size_t)img * a.scan_img_stride_words;
+
+    while (true) {
+        // chunks are taken in START order, so a waiting chunk's predecessors are always running or done
+        __syncthreads();
+        if (tid == 0) s_chunk = atomicAdd(&a.ticket[img], 1u);
+        __syncthreads();
+        const uint32_t chunk = s_chunk;
+        if (chunk >= a.n_chunks) return;
+        const uint32_t ntok = a.tb.ntok[(size_t)img * a.n_chunks + chunk];
+        const uint32_t* __restrict__ tok =
+            a.tb.tok + (size_t)img * a.tb.img_stride_words + (size_t)chunk * a.tb.chunk_cap;
+        // contiguous token range of this warp (multiple of 256 so the 128-bit loads stay aligned)
+        const uint32_t per_warp = ((ntok + EB / 32 * K3_STEP - 1) / (EB / 32 * K3_STEP)) * K3_STEP;
+        const uint32_t begin = min(ntok, wid * per_warp), end = min(ntok, begin + per_warp);
+
+        // pass A: bits of the range
+        uint32_t wbits = 0;
+        bool sym_ok = true;
+        for (uint32_t wb = begin; wb < end; wb += K3_STEP) {
+            const uint32_t base = wb + lane * K3_RUN;
+            uint32_t t[K3_RUN];
+            load_run(tok, base, end, t);
+            uint32_t nb = 0;
+#pragma unroll
+            for (int i = 0; i < K3_RUN; i++) {
+                if (base + i < end) {
+                    const uint32_t e = s_enc[t[i] & 0x3FFu];
+                    if ((e >> 16) == 0u) sym_ok = false;  // Error::HuffmanSymbolNotPresentInTranslator
+                    nb += token_bits(t[i], e, zl_y, zl_c);
+                }
+            }
+            wbits += __reduce_add_sync(0xffffffffu, nb);
         }
-        if (pad && threadIdx.x == 0) {
-            BitSink<false> sink;
-            sink.init(gscan, g0 + chunk_bits);
-            sink.put((1u << pad) - 1u, (int)pad);
-            sink.flush();
+        if (!sym_ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_SYMBOL);
+        if (lane == 0) s_wsum[wid] = wbits;
+        __syncthreads();
+        uint32_t wbase = 0, chunk_bits = 0;
+#pragma unroll
+        for (int w = 0; w < EB / 32; w++) {
+            const uint32_t v = s_wsum[w];
+            if (w < wid) wbase += v;
+            chunk_bits += v;
+        }
+        if (tid == 0) s_prefix = lookback_exclusive(a.lb_state + (size_t)img * a.n_chunks, (int)chunk, chunk_bits);
+        __syncthreads();
+        const unsigned long long g0 = a.seed_bits + s_prefix;        // global bit position of the chunk
+        const unsigned long long gw0 = g0 >> 5;                      // first global word touched
+        const uint32_t phase = (uint32_t)(g0 & 31);
+        const bool last_chunk = (chunk == a.n_chunks - 1);
+        uint32_t pad = 0;
+        if (last_chunk && a.pad_ones) pad = (uint32_t)((8 - ((g0 + chunk_bits) & 7)) & 7);
+        const uint32_t span_bits = phase + chunk_bits + pad;
+        const uint32_t n_words = (span_bits + 31) >> 5;
+
+        if (n_words + 1 <= K3_OUT_WORDS) {
+            // the chunk's bits fit the shared bit buffer: assemble there, one coalesced flush
+            for (uint32_t i = tid; i < n_words + 1; i += EB) s_out[i] = 0u;
+            __syncthreads();
+            emit_range<true>(tok, begin, end, s_enc, zl_y, zl_c, s_out, phase + wbase);
+            if (pad && tid == 0) or_bits<true>(s_out, phase + chunk_bits, (1u << pad) - 1u, pad);
+            __syncthreads();
+            for (uint32_t i = tid; i < n_words; i += EB) {
+                const uint32_t v = bswap32(s_out[i]);
+                if (i == 0 || i == n_words - 1) {  // words shared with the neighbouring chunks
+                    if (v) atomicOr(&gscan[gw0 + i], v);
+                } else {
+                    gscan[gw0 + i] = v;
+                }
+            }
+        } else {
+            // dense chunk: OR straight into the zeroed global stream
+            emit_range<false>(tok, begin, end, s_enc, zl_y, zl_c, gscan, g0 + wbase);
+            if (pad && tid == 0) or_bits<false>(gscan, g0 + chunk_bits, (1u << pad) - 1u, pad);
         }
     }
 }
@@ -875,11 +948,13 @@ __global__ void __launch_bounds__(256) k5_copy(const uint8_t* __restrict__ out, 
 
 // ------------------------------------------------------------------------------------------
 // host launchers
+uint32_t k3_chunks(const Geom& g) { return (g.n_blocks + EB - 1) / EB; }
+uint32_t tok_blocks_per_chunk() { return EB; }
 cudaError_t launch_k2(const Geom& g, const int16_t* coef, size_t coef_img_stride, int n, unsigned int* hist,
-                      ImgMeta* meta, const int16_t* seed_dc, cudaStream_t st) {
-    K2Args a{coef, coef_img_stride, g.n_blocks, g.ypm, g.bpm, hist, meta, seed_dc};
-    dim3 grid((g.n_blocks + EB - 1) / EB, n);
-    k2_histogram<<<grid, EB, 0, st>>>(a);
+                      ImgMeta* meta, const int16_t* seed_dc, const TokBuf& tb, cudaStream_t st) {
+    K2Args a{coef, coef_img_stride, g.n_blocks, k3_chunks(g), g.ypm, g.bpm, hist, meta, seed_dc, tb};
+    dim3 grid(a.n_chunks, n);
+    k2_tokenize<<<grid, EB, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -917,16 +992,17 @@ cudaError_t launch_zero_scan(uint32_t* scan, size_t stride_words, const ImgMeta*
     return cudaGetLastError();
 }
 
-uint32_t k3_chunks(const Geom& g) { return (g.n_blocks + EB - 1) / EB; }
 uint32_t k4_max_chunks(size_t scan_cap_bytes) { return (uint32_t)((scan_cap_bytes + K4_CHUNK - 1) / K4_CHUNK); }
 
-cudaError_t launch_k3(const Geom& g, const int16_t* coef, size_t coef_img_stride, int n, const EncTables* enc,
-                      ImgMeta* meta, unsigned long long* lb_state, unsigned int* ticket, uint32_t* scan,
-                      size_t scan_stride_words, const int16_t* seed_dc, unsigned long long seed_bits,
-                      int pad_ones, cudaStream_t st) {
-    K3Args a{coef, coef_img_stride, g.n_blocks, k3_chunks(g), g.ypm, g.bpm, enc, meta, lb_state, ticket,
-             scan, scan_stride_words, seed_dc, seed_bits, pad_ones};
-    k3_pack<<<dim3(a.n_chunks, n), EB, 0, st>>>(a);
+cudaError_t launch_k3(const Geom& g, int n, const TokBuf& tb, const EncTables* enc, ImgMeta* meta,
+                      unsigned long long* lb_state, unsigned int* ticket, uint32_t* scan, size_t scan_stride_words,
+                      unsigned long long seed_bits, int pad_ones, cudaStream_t st) {
+    K3Args a{k3_chunks(g), tb, enc, meta, lb_state, ticket, scan, scan_stride_words, seed_bits, pad_ones};
+    // CTAs take chunks by ticket and keep their encoder LUT in shared memory: about 6 CTAs per SM
+    uint32_t per_image = (uint32_t)((148 * 6 + n - 1) / n);
+    if (per_image < 4) per_image = 4;
+    if (per_image > a.n_chunks) per_image = a.n_chunks;
+    k3_pack<<<dim3(per_image, n), EB, 0, st>>>(a);
     return cudaGetLastError();
 }
 
