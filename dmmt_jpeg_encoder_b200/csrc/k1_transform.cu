@@ -22,6 +22,8 @@
 //            the Arai flow graph without any transpose, IEEE division by the quantiser, round half
 //            away from zero, zig-zag by register renaming, 8 x 16-byte stores of the block.
 // Output: int16 [n_mcus][blocks_per_mcu][64] in MCU-interleaved STREAM order, zig-zag inside a block.
+#include <cstdlib>
+
 #include "dmmt_kernels.h"
 
 namespace dmmt {
@@ -202,6 +204,7 @@ struct K1Args {
     ImgMeta* meta;               // [n] error flags
     QuantF qf;                   // divisors
     QuantF rq_hi, rq_lo;         // 1/q split in two f32 (see quantize)
+    int force_scalar;            // DMMT_K1_SCALAR=1: use the scalar kernel for P420 too (A/B measurements)
 };
 
 // EXACT: IEEE divisions everywhere (fallback when the host-side proof of the fast normalisation
@@ -419,8 +422,272 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform(const __grid_const
     k1_tile<HR, VR, FMT, DBG, EXACT>(a, sY, sCb, sCr, &s_flag);
 }
 
+// ==========================================================================================
+// P420 fast path: the same arithmetic with sm_100a's packed FP32 instructions (FADD2/FMUL2/FFMA2,
+// PTX add/mul/fma.rn.f32x2).  A packed instruction performs two independent IEEE round-to-nearest
+// operations, so results are bit-identical to the scalar path while the kernel needs about a third
+// fewer issue slots, which moves it from issue-bound to FP32-lane-bound (tools/ubench_pipes.cu).
+//
+// CAUTION (verified on ptxas 12.9): ptxas contracts mul.rn.f32x2 feeding add/sub.rn.f32x2 into
+// FFMA2 even under --fmad=false.  Therefore every multiplication whose product feeds an addition
+// is issued as a SCALAR __fmul_rn (never contracted); packed multiplies are only used where the
+// product feeds a multiply, an fma multiplicand/addend, a conversion or a store.
+// tests/test_cuda_parity.py compares every coefficient bit for bit, which would expose a contraction.
+typedef unsigned long long f2;  // two f32 in an aligned register pair: {lo, hi}
+
+__device__ __forceinline__ f2 pk(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo_of(f2 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ float hi_of(f2 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+}
+__device__ __forceinline__ f2 bc(float c) { return pk(c, c); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+    f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {  // ONLY where the product does not feed an add/sub
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// product that feeds an addition: two scalar multiplies (see CAUTION above)
+__device__ __forceinline__ f2 mul2s(f2 a, float c) { return pk(__fmul_rn(lo_of(a), c), __fmul_rn(hi_of(a), c)); }
+
+// arai.rs:29-92 on two independent 8-vectors at once.  -v24 never materialises: with u24 = v14 + v15,
+// v24 = (-v14) - v15 = -u24 exactly, (-v24) * A2 = u24 * A2 and v24 + v26 = v26 - u24 (same roundings).
+// The eight scaled outputs are produced by `out(k, v, S_k)`.
+template <class Out>
+__device__ __forceinline__ void fast_arai2(f2 x0, f2 x1, f2 x2, f2 x3, f2 x4, f2 x5, f2 x6, f2 x7, Out&& out) {
+    const f2 v10 = add2(x0, x7), v11 = add2(x1, x6), v12 = add2(x2, x5), v13 = add2(x3, x4);
+    const f2 v14 = sub2(x3, x4), v15 = sub2(x2, x5), v16 = sub2(x1, x6), v17 = sub2(x0, x7);
+    const f2 v20 = add2(v10, v13), v21 = add2(v11, v12), v22 = sub2(v11, v12), v23 = sub2(v10, v13);
+    const f2 u24 = add2(v14, v15), v25 = add2(v15, v16), v26 = add2(v16, v17);
+    const f2 v30 = add2(v20, v21), v31 = sub2(v20, v21), v32 = add2(v22, v23);
+    const f2 v42 = mul2s(v32, kA1);
+    const f2 t5 = mul2s(sub2(v26, u24), kA5);
+    const f2 v44 = sub2(mul2s(u24, kA2), t5);
+    const f2 v45 = mul2s(v25, kA3);
+    const f2 v46 = sub2(mul2s(v26, kA4), t5);
+    const f2 v52 = add2(v42, v23), v53 = sub2(v23, v42), v55 = add2(v45, v17), v57 = sub2(v17, v45);
+    const f2 v64 = add2(v44, v57), v65 = add2(v55, v46), v66 = sub2(v55, v46), v67 = sub2(v57, v44);
+    out(0, v30, kS0);
+    out(4, v31, kS4);
+    out(2, v52, kS2);
+    out(6, v53, kS6);
+    out(5, v64, kS5);
+    out(1, v65, kS1);
+    out(7, v66, kS7);
+    out(3, v67, kS3);
+}
+
+// raw sample i (0..47) of a strip row as f32 (before normalisation)
+template <int FMT>
+__device__ __forceinline__ float sample_raw(const uint32_t (&w)[Px<FMT>::kWords], int i) {
+    if constexpr (FMT == DMMT_RGB_F32_NORM) return __uint_as_float(w[i]);
+    else if constexpr (FMT == DMMT_RGB_U8) return (float)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+    else return (float)((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(K1_THREADS, 4) k1_transform_p420(const __grid_constant__ K1Args a) {
+    // planes as ROW-PAIR interleaved float4 = {v(x,2j), v(x,2j+1), v(x+1,2j), v(x+1,2j+1)}:
+    //   sY[row pair][16-byte chunk: 2 columns][strip], sC*[row pair][chunk][strip]
+    __shared__ float4 sY[8][8][16];
+    __shared__ float4 sCb[4][4][16];
+    __shared__ float4 sCr[4][4][16];
+    __shared__ int s_flag;
+    constexpr int BPM = 6, MPT = 16, NYU = 64, NCU = 16, NUNITS = 96;
+    if constexpr (FMT == DMMT_RGB_F32_NORM) {
+        if (threadIdx.x == 0) s_flag = 0;
+        __syncthreads();
+    }
+    const int tile_x = blockIdx.x, mrow = blockIdx.y, img = blockIdx.z;
+    const uint8_t* __restrict__ pix = a.pixels + (size_t)img * a.img_stride_bytes;
+    const size_t pitch = (size_t)a.W * Px<FMT>::kBytes;
+
+    // ---------------- phase A: strip = 16 px x 2 rows, both rows packed in one register pair ----------------
+    {
+        const int sx = threadIdx.x & 15, sy = threadIdx.x >> 4;  // sy = row pair of the MCU row
+        const int x0 = tile_x * TILE_W + sx * 16;
+        const int y = mrow * 16 + 2 * sy;
+        uint32_t w0[Px<FMT>::kWords], w1[Px<FMT>::kWords];
+        load_strip_row<FMT>(pix + (size_t)y * pitch, x0, a.W, y < a.H, a.vec_ok != 0, w0);
+        load_strip_row<FMT>(pix + (size_t)(y + 1) * pitch, x0, a.W, y + 1 < a.H, a.vec_ok != 0, w1);
+        bool bad = false;
+        if constexpr (FMT != DMMT_RGB_F32_NORM) {
+            if (a.check_max) {  // color.rs:62-65 (SIMD-in-word compare)
+#pragma unroll
+                for (int i = 0; i < Px<FMT>::kWords; i++) {
+                    bad |= (FMT == DMMT_RGB_U8 ? __vcmpgtu4(w0[i], a.max_rep) : __vcmpgtu2(w0[i], a.max_rep)) != 0u;
+                    bad |= (FMT == DMMT_RGB_U8 ? __vcmpgtu4(w1[i], a.max_rep) : __vcmpgtu2(w1[i], a.max_rep)) != 0u;
+                }
+            }
+        }
+        const f2 rhi = bc(a.r_hi), rlo = bc(a.r_lo);
+        float* cbp = reinterpret_cast<float*>(&sCb[sy >> 1][0][sx]) + (sy & 1);
+        float* crp = reinterpret_cast<float*>(&sCr[sy >> 1][0][sx]) + (sy & 1);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {  // chunk = 2 pixels x 2 rows
+            f2 yy[2], cb[2], cr[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int p = 2 * c + q;
+                f2 n[3];
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    const f2 v = pk(sample_raw<FMT>(w0, 3 * p + ch), sample_raw<FMT>(w1, 3 * p + ch));
+                    if constexpr (FMT == DMMT_RGB_F32_NORM) {
+                        n[ch] = v;
+                        bad |= !(fabsf(lo_of(v)) <= 1024.0f) | !(fabsf(hi_of(v)) <= 1024.0f);
+                    } else {
+                        n[ch] = fma2(v, rhi, mul2(v, rlo));  // v / max, proven per plan (make_k1_consts)
+                    }
+                }
+                // color.rs:75-100, products scalar (they feed additions), sums and final scale packed
+                constexpr float kShift = 128.0f / 255.0f;
+                yy[q] = mul2(add2(add2(add2(mul2s(n[0], 0.299f), mul2s(n[1], 0.587f)), mul2s(n[2], 0.114f)), bc(-kShift)),
+                             bc(255.0f));
+                cb[q] = pk(__fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(lo_of(n[0]), -0.1687f), __fmul_rn(lo_of(n[1]), -0.3312f)),
+                                               __fmul_rn(lo_of(n[2]), 0.5f)), 255.0f),
+                           __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(hi_of(n[0]), -0.1687f), __fmul_rn(hi_of(n[1]), -0.3312f)),
+                                               __fmul_rn(hi_of(n[2]), 0.5f)), 255.0f));
+                cr[q] = pk(__fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(lo_of(n[0]), 0.5f), __fmul_rn(lo_of(n[1]), -0.4186f)),
+                                               __fmul_rn(lo_of(n[2]), -0.0813f)), 255.0f),
+                           __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(hi_of(n[0]), 0.5f), __fmul_rn(hi_of(n[1]), -0.4186f)),
+                                               __fmul_rn(hi_of(n[2]), -0.0813f)), 255.0f));
+            }
+            sY[sy][c][sx] = make_float4(lo_of(yy[0]), hi_of(yy[0]), lo_of(yy[1]), hi_of(yy[1]));
+            // window (x,y),(x,y+1),(x+1,y),(x+1,y+1), f32 sum from 0, / 4 (subsampling.rs:108-122,231-236)
+            const float sb = __fadd_rn(__fadd_rn(__fadd_rn(lo_of(cb[0]), hi_of(cb[0])), lo_of(cb[1])), hi_of(cb[1]));
+            const float sr = __fadd_rn(__fadd_rn(__fadd_rn(lo_of(cr[0]), hi_of(cr[0])), lo_of(cr[1])), hi_of(cr[1]));
+            // chroma column c of the strip: chunk c >> 1, column c & 1; this thread owns half `sy & 1` of each pair
+            cbp[(c >> 1) * 64 + (c & 1) * 2] = __fmul_rn(sb, 0.25f);
+            crp[(c >> 1) * 64 + (c & 1) * 2] = __fmul_rn(sr, 0.25f);
+        }
+        if (bad) {
+            if constexpr (FMT == DMMT_RGB_F32_NORM) s_flag = 1;
+            else if (a.check_max) atomicCAS(&a.meta[img].error, 0, DMMT_E_INVALID);
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase B: unit = one 8x8 block ----------------
+    const int u = threadIdx.x;
+    if (u >= NUNITS) return;
+    int m, k, comp;
+    f2 P[4][8];  // P[j][c] = {d[2j][c], d[2j+1][c]}
+    if (u < NYU) {
+        const int q = u >> 4, sx = u & 15;
+        const int byl = q >> 1, p = q & 1;
+        comp = 0, m = sx, k = byl * 2 + p;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) {
+                const float4 v = sY[4 * byl + j][4 * p + cc][sx];
+                P[j][2 * cc] = pk(v.x, v.y), P[j][2 * cc + 1] = pk(v.z, v.w);
+            }
+    } else {
+        const int v = u - NYU;
+        const int ch = v / NCU, sx = v % NCU;
+        comp = 1, m = sx, k = 4 + ch;
+        const float4(*pl)[4][16] = ch ? sCr : sCb;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) {
+                const float4 t = pl[j][cc][sx];
+                P[j][2 * cc] = pk(t.x, t.y), P[j][2 * cc + 1] = pk(t.z, t.w);
+            }
+    }
+    const int gmx = tile_x * MPT + m;
+    if (gmx >= a.mcus_x) return;  // tile overhangs the padded image
+
+    // row passes on row pairs; the scaled outputs are written as COLUMN pairs C[r][kp] = {d[r][2kp], d[r][2kp+1]}
+    float d[64];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        fast_arai2(P[j][0], P[j][1], P[j][2], P[j][3], P[j][4], P[j][5], P[j][6], P[j][7], [&](int kk, f2 v, float S) {
+            d[16 * j + kk] = __fmul_rn(lo_of(v), S);
+            d[16 * j + 8 + kk] = __fmul_rn(hi_of(v), S);
+        });
+    // column passes on column pairs; outputs feed the quantiser's multiplies, so the scale is packed
+    f2 D[8][4];  // D[r][kp] = {coef[8r + 2kp], coef[8r + 2kp + 1]}
+#pragma unroll
+    for (int kp = 0; kp < 4; kp++)
+        fast_arai2(pk(d[2 * kp], d[2 * kp + 1]), pk(d[8 + 2 * kp], d[8 + 2 * kp + 1]), pk(d[16 + 2 * kp], d[16 + 2 * kp + 1]),
+                   pk(d[24 + 2 * kp], d[24 + 2 * kp + 1]), pk(d[32 + 2 * kp], d[32 + 2 * kp + 1]),
+                   pk(d[40 + 2 * kp], d[40 + 2 * kp + 1]), pk(d[48 + 2 * kp], d[48 + 2 * kp + 1]),
+                   pk(d[56 + 2 * kp], d[56 + 2 * kp + 1]), [&](int r, f2 v, float S) { D[r][kp] = mul2(v, bc(S)); });
+
+    // quantise: x = fma(d, rq_hi, d * rq_lo), round half away from zero, saturate (see quantize<>)
+    bool exact = false;
+    if constexpr (FMT == DMMT_RGB_F32_NORM) exact = s_flag != 0;
+    uint32_t qv[64];
+    if (!exact) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int kp = 0; kp < 4; kp++) {
+                const int n0 = 8 * r + 2 * kp;
+                const f2 x = fma2(D[r][kp], pk(a.rq_hi.q[comp][n0], a.rq_hi.q[comp][n0 + 1]),
+                                  mul2(D[r][kp], pk(a.rq_lo.q[comp][n0], a.rq_lo.q[comp][n0 + 1])));
+                const float xl = lo_of(x), xh = hi_of(x);
+                const f2 h = pk(__int_as_float((__float_as_int(xl) & 0x80000000) | 0x3EFFFFFF),
+                                __int_as_float((__float_as_int(xh) & 0x80000000) | 0x3EFFFFFF));
+                const f2 t = add2(x, h);
+                unsigned short q0, q1;
+                asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(q0) : "f"(lo_of(t)));
+                asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(q1) : "f"(hi_of(t)));
+                qv[n0] = q0, qv[n0 + 1] = q1;
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            const float dv = (i & 1) ? hi_of(D[i >> 3][(i & 7) >> 1]) : lo_of(D[i >> 3][(i & 7) >> 1]);
+            qv[i] = quantize<true>(dv, a.qf.q[comp][i], 0.f, 0.f);
+        }
+    }
+    const size_t sblk = ((size_t)mrow * a.mcus_x + gmx) * BPM + k;  // stream block index
+    uint4* out = reinterpret_cast<uint4*>(a.coef + (size_t)img * a.coef_img_stride + sblk * 64);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[j] = __byte_perm(qv[zz_at(8 * i + 2 * j)], qv[zz_at(8 * i + 2 * j + 1)], 0x5410);
+        out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 template <int HR, int VR, int FMT>
 cudaError_t launch_fmt(const K1Args& a, dim3 grid, bool dbg, bool exact, cudaStream_t st) {
+    if constexpr (HR == 2 && VR == 2) {
+        if (!dbg && !exact && !a.force_scalar) {
+            k1_transform_p420<FMT><<<grid, K1_THREADS, 0, st>>>(a);
+            return cudaGetLastError();
+        }
+    }
     if (dbg) {
         if (exact) k1_transform<HR, VR, FMT, true, true><<<grid, K1_THREADS, 0, st>>>(a);
         else k1_transform<HR, VR, FMT, true, false><<<grid, K1_THREADS, 0, st>>>(a);
@@ -469,6 +736,10 @@ cudaError_t launch_k1(const Geom& g, int fmt, const K1Consts& c, int check_max, 
     a.qf = c.qf;
     a.rq_hi = c.rq_hi;
     a.rq_lo = c.rq_lo;
+    {
+        static const bool scalar = [] { const char* e = getenv("DMMT_K1_SCALAR"); return e && e[0] == '1'; }();
+        a.force_scalar = scalar ? 1 : 0;
+    }
     const int pw = g.mcus_x * 8 * g.hr;
     dim3 grid((pw + TILE_W - 1) / TILE_W, g.mcus_y, n_images);
     const bool dbg = d_dbg != nullptr;
