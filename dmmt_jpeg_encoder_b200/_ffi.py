@@ -120,8 +120,8 @@ def lib():
     """Loads (building first if needed) the CUDA library.  Raises if that is impossible."""
     global _lib
     if _lib is None:
-        path = _build.SO
-        if not os.path.exists(path):
+        path = os.environ.get("DMMT_CUDA_LIB") or _build.SO  # override: A/B builds of the same ABI
+        if path == _build.SO and not os.path.exists(path):
             _build.build()
         L = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():

@@ -509,13 +509,113 @@ __device__ __forceinline__ float sample_raw(const uint32_t (&w)[Px<FMT>::kWords]
     else return (float)((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
 }
 
+template <int COMP>
+__device__ __forceinline__ void quantize_block_packed(const K1Args& a, const f2 (&D)[8][4], unsigned short (&qv)[64]) {
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+        for (int kp = 0; kp < 4; kp++) {
+            const int n0 = 8 * r + 2 * kp;
+            const f2 x = fma2(D[r][kp], pk(a.rq_hi.q[COMP][n0], a.rq_hi.q[COMP][n0 + 1]),
+                              mul2(D[r][kp], pk(a.rq_lo.q[COMP][n0], a.rq_lo.q[COMP][n0 + 1])));
+            const float xl = lo_of(x), xh = hi_of(x);
+            const f2 h = pk(__int_as_float((__float_as_int(xl) & 0x80000000) | 0x3EFFFFFF),
+                            __int_as_float((__float_as_int(xh) & 0x80000000) | 0x3EFFFFFF));
+            const f2 t = add2(x, h);
+            asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(qv[n0]) : "f"(lo_of(t)));
+            asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(qv[n0 + 1]) : "f"(hi_of(t)));
+        }
+}
+
 template <int FMT>
-__global__ void __launch_bounds__(K1_THREADS, 4) k1_transform_p420(const __grid_constant__ K1Args a) {
+__device__ __forceinline__ void p420_phase_b(const K1Args& a, int u, int mcus_here, const float4 (*sY)[8][16],
+                                             const float4 (*sCb)[4][16], const float4 (*sCr)[4][16], uint4* s_stage,
+                                             const int* s_flag_p) {
+    constexpr int BPM = 6, NYU = 64, NCU = 16;
+    int m, k, comp;
+    f2 P[4][8];  // P[j][c] = {d[2j][c], d[2j+1][c]}
+    if (u < NYU) {
+        const int q = u >> 4, sx = u & 15;
+        const int byl = q >> 1, p = q & 1;
+        comp = 0, m = sx, k = byl * 2 + p;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) {
+                const float4 v = sY[4 * byl + j][4 * p + cc][sx];
+                P[j][2 * cc] = pk(v.x, v.y), P[j][2 * cc + 1] = pk(v.z, v.w);
+            }
+    } else {
+        const int v = u - NYU;
+        const int ch = v / NCU, sx = v % NCU;
+        comp = 1, m = sx, k = 4 + ch;
+        const float4(*pl)[4][16] = ch ? sCr : sCb;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) {
+                const float4 t = pl[j][cc][sx];
+                P[j][2 * cc] = pk(t.x, t.y), P[j][2 * cc + 1] = pk(t.z, t.w);
+            }
+    }
+    if (m >= mcus_here) return;  // tile overhangs the padded image
+
+    // row passes on row pairs; the scaled outputs are written as COLUMN pairs C[r][kp] = {d[r][2kp], d[r][2kp+1]}
+    float d[64];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        fast_arai2(P[j][0], P[j][1], P[j][2], P[j][3], P[j][4], P[j][5], P[j][6], P[j][7], [&](int kk, f2 v, float S) {
+            d[16 * j + kk] = __fmul_rn(lo_of(v), S);
+            d[16 * j + 8 + kk] = __fmul_rn(hi_of(v), S);
+        });
+    // column passes on column pairs; outputs feed the quantiser's multiplies, so the scale is packed
+    f2 D[8][4];  // D[r][kp] = {coef[8r + 2kp], coef[8r + 2kp + 1]}
+#pragma unroll
+    for (int kp = 0; kp < 4; kp++)
+        fast_arai2(pk(d[2 * kp], d[2 * kp + 1]), pk(d[8 + 2 * kp], d[8 + 2 * kp + 1]), pk(d[16 + 2 * kp], d[16 + 2 * kp + 1]),
+                   pk(d[24 + 2 * kp], d[24 + 2 * kp + 1]), pk(d[32 + 2 * kp], d[32 + 2 * kp + 1]),
+                   pk(d[40 + 2 * kp], d[40 + 2 * kp + 1]), pk(d[48 + 2 * kp], d[48 + 2 * kp + 1]),
+                   pk(d[56 + 2 * kp], d[56 + 2 * kp + 1]), [&](int r, f2 v, float S) { D[r][kp] = mul2(v, bc(S)); });
+
+    // quantise: x = fma(d, rq_hi, d * rq_lo), round half away from zero, saturate (see quantize<>).
+    // `comp` is warp-uniform (warps 0-1 luma, warp 2 chroma), so the table is selected by a uniform
+    // branch and its entries become uniform-register operands.
+    bool exact = false;
+    if constexpr (FMT == DMMT_RGB_F32_NORM) exact = *s_flag_p != 0;
+    unsigned short qv[64];
+    if (!exact) {
+        if (comp == 0) quantize_block_packed<0>(a, D, qv);
+        else quantize_block_packed<1>(a, D, qv);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 64; i++) {
+            const float dv = (i & 1) ? hi_of(D[i >> 3][(i & 7) >> 1]) : lo_of(D[i >> 3][(i & 7) >> 1]);
+            qv[i] = (unsigned short)quantize<true>(dv, a.qf.q[comp][i], 0.f, 0.f);
+        }
+    }
+    // zig-zag by register renaming, two i16 per word, staged so that the tile leaves as ONE contiguous,
+    // coalesced 12 KB run (16 MCUs x 6 blocks x 128 B in stream order)
+    {
+        const int slot = m * BPM + k;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                asm("mov.b32 %0, {%1, %2};" : "=r"(w[j]) : "h"(qv[zz_at(8 * i + 2 * j)]), "h"(qv[zz_at(8 * i + 2 * j + 1)]));
+            s_stage[slot * 8 + (i ^ (slot & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(K1_THREADS, 5) k1_transform_p420(const __grid_constant__ K1Args a) {
     // planes as ROW-PAIR interleaved float4 = {v(x,2j), v(x,2j+1), v(x+1,2j), v(x+1,2j+1)}:
     //   sY[row pair][16-byte chunk: 2 columns][strip], sC*[row pair][chunk][strip]
     __shared__ float4 sY[8][8][16];
     __shared__ float4 sCb[4][4][16];
     __shared__ float4 sCr[4][4][16];
+    __shared__ uint4 s_stage[96 * 8];
     __shared__ int s_flag;
     constexpr int BPM = 6, MPT = 16, NYU = 64, NCU = 16, NUNITS = 96;
     if constexpr (FMT == DMMT_RGB_F32_NORM) {
@@ -556,6 +656,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform_p420(const __grid_
                 f2 n[3];
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++) {
+                    // (u8 -> f32 stays on I2F: the PRMT 0x4B000000 + FADD2 trick was measured 7 % slower, the
+                    // quarter-rate conversion pipe is not what limits this kernel)
                     const f2 v = pk(sample_raw<FMT>(w0, 3 * p + ch), sample_raw<FMT>(w1, 3 * p + ch));
                     if constexpr (FMT == DMMT_RGB_F32_NORM) {
                         n[ch] = v;
@@ -568,14 +670,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform_p420(const __grid_
                 constexpr float kShift = 128.0f / 255.0f;
                 yy[q] = mul2(add2(add2(add2(mul2s(n[0], 0.299f), mul2s(n[1], 0.587f)), mul2s(n[2], 0.114f)), bc(-kShift)),
                              bc(255.0f));
-                cb[q] = pk(__fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(lo_of(n[0]), -0.1687f), __fmul_rn(lo_of(n[1]), -0.3312f)),
-                                               __fmul_rn(lo_of(n[2]), 0.5f)), 255.0f),
-                           __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(hi_of(n[0]), -0.1687f), __fmul_rn(hi_of(n[1]), -0.3312f)),
-                                               __fmul_rn(hi_of(n[2]), 0.5f)), 255.0f));
-                cr[q] = pk(__fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(lo_of(n[0]), 0.5f), __fmul_rn(lo_of(n[1]), -0.4186f)),
-                                               __fmul_rn(lo_of(n[2]), -0.0813f)), 255.0f),
-                           __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(hi_of(n[0]), 0.5f), __fmul_rn(hi_of(n[1]), -0.4186f)),
-                                               __fmul_rn(hi_of(n[2]), -0.0813f)), 255.0f));
+                cb[q] = mul2(add2(add2(mul2s(n[0], -0.1687f), mul2s(n[1], -0.3312f)), mul2s(n[2], 0.5f)), bc(255.0f));
+                cr[q] = mul2(add2(add2(mul2s(n[0], 0.5f), mul2s(n[1], -0.4186f)), mul2s(n[2], -0.0813f)), bc(255.0f));
             }
             sY[sy][c][sx] = make_float4(lo_of(yy[0]), hi_of(yy[0]), lo_of(yy[1]), hi_of(yy[1]));
             // window (x,y),(x,y+1),(x+1,y),(x+1,y+1), f32 sum from 0, / 4 (subsampling.rs:108-122,231-236)
@@ -594,92 +690,20 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform_p420(const __grid_
 
     // ---------------- phase B: unit = one 8x8 block ----------------
     const int u = threadIdx.x;
-    if (u >= NUNITS) return;
-    int m, k, comp;
-    f2 P[4][8];  // P[j][c] = {d[2j][c], d[2j+1][c]}
-    if (u < NYU) {
-        const int q = u >> 4, sx = u & 15;
-        const int byl = q >> 1, p = q & 1;
-        comp = 0, m = sx, k = byl * 2 + p;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-#pragma unroll
-            for (int cc = 0; cc < 4; cc++) {
-                const float4 v = sY[4 * byl + j][4 * p + cc][sx];
-                P[j][2 * cc] = pk(v.x, v.y), P[j][2 * cc + 1] = pk(v.z, v.w);
-            }
-    } else {
-        const int v = u - NYU;
-        const int ch = v / NCU, sx = v % NCU;
-        comp = 1, m = sx, k = 4 + ch;
-        const float4(*pl)[4][16] = ch ? sCr : sCb;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-#pragma unroll
-            for (int cc = 0; cc < 4; cc++) {
-                const float4 t = pl[j][cc][sx];
-                P[j][2 * cc] = pk(t.x, t.y), P[j][2 * cc + 1] = pk(t.z, t.w);
-            }
-    }
-    const int gmx = tile_x * MPT + m;
-    if (gmx >= a.mcus_x) return;  // tile overhangs the padded image
-
-    // row passes on row pairs; the scaled outputs are written as COLUMN pairs C[r][kp] = {d[r][2kp], d[r][2kp+1]}
-    float d[64];
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-        fast_arai2(P[j][0], P[j][1], P[j][2], P[j][3], P[j][4], P[j][5], P[j][6], P[j][7], [&](int kk, f2 v, float S) {
-            d[16 * j + kk] = __fmul_rn(lo_of(v), S);
-            d[16 * j + 8 + kk] = __fmul_rn(hi_of(v), S);
-        });
-    // column passes on column pairs; outputs feed the quantiser's multiplies, so the scale is packed
-    f2 D[8][4];  // D[r][kp] = {coef[8r + 2kp], coef[8r + 2kp + 1]}
-#pragma unroll
-    for (int kp = 0; kp < 4; kp++)
-        fast_arai2(pk(d[2 * kp], d[2 * kp + 1]), pk(d[8 + 2 * kp], d[8 + 2 * kp + 1]), pk(d[16 + 2 * kp], d[16 + 2 * kp + 1]),
-                   pk(d[24 + 2 * kp], d[24 + 2 * kp + 1]), pk(d[32 + 2 * kp], d[32 + 2 * kp + 1]),
-                   pk(d[40 + 2 * kp], d[40 + 2 * kp + 1]), pk(d[48 + 2 * kp], d[48 + 2 * kp + 1]),
-                   pk(d[56 + 2 * kp], d[56 + 2 * kp + 1]), [&](int r, f2 v, float S) { D[r][kp] = mul2(v, bc(S)); });
-
-    // quantise: x = fma(d, rq_hi, d * rq_lo), round half away from zero, saturate (see quantize<>)
-    bool exact = false;
-    if constexpr (FMT == DMMT_RGB_F32_NORM) exact = s_flag != 0;
-    uint32_t qv[64];
-    if (!exact) {
-#pragma unroll
-        for (int r = 0; r < 8; r++)
-#pragma unroll
-            for (int kp = 0; kp < 4; kp++) {
-                const int n0 = 8 * r + 2 * kp;
-                const f2 x = fma2(D[r][kp], pk(a.rq_hi.q[comp][n0], a.rq_hi.q[comp][n0 + 1]),
-                                  mul2(D[r][kp], pk(a.rq_lo.q[comp][n0], a.rq_lo.q[comp][n0 + 1])));
-                const float xl = lo_of(x), xh = hi_of(x);
-                const f2 h = pk(__int_as_float((__float_as_int(xl) & 0x80000000) | 0x3EFFFFFF),
-                                __int_as_float((__float_as_int(xh) & 0x80000000) | 0x3EFFFFFF));
-                const f2 t = add2(x, h);
-                unsigned short q0, q1;
-                asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(q0) : "f"(lo_of(t)));
-                asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(q1) : "f"(hi_of(t)));
-                qv[n0] = q0, qv[n0 + 1] = q1;
-            }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 64; i++) {
-            const float dv = (i & 1) ? hi_of(D[i >> 3][(i & 7) >> 1]) : lo_of(D[i >> 3][(i & 7) >> 1]);
-            qv[i] = quantize<true>(dv, a.qf.q[comp][i], 0.f, 0.f);
+    const int mcus_here = min(MPT, a.mcus_x - tile_x * MPT);  // MCUs of this tile inside the padded image
+    if (u < NUNITS) p420_phase_b<FMT>(a, u, mcus_here, sY, sCb, sCr, s_stage, &s_flag);
+    __syncthreads();
+    // ---------------- phase C: the tile's blocks, contiguous in stream order ----------------
+    {
+        const size_t sblk0 = ((size_t)mrow * a.mcus_x + (size_t)tile_x * MPT) * BPM;
+        uint4* out = reinterpret_cast<uint4*>(a.coef + (size_t)img * a.coef_img_stride + sblk0 * 64);
+        const int n16 = mcus_here * BPM * 8;
+        for (int i = threadIdx.x; i < n16; i += K1_THREADS) {
+            const int slot = i >> 3;
+            out[i] = s_stage[slot * 8 + ((i & 7) ^ (slot & 7))];
         }
     }
-    const size_t sblk = ((size_t)mrow * a.mcus_x + gmx) * BPM + k;  // stream block index
-    uint4* out = reinterpret_cast<uint4*>(a.coef + (size_t)img * a.coef_img_stride + sblk * 64);
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        uint32_t w[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) w[j] = __byte_perm(qv[zz_at(8 * i + 2 * j)], qv[zz_at(8 * i + 2 * j + 1)], 0x5410);
-        out[i] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
 }
-
 template <int HR, int VR, int FMT>
 cudaError_t launch_fmt(const K1Args& a, dim3 grid, bool dbg, bool exact, cudaStream_t st) {
     if constexpr (HR == 2 && VR == 2) {
