@@ -39,24 +39,41 @@ def photo(index: int, h: int, w: int, device="cpu") -> torch.Tensor:
     return v.clamp_(0, 255).to(torch.uint8)
 
 
-def grad(h: int, w: int, device="cpu") -> torch.Tensor:
+def grad(h: int, w: int, device="cpu", y0: int = 0) -> torch.Tensor:
+    """rows [y0, y0 + h) of the pattern (position-pure, so MCU-row shards can generate their own rows)"""
     dev = torch.device(device)
-    y = torch.arange(h, dtype=torch.int64, device=dev).view(h, 1)
+    y = torch.arange(y0, y0 + h, dtype=torch.int64, device=dev).view(h, 1)
     x = torch.arange(w, dtype=torch.int64, device=dev).view(1, w)
     return torch.stack([(x + 8 * y) & 255, (2 * x + 3 * y + 85) & 255, (5 * x + y + 170) & 255], -1).to(torch.uint8)
 
 
-def uniform(index: int, h: int, w: int, device="cpu") -> torch.Tensor:
+def uniform(index: int, h: int, w: int, device="cpu", y0: int = 0) -> torch.Tensor:
     dev = torch.device(device)
-    flat = torch.arange(h * w * 3, dtype=torch.int64, device=dev).view(h, w, 3)
+    flat = torch.arange(y0 * w * 3, (y0 + h) * w * 3, dtype=torch.int64, device=dev).view(h, w, 3)
     return (_hash32(flat + (1234 + index) * 2654435761) & 0xFF).to(torch.uint8)
 
 
-def make(kind: str, index: int, h: int, w: int, device="cpu") -> torch.Tensor:
+def smooth(index: int, h: int, w: int, device="cpu", y0: int = 0) -> torch.Tensor:
+    """Position-pure photo-like rows [y0, y0 + h): three incommensurate integer ramps per channel plus
+    +-32 levels of hash noise (about 0.11 B/px at 4:2:0); used for the MCU-row sharded workload."""
+    dev = torch.device(device)
+    y = torch.arange(y0, y0 + h, dtype=torch.int64, device=dev).view(h, 1, 1)
+    x = torch.arange(w, dtype=torch.int64, device=dev).view(1, w, 1)
+    c = torch.arange(3, dtype=torch.int64, device=dev).view(1, 1, 3)
+    tri = lambda t, p: ((t % (2 * p)) - p).abs()                     # triangle wave 0..p
+    v = (tri(x * (3 + c) + y * 2, 1531) * 255) // 1531 + (tri(y * (5 + 2 * c) + x, 977) * 255) // 977
+    v = v // 2 + ((_hash32((y * w + x) * 3 + c + (1234 + index) * 2654435761) & 63) - 32)
+    return v.clamp_(0, 255).to(torch.uint8)
+
+
+def make(kind: str, index: int, h: int, w: int, device="cpu", y0: int = 0) -> torch.Tensor:
     if kind == "photo":
+        assert y0 == 0, "photo is not position-pure (blur wraps around the whole frame)"
         return photo(index, h, w, device)
     if kind == "grad":
-        return grad(h, w, device)
+        return grad(h, w, device, y0)
     if kind == "uniform":
-        return uniform(index, h, w, device)
+        return uniform(index, h, w, device, y0)
+    if kind == "smooth":
+        return smooth(index, h, w, device, y0)
     raise ValueError(kind)
