@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--kind", default="photo", choices=["photo", "grad", "uniform"])
-    ap.add_argument("--sub-batch", type=int, default=32)
+    ap.add_argument("--sub-batch", type=int, default=64)
     ap.add_argument("--depth", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=64, help="images of the batch timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")

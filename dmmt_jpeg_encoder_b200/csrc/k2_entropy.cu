@@ -26,7 +26,6 @@ namespace dmmt {
 namespace {
 
 constexpr int EB = 256;           // blocks per CTA chunk in K2/K3 (= threads)
-constexpr int K3_OUT_WORDS = 2560;  // 10 KB shared bit buffer per K3 chunk (avg 40 B per block)
 constexpr int K4_THREADS = 256;
 constexpr int K4_BYTES_PER_THREAD = 32;
 constexpr int K4_CHUNK = K4_THREADS * K4_BYTES_PER_THREAD;  // 8 KB of unstuffed scan per CTA
@@ -510,11 +509,16 @@ __device__ __forceinline__ void load_run(const uint32_t* __restrict__ tok, uint3
 // (2 x 128-bit loads): the bit lengths are scanned inside the warp and each lane then appends its
 // run into a 64-bit accumulator, ORing finished 32-bit words into the bit buffer -- only the first
 // and last word of a run are shared with the neighbouring lanes, so the atomics rarely collide.
+//   Shared: `words` is shared memory (host byte order), else the global big-endian stream.
+//   cap_bits: emission stops (counting continues) once the range would run past it -> *overflow.
+// Returns the bits of the whole range.
 template <bool Shared>
-__device__ __forceinline__ void emit_range(const uint32_t* __restrict__ tok, uint32_t begin, uint32_t end,
-                                           const uint32_t* s_enc, uint32_t zl_y, uint32_t zl_c, uint32_t* words,
-                                           unsigned long long bitpos) {
+__device__ __forceinline__ unsigned long long emit_range(const uint32_t* __restrict__ tok, uint32_t begin,
+                                                         uint32_t end, const uint32_t* s_enc, uint32_t zl_y,
+                                                         uint32_t zl_c, uint32_t* words, unsigned long long bitpos,
+                                                         unsigned long long cap_bits, bool& sym_ok, bool& overflow) {
     const int lane = threadIdx.x & 31;
+    const unsigned long long start = bitpos;
     for (uint32_t wbase = begin; wbase < end; wbase += K3_STEP) {
         const uint32_t base = wbase + lane * K3_RUN;
         uint32_t t[K3_RUN], e[K3_RUN];
@@ -523,7 +527,10 @@ __device__ __forceinline__ void emit_range(const uint32_t* __restrict__ tok, uin
 #pragma unroll
         for (int i = 0; i < K3_RUN; i++) {
             e[i] = s_enc[t[i] & 0x3FFu];
-            if (base + i < end) nb += token_bits(t[i], e[i], zl_y, zl_c);
+            if (base + i < end) {
+                if ((e[i] >> 16) == 0u) sym_ok = false;  // Error::HuffmanSymbolNotPresentInTranslator
+                nb += token_bits(t[i], e[i], zl_y, zl_c);
+            }
         }
         uint32_t inc = nb;
 #pragma unroll
@@ -531,7 +538,9 @@ __device__ __forceinline__ void emit_range(const uint32_t* __restrict__ tok, uin
             const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc += u;
         }
-        if (nb) {
+        const uint32_t step_bits = __shfl_sync(0xffffffffu, inc, 31);
+        if (bitpos + step_bits > cap_bits) overflow = true;  // warp-uniform
+        if (nb && !overflow) {
             const unsigned long long pos = bitpos + (inc - nb);
             uint32_t* w = words + (pos >> 5);
             unsigned long long acc = 0ull;     // left-aligned pending bits
@@ -564,17 +573,20 @@ __device__ __forceinline__ void emit_range(const uint32_t* __restrict__ tok, uin
                 if (v) atomicOr(w, Shared ? v : bswap32(v));
             }
         }
-        bitpos += __shfl_sync(0xffffffffu, inc, 31);
+        bitpos += step_bits;
     }
+    return bitpos - start;
 }
 
+constexpr int K3_WBUF_WORDS = 640;  // per-warp private bit buffer: 20480 bits (2.5 KB), 20 KB per CTA
+
 __global__ void __launch_bounds__(EB) k3_pack(const K3Args a) {
-    __shared__ uint32_t s_out[K3_OUT_WORDS];
+    __shared__ __align__(16) uint32_t s_wbuf[EB / 32][K3_WBUF_WORDS];
     __shared__ uint32_t s_enc[4 * 256];
-    __shared__ uint32_t s_wsum[EB / 32];
+    __shared__ unsigned long long s_wsum[EB / 32];
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned int s_chunk;
-    __shared__ int s_err;
+    __shared__ int s_err, s_ovf;
 
     const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // Images flagged by K1/K2/K2b (range / capacity) are skipped; the flag is read once per CTA
@@ -585,11 +597,12 @@ __global__ void __launch_bounds__(EB) k3_pack(const K3Args a) {
     if (s_err != 0 && s_err != DMMT_E_SYMBOL) return;
     const uint32_t zl_y = s_enc[T_YAC * 256 + 0xF0] >> 16, zl_c = s_enc[T_CAC * 256 + 0xF0] >> 16;
     uint32_t* gscan = a.scan + (size_t)img * a.scan_img_stride_words;
+    uint32_t* wbuf = s_wbuf[wid];
 
     while (true) {
         // chunks are taken in START order, so a waiting chunk's predecessors are always running or done
         __syncthreads();
-        if (tid == 0) s_chunk = atomicAdd(&a.ticket[img], 1u);
+        if (tid == 0) s_chunk = atomicAdd(&a.ticket[img], 1u), s_ovf = 0;
         __syncthreads();
         const uint32_t chunk = s_chunk;
         if (chunk >= a.n_chunks) return;
@@ -600,64 +613,56 @@ __global__ void __launch_bounds__(EB) k3_pack(const K3Args a) {
         const uint32_t per_warp = ((ntok + EB / 32 * K3_STEP - 1) / (EB / 32 * K3_STEP)) * K3_STEP;
         const uint32_t begin = min(ntok, wid * per_warp), end = min(ntok, begin + per_warp);
 
-        // pass A: bits of the range
-        uint32_t wbits = 0;
-        bool sym_ok = true;
-        for (uint32_t wb = begin; wb < end; wb += K3_STEP) {
-            const uint32_t base = wb + lane * K3_RUN;
-            uint32_t t[K3_RUN];
-            load_run(tok, base, end, t);
-            uint32_t nb = 0;
+        // ONE pass over the tokens: the warp packs its range into its private buffer from bit 0;
+        // where the range starts in the scan is only known after the look-back below
 #pragma unroll
-            for (int i = 0; i < K3_RUN; i++) {
-                if (base + i < end) {
-                    const uint32_t e = s_enc[t[i] & 0x3FFu];
-                    if ((e >> 16) == 0u) sym_ok = false;  // Error::HuffmanSymbolNotPresentInTranslator
-                    nb += token_bits(t[i], e, zl_y, zl_c);
-                }
-            }
-            wbits += __reduce_add_sync(0xffffffffu, nb);
-        }
+        for (int i = 0; i < K3_WBUF_WORDS / 128; i++)
+            reinterpret_cast<uint4*>(wbuf)[i * 32 + lane] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        bool sym_ok = true, ovf = false;
+        const unsigned long long wbits =
+            emit_range<true>(tok, begin, end, s_enc, zl_y, zl_c, wbuf, 0ull, (unsigned long long)K3_WBUF_WORDS * 32 - 64, sym_ok, ovf);
         if (!sym_ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_SYMBOL);
-        if (lane == 0) s_wsum[wid] = wbits;
+        if (lane == 0) {
+            s_wsum[wid] = wbits;
+            if (ovf) s_ovf = 1;
+        }
         __syncthreads();
-        uint32_t wbase = 0, chunk_bits = 0;
+        unsigned long long wbase = 0, chunk_bits = 0;
 #pragma unroll
         for (int w = 0; w < EB / 32; w++) {
-            const uint32_t v = s_wsum[w];
+            const unsigned long long v = s_wsum[w];
             if (w < wid) wbase += v;
             chunk_bits += v;
         }
         if (tid == 0) s_prefix = lookback_exclusive(a.lb_state + (size_t)img * a.n_chunks, (int)chunk, chunk_bits);
         __syncthreads();
         const unsigned long long g0 = a.seed_bits + s_prefix;        // global bit position of the chunk
-        const unsigned long long gw0 = g0 >> 5;                      // first global word touched
-        const uint32_t phase = (uint32_t)(g0 & 31);
-        const bool last_chunk = (chunk == a.n_chunks - 1);
-        uint32_t pad = 0;
-        if (last_chunk && a.pad_ones) pad = (uint32_t)((8 - ((g0 + chunk_bits) & 7)) & 7);
-        const uint32_t span_bits = phase + chunk_bits + pad;
-        const uint32_t n_words = (span_bits + 31) >> 5;
-
-        if (n_words + 1 <= K3_OUT_WORDS) {
-            // the chunk's bits fit the shared bit buffer: assemble there, one coalesced flush
-            for (uint32_t i = tid; i < n_words + 1; i += EB) s_out[i] = 0u;
-            __syncthreads();
-            emit_range<true>(tok, begin, end, s_enc, zl_y, zl_c, s_out, phase + wbase);
-            if (pad && tid == 0) or_bits<true>(s_out, phase + chunk_bits, (1u << pad) - 1u, pad);
-            __syncthreads();
-            for (uint32_t i = tid; i < n_words; i += EB) {
-                const uint32_t v = bswap32(s_out[i]);
-                if (i == 0 || i == n_words - 1) {  // words shared with the neighbouring chunks
-                    if (v) atomicOr(&gscan[gw0 + i], v);
+        const unsigned long long p0 = g0 + wbase;                    // ... and of this warp's range
+        if (!s_ovf) {
+            // shifted copy of the private buffer to its place: destination word k holds relative bits
+            // [32k - s, 32k - s + 32); the first and last word are shared with the neighbours
+            const uint32_t sft = (uint32_t)(p0 & 31);
+            const uint32_t n_dst = (uint32_t)((sft + wbits + 31) >> 5);
+            uint32_t* dst = gscan + (p0 >> 5);
+            for (uint32_t k = lane; k < n_dst; k += 32) {
+                const uint32_t cur = k < (uint32_t)K3_WBUF_WORDS ? wbuf[k] : 0u;
+                const uint32_t prv = k ? wbuf[k - 1] : 0u;
+                const uint32_t v = bswap32(__funnelshift_r(cur, prv, sft));
+                if (k == 0 || k == n_dst - 1) {
+                    if (v) atomicOr(dst + k, v);
                 } else {
-                    gscan[gw0 + i] = v;
+                    dst[k] = v;
                 }
             }
         } else {
-            // dense chunk: OR straight into the zeroed global stream
-            emit_range<false>(tok, begin, end, s_enc, zl_y, zl_c, gscan, g0 + wbase);
-            if (pad && tid == 0) or_bits<false>(gscan, g0 + chunk_bits, (1u << pad) - 1u, pad);
+            // a range too dense for the private buffer (rare): second pass straight into the zeroed stream
+            bool d0 = true, d1 = false;
+            (void)emit_range<false>(tok, begin, end, s_enc, zl_y, zl_c, gscan, p0, ~0ull, d0, d1);
+        }
+        if (chunk == a.n_chunks - 1 && a.pad_ones && tid == 0) {
+            const uint32_t pad = (uint32_t)((8 - ((g0 + chunk_bits) & 7)) & 7);  // binary_stream.rs:89-96
+            if (pad) or_bits<false>(gscan, g0 + chunk_bits, (1u << pad) - 1u, pad);
         }
     }
 }
