@@ -125,6 +125,8 @@ static void plan_free_scratch(dmmt_plan* p) {
     (void)cudaFree(p->scan), p->scan = nullptr;
     (void)cudaFree(p->tb.tok), p->tb.tok = nullptr;
     (void)cudaFree(p->tb.ntok), p->tb.ntok = nullptr;
+    (void)cudaFree(p->fo.last_dc), p->fo.last_dc = nullptr;
+    (void)cudaFree(p->fo.dcpos), p->fo.dcpos = nullptr;
     (void)cudaFree(p->d_lens), p->d_lens = nullptr;
     (void)cudaFree(p->d_offsets), p->d_offsets = nullptr;
     (void)cudaFree(p->d_seed_dc), p->d_seed_dc = nullptr;
@@ -152,18 +154,36 @@ static int plan_alloc_scan(dmmt_plan* p, size_t scan_cap_bytes) {
     p->max_chunks4 = k4_max_chunks(p->scan_cap_bytes + 8);
     DMMT_CUDA(cudaMalloc(&p->scan, (size_t)p->n * p->scan_stride_words * 4));
     // token stream: 32 tokens per block by default (the bytes of the coefficient stream); the worst
-    // case is 65 (DC + 63 AC + EOB never coexist with 63 AC, but 65 bounds it) once the scan capacity
-    // has been grown to the worst case as well
+    // case is 65 per block (68 allocated) once the scan capacity has been grown to the worst case.
+    // The same buffer serves the generic path (regions = K2's 256-block chunks) and the fused 4:2:0
+    // path (regions = K1's 96-block tiles).
     const bool worst = p->scan_cap_bytes >= (size_t)p->g.n_blocks * 209;
-    p->tb.chunk_cap = tok_blocks_per_chunk() * (worst ? 68u : 32u);
-    p->tb.img_stride_words = (size_t)p->n_chunks3 * p->tb.chunk_cap;
-    DMMT_CUDA(cudaMalloc(&p->tb.tok, (size_t)p->n * p->tb.img_stride_words * 4));
-    DMMT_CUDA(cudaMalloc(&p->tb.ntok, (size_t)p->n * p->n_chunks3 * 4));
+    const uint32_t per_block = worst ? 68u : 32u;
+    p->tb.chunk_cap = tok_blocks_per_chunk() * per_block;
+    p->fused = k1_fused_supported(p->g, p->k1c) && !p->force_generic;
+    p->fo.tiles_x = k1_tiles_x(p->g);
+    p->fo.tiles = p->fo.tiles_x * (uint32_t)p->g.mcus_y;
+    p->fo.tile_cap = 96u * per_block;
+    p->n_chunks3f = (p->fo.tiles + 7) / 8;
+    const size_t words_generic = (size_t)p->n_chunks3 * p->tb.chunk_cap;
+    const size_t words_fused = (size_t)p->fo.tiles * p->fo.tile_cap;
+    const size_t img_words = std::max(words_generic, words_fused);
+    p->tb.img_stride_words = img_words;
+    p->fo.img_stride_words = img_words;
+    DMMT_CUDA(cudaMalloc(&p->tb.tok, (size_t)p->n * img_words * 4));
+    const size_t n_regions = std::max<size_t>(p->n_chunks3, p->fo.tiles);
+    DMMT_CUDA(cudaMalloc(&p->tb.ntok, (size_t)p->n * n_regions * 4));
+    p->fo.tok = p->tb.tok;
+    p->fo.ntok = p->tb.ntok;
+    (void)cudaFree(p->fo.last_dc), p->fo.last_dc = nullptr;
+    (void)cudaFree(p->fo.dcpos), p->fo.dcpos = nullptr;
+    DMMT_CUDA(cudaMalloc(&p->fo.last_dc, (size_t)p->n * p->fo.tiles * 4 * sizeof(int16_t)));
+    DMMT_CUDA(cudaMalloc(&p->fo.dcpos, (size_t)p->n * p->fo.tiles * 2 * sizeof(uint32_t)));
     // one zero-initialised region per run: hist | meta | lb3 | lb4 | tk3 | tk4
     const size_t o_hist = 0;
     const size_t o_meta = o_hist + align_up((size_t)p->n * 1024 * sizeof(unsigned int), 16);
     const size_t o_lb3 = o_meta + align_up((size_t)p->n * sizeof(ImgMeta), 16);
-    const size_t o_lb4 = o_lb3 + (size_t)p->n * p->n_chunks3 * 8;
+    const size_t o_lb4 = o_lb3 + (size_t)p->n * std::max(p->n_chunks3, p->n_chunks3f) * 8;
     const size_t o_tk3 = o_lb4 + (size_t)p->n * p->max_chunks4 * 8;
     const size_t o_tk4 = o_tk3 + align_up((size_t)p->n * 4, 16);
     p->zero_bytes = o_tk4 + align_up((size_t)p->n * 4, 16);
@@ -289,6 +309,15 @@ extern "C" int dmmt_plan_set_scan_capacity(dmmt_plan* p, size_t bytes_per_image)
     return plan_alloc_scan(p, bytes_per_image);
 }
 
+extern "C" int dmmt_plan_set_generic_path(dmmt_plan* p, int generic) {
+    if (!p) return DMMT_E_INVALID;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    DMMT_CUDA(cudaStreamSynchronize(p->stream));
+    p->force_generic = generic ? 1 : 0;
+    p->fused = k1_fused_supported(p->g, p->k1c) && !p->force_generic;
+    return DMMT_OK;
+}
+
 extern "C" int dmmt_plan_set_profiling(dmmt_plan* p, int enabled) {
     if (!p) return DMMT_E_INVALID;
     DMMT_CUDA(cudaSetDevice(p->ctx->device));
@@ -310,11 +339,12 @@ int dmmt_plan_chain(dmmt_plan* p, const void* d_pixels, int n, uint8_t* d_out, u
     DMMT_CUDA(mark(0));
     const int check_max = (p->fmt == DMMT_RGB_U8 && p->max_value < 255) ||
                           (p->fmt == DMMT_RGB_U16 && p->max_value < 65535);
-    DMMT_CUDA(launch_k1(p->g, p->fmt, p->k1c, check_max, d_pixels, p->pixel_bytes, n,
-                        p->coef, p->coef_stride, nullptr, p->meta, st));
+    DMMT_CUDA(launch_k1(p->g, p->fmt, p->k1c, check_max, d_pixels, p->pixel_bytes, n, p->coef, p->coef_stride, nullptr,
+                        p->meta, p->fused ? &p->fo : nullptr, p->hist, st));
     launches += 1;
     DMMT_CUDA(mark(1));
-    DMMT_CUDA(launch_k2(p->g, p->coef, p->coef_stride, n, p->hist, p->meta, nullptr, p->tb, st));
+    if (p->fused) DMMT_CUDA(launch_k2_fix_dc(p->fo, n, p->hist, p->meta, nullptr, st));
+    else DMMT_CUDA(launch_k2(p->g, p->coef, p->coef_stride, n, p->hist, p->meta, nullptr, p->tb, st));
     launches += 1;
     DMMT_CUDA(mark(2));
     K2bHostArgs b{};
@@ -330,7 +360,12 @@ int dmmt_plan_chain(dmmt_plan* p, const void* d_pixels, int n, uint8_t* d_out, u
     DMMT_CUDA(mark(3));
     const int zero_blocks = (int)std::min<size_t>(std::max<size_t>(p->scan_cap_bytes / 65536, 1), 128);
     DMMT_CUDA(launch_zero_scan(p->scan, p->scan_stride_words, p->meta, n, 0ull, zero_blocks, st));
-    DMMT_CUDA(launch_k3(p->g, n, p->tb, p->enc, p->meta, p->lb3, p->tk3, p->scan, p->scan_stride_words, 0ull, 1, st));
+    {
+        TokBuf tb = p->tb;
+        if (p->fused) tb.chunk_cap = p->fo.tile_cap;
+        DMMT_CUDA(launch_k3(p->fused ? p->n_chunks3f : p->n_chunks3, p->fused ? p->fo.tiles : 0u, n, tb, p->enc, p->meta,
+                            p->lb3, p->tk3, p->scan, p->scan_stride_words, 0ull, 1, st));
+    }
     launches += 2;
     DMMT_CUDA(mark(4));
     K4HostArgs k{};
@@ -605,7 +640,7 @@ extern "C" int dmmt_plan_debug_dct(dmmt_plan* p, const void* d_pixels, int index
     const uint8_t* px = static_cast<const uint8_t*>(d_pixels) + (size_t)index * p->pixel_bytes;
     cudaError_t e = launch_k1(p->g, p->fmt, p->k1c, 0, px, p->pixel_bytes, 1,
                               p->coef + (size_t)index * p->coef_stride, p->coef_stride, d_dbg, p->meta + index,
-                              p->stream);
+                              nullptr, nullptr, p->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dst, d_dbg, p->coef_stride * sizeof(float), cudaMemcpyDeviceToHost, p->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
     (void)cudaFree(d_dbg);

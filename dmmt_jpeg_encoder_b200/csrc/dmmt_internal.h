@@ -63,7 +63,11 @@ struct dmmt_plan {
     dmmt::EncTables* enc = nullptr;
     dmmt::LenTables* lens = nullptr;
     uint32_t* scan = nullptr;
-    dmmt::TokBuf tb{};                        // K2 -> K3 token stream
+    dmmt::TokBuf tb{};                        // K2 -> K3 token stream (generic path)
+    dmmt::TileTok fo{};                       // fused K1 -> K3 token stream (4:2:0 fast path), shares tb.tok
+    bool fused = false;                       // this plan runs the fused path
+    int force_generic = 0;                    // dmmt_plan_set_generic_path
+    uint32_t n_chunks3f = 0;                  // look-back chunks of K3 in tile mode
     unsigned long long* d_lens = nullptr;     // [n]
     unsigned long long* d_offsets = nullptr;  // [n + 1]
     int16_t* d_seed_dc = nullptr;             // [3] shard predictors

@@ -12,10 +12,24 @@ struct K1Consts {
     int exact;               // 1: use the IEEE-division kernels (fast forms not proven for this plan)
     QuantF qf, rq_hi, rq_lo; // divisors and 1/q split in two f32
 };
+// Fused K1 output (4:2:0 fast path): one token region per 256x16-pixel tile, tiles in stream order.
+struct TileTok {
+    uint32_t* tok;            // [n][tiles][tile_cap]
+    size_t img_stride_words;
+    uint32_t tile_cap;        // tokens per tile (multiple of 8)
+    uint32_t* ntok;           // [n][tiles]
+    int16_t* last_dc;         // [n][tiles][4]: quantised DC of the tile's last Y, Cb, Cr block
+    uint32_t* dcpos;          // [n][tiles][2]: token index of the tile's first Cb / Cr DC token
+    uint32_t tiles_x, tiles;
+};
+bool k1_fused_supported(const Geom& g, const K1Consts& c);
+uint32_t k1_tiles_x(const Geom& g);
+cudaError_t launch_k2_fix_dc(const TileTok& fo, int n, unsigned int* hist, ImgMeta* meta, const int16_t* seed_dc,
+                             cudaStream_t st);
 void make_k1_consts(int fmt, int max_value, const uint8_t* q_luma, const uint8_t* q_chroma, K1Consts* c);
 cudaError_t launch_k1(const Geom& g, int fmt, const K1Consts& c, int check_max, const void* d_pixels,
                       size_t img_stride_bytes, int n_images, int16_t* d_coef, size_t coef_img_stride,
-                      float* d_dbg, ImgMeta* meta, cudaStream_t st);
+                      float* d_dbg, ImgMeta* meta, const TileTok* fused, unsigned int* hist, cudaStream_t st);
 
 // K2 (k2_entropy.cu): tokens of chunk c (256 stream blocks) of image i live at
 // tok + i * img_stride_words + c * chunk_cap; ntok[i * n_chunks + c] of them are valid.
@@ -52,7 +66,9 @@ cudaError_t launch_zero_scan(uint32_t* scan, size_t stride_words, const ImgMeta*
 uint32_t k3_chunks(const Geom& g);
 uint32_t k4_max_chunks(size_t scan_cap_bytes);
 
-cudaError_t launch_k3(const Geom& g, int n, const TokBuf& tb, const EncTables* enc, ImgMeta* meta,
+// n_segs == 0: chunk c = token region c (K2's 256-block chunks), sliced over the 8 warps of a CTA;
+// n_segs > 0 (fused K1): region = tile, chunk c = tiles [8c, 8c + 8), one warp per tile.
+cudaError_t launch_k3(uint32_t n_chunks, uint32_t n_segs, int n, const TokBuf& tb, const EncTables* enc, ImgMeta* meta,
                       unsigned long long* lb_state, unsigned int* ticket, uint32_t* scan, size_t scan_stride_words,
                       unsigned long long seed_bits, int pad_ones, cudaStream_t st);
 

@@ -95,9 +95,15 @@ static int shard_transform_launch(dmmt_shard* s, const void* d_pixels) {
     DMMT_CUDA(cudaSetDevice(p->ctx->device));
     DMMT_CUDA(cudaMemsetAsync(p->zero_region, 0, p->zero_bytes, p->stream));
     const int check_max = (p->fmt == DMMT_RGB_U8 && p->max_value < 255) || (p->fmt == DMMT_RGB_U16 && p->max_value < 65535);
-    DMMT_CUDA(launch_k1(p->g, p->fmt, p->k1c, check_max, d_pixels, p->pixel_bytes, 1, p->coef,
-                        p->coef_stride, nullptr, p->meta, p->stream));
-    DMMT_CUDA(launch_last_dc(p->g, p->coef, p->d_last_dc, p->stream));
+    DMMT_CUDA(launch_k1(p->g, p->fmt, p->k1c, check_max, d_pixels, p->pixel_bytes, 1, p->coef, p->coef_stride, nullptr,
+                        p->meta, p->fused ? &p->fo : nullptr, p->hist, p->stream));
+    if (p->fused) {
+        // quantised DC of the shard's last Y, Cb, Cr block = last_dc of its last tile
+        DMMT_CUDA(cudaMemcpyAsync(p->d_last_dc, p->fo.last_dc + (size_t)(p->fo.tiles - 1) * 4, 3 * sizeof(int16_t),
+                                  cudaMemcpyDeviceToDevice, p->stream));
+    } else {
+        DMMT_CUDA(launch_last_dc(p->g, p->coef, p->d_last_dc, p->stream));
+    }
     p->last_launches = 2;
     p->last_n = 1;
     return DMMT_OK;
@@ -121,7 +127,8 @@ static int shard_histogram_launch(dmmt_shard* s, const int16_t seed_dc[3]) {
     DMMT_CUDA(cudaSetDevice(p->ctx->device));
     DMMT_CUDA(cudaMemcpyAsync(p->d_seed_dc, seed_dc, 3 * sizeof(int16_t), cudaMemcpyHostToDevice, p->stream));
     s->have_seed = true;
-    DMMT_CUDA(launch_k2(p->g, p->coef, p->coef_stride, 1, p->hist, p->meta, p->d_seed_dc, p->tb, p->stream));
+    if (p->fused) DMMT_CUDA(launch_k2_fix_dc(p->fo, 1, p->hist, p->meta, p->d_seed_dc, p->stream));
+    else DMMT_CUDA(launch_k2(p->g, p->coef, p->coef_stride, 1, p->hist, p->meta, p->d_seed_dc, p->tb, p->stream));
     p->last_launches += 1;
     DMMT_CUDA(cudaMemcpyAsync(s->h_hist, p->hist, 1024 * sizeof(unsigned int), cudaMemcpyDeviceToHost, p->stream));
     return DMMT_OK;
@@ -180,8 +187,12 @@ static int shard_pack_launch(dmmt_shard* s, uint64_t global_bit_offset, int is_l
     s->seed_bits = global_bit_offset & 7;  // the shard's buffer starts at the byte holding its first bit
     const int zero_blocks = (int)std::min<size_t>(std::max<size_t>(p->scan_cap_bytes / 65536, 1), 1024);
     DMMT_CUDA(launch_zero_scan(p->scan, p->scan_stride_words, p->meta, 1, s->seed_bits, zero_blocks, p->stream));
-    DMMT_CUDA(launch_k3(p->g, 1, p->tb, p->enc, p->meta, p->lb3, p->tk3, p->scan, p->scan_stride_words, s->seed_bits,
-                        is_last ? 1 : 0, p->stream));
+    {
+        TokBuf tb = p->tb;
+        if (p->fused) tb.chunk_cap = p->fo.tile_cap;
+        DMMT_CUDA(launch_k3(p->fused ? p->n_chunks3f : p->n_chunks3, p->fused ? p->fo.tiles : 0u, 1, tb, p->enc, p->meta,
+                            p->lb3, p->tk3, p->scan, p->scan_stride_words, s->seed_bits, is_last ? 1 : 0, p->stream));
+    }
     p->last_launches += 2;
     return DMMT_OK;
 }

@@ -205,6 +205,8 @@ struct K1Args {
     QuantF qf;                   // divisors
     QuantF rq_hi, rq_lo;         // 1/q split in two f32 (see quantize)
     int force_scalar;            // DMMT_K1_SCALAR=1: use the scalar kernel for P420 too (A/B measurements)
+    TileTok fo;                  // fused path: token stream per tile (k1_transform_p420<FMT, true>)
+    unsigned int* hist;          // fused path: [n][4][256]
 };
 
 // EXACT: IEEE divisions everywhere (fallback when the host-side proof of the fast normalisation
@@ -527,12 +529,14 @@ __device__ __forceinline__ void quantize_block_packed(const K1Args& a, const f2 
         }
 }
 
+// Phase B of the P420 kernels: block `u` of the tile (stream slot m * 6 + k) -> 64 quantised
+// coefficients in NATURAL order.  Returns false for blocks of MCUs beyond the padded image.
 template <int FMT>
-__device__ __forceinline__ void p420_phase_b(const K1Args& a, int u, int mcus_here, const float4 (*sY)[8][16],
-                                             const float4 (*sCb)[4][16], const float4 (*sCr)[4][16], uint4* s_stage,
-                                             const int* s_flag_p) {
-    constexpr int BPM = 6, NYU = 64, NCU = 16;
-    int m, k, comp;
+__device__ __forceinline__ bool p420_block_coefs(const K1Args& a, int u, int mcus_here, const float4 (*sY)[8][16],
+                                                 const float4 (*sCb)[4][16], const float4 (*sCr)[4][16],
+                                                 const int* s_flag_p, unsigned short (&qv)[64], int& m, int& k,
+                                                 int& comp) {
+    constexpr int NYU = 64, NCU = 16;
     f2 P[4][8];  // P[j][c] = {d[2j][c], d[2j+1][c]}
     if (u < NYU) {
         const int q = u >> 4, sx = u & 15;
@@ -558,7 +562,7 @@ __device__ __forceinline__ void p420_phase_b(const K1Args& a, int u, int mcus_he
                 P[j][2 * cc] = pk(t.x, t.y), P[j][2 * cc + 1] = pk(t.z, t.w);
             }
     }
-    if (m >= mcus_here) return;  // tile overhangs the padded image
+    if (m >= mcus_here) return false;  // tile overhangs the padded image
 
     // row passes on row pairs; the scaled outputs are written as COLUMN pairs C[r][kp] = {d[r][2kp], d[r][2kp+1]}
     float d[64];
@@ -582,7 +586,6 @@ __device__ __forceinline__ void p420_phase_b(const K1Args& a, int u, int mcus_he
     // branch and its entries become uniform-register operands.
     bool exact = false;
     if constexpr (FMT == DMMT_RGB_F32_NORM) exact = *s_flag_p != 0;
-    unsigned short qv[64];
     if (!exact) {
         if (comp == 0) quantize_block_packed<0>(a, D, qv);
         else quantize_block_packed<1>(a, D, qv);
@@ -593,29 +596,31 @@ __device__ __forceinline__ void p420_phase_b(const K1Args& a, int u, int mcus_he
             qv[i] = (unsigned short)quantize<true>(dv, a.qf.q[comp][i], 0.f, 0.f);
         }
     }
-    // zig-zag by register renaming, two i16 per word, staged so that the tile leaves as ONE contiguous,
-    // coalesced 12 KB run (16 MCUs x 6 blocks x 128 B in stream order)
-    {
-        const int slot = m * BPM + k;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            uint32_t w[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                asm("mov.b32 %0, {%1, %2};" : "=r"(w[j]) : "h"(qv[zz_at(8 * i + 2 * j)]), "h"(qv[zz_at(8 * i + 2 * j + 1)]));
-            s_stage[slot * 8 + (i ^ (slot & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-    }
+    return true;
 }
 
-template <int FMT>
+// categorize.rs:22-41 for a non-zero value: category and the cat low bits of the pattern
+__device__ __forceinline__ void k1_cat_bits(int v, int& cat, uint32_t& bits) {
+    const int av = abs(v);
+    cat = 32 - __clz(av);
+    bits = (uint32_t)(v > 0 ? v : v - 1) & ((1u << cat) - 1u);
+}
+__device__ __forceinline__ uint32_t k1_token(int table, int sym, int nzrl, uint32_t extra) {
+    return (uint32_t)sym | ((uint32_t)table << 8) | ((uint32_t)nzrl << 10) | (extra << 16);
+}
+
+template <int FMT, bool FUSED>
 __global__ void __launch_bounds__(K1_THREADS, 5) k1_transform_p420(const __grid_constant__ K1Args a) {
     // planes as ROW-PAIR interleaved float4 = {v(x,2j), v(x,2j+1), v(x+1,2j), v(x+1,2j+1)}:
     //   sY[row pair][16-byte chunk: 2 columns][strip], sC*[row pair][chunk][strip]
-    __shared__ float4 sY[8][8][16];
-    __shared__ float4 sCb[4][4][16];
-    __shared__ float4 sCr[4][4][16];
-    __shared__ uint4 s_stage[96 * 8];
+    __shared__ __align__(16) float4 s_planes[8 * 8 * 16 + 2 * 4 * 4 * 16];  // 24 KB: Y | Cb | Cr (reused for tokens)
+    float4(*sY)[8][16] = reinterpret_cast<float4(*)[8][16]>(s_planes);
+    float4(*sCb)[4][16] = reinterpret_cast<float4(*)[4][16]>(s_planes + 1024);
+    float4(*sCr)[4][16] = reinterpret_cast<float4(*)[4][16]>(s_planes + 1280);
+    __shared__ uint4 s_stage[96 * 8];                    // quantised blocks of the tile in stream order (zig-zag, swizzled)
+    __shared__ unsigned int s_hist[FUSED ? 1024 : 1];   // fused path: symbol counts of the tile
+    __shared__ uint32_t s_cnt[FUSED ? 100 : 1];         // tokens per block, then exclusive offsets (+ total)
+    __shared__ short s_dc[FUSED ? 96 : 1];
     __shared__ int s_flag;
     constexpr int BPM = 6, MPT = 16, NYU = 64, NCU = 16, NUNITS = 96;
     if constexpr (FMT == DMMT_RGB_F32_NORM) {
@@ -691,24 +696,190 @@ __global__ void __launch_bounds__(K1_THREADS, 5) k1_transform_p420(const __grid_
     // ---------------- phase B: unit = one 8x8 block ----------------
     const int u = threadIdx.x;
     const int mcus_here = min(MPT, a.mcus_x - tile_x * MPT);  // MCUs of this tile inside the padded image
-    if (u < NUNITS) p420_phase_b<FMT>(a, u, mcus_here, sY, sCb, sCr, s_stage, &s_flag);
-    __syncthreads();
-    // ---------------- phase C: the tile's blocks, contiguous in stream order ----------------
-    {
+    unsigned short qv[64];
+    int m = 0, k = 0, comp = 0;
+    bool active = false;
+    if (u < NUNITS) active = p420_block_coefs<FMT>(a, u, mcus_here, sY, sCb, sCr, &s_flag, qv, m, k, comp);
+    const int slot = m * BPM + k;
+
+    // zig-zag by register renaming, two i16 per word, into the tile's staging area (slot = stream order)
+    uint32_t mlo = 0, mhi = 0;  // occupancy mask of the block (fused path)
+    if (active) {
+        uint32_t mm[2] = {0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                asm("mov.b32 %0, {%1, %2};" : "=r"(w[j]) : "h"(qv[zz_at(8 * i + 2 * j)]), "h"(qv[zz_at(8 * i + 2 * j + 1)]));
+            s_stage[slot * 8 + (i ^ (slot & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
+            if constexpr (FUSED) {
+                // 0xFFFF per non-zero half -> one flag byte per coefficient -> 8 mask bits (as in K2)
+                const uint32_t f01 = __byte_perm(__vcmpne2(w[0], 0u), __vcmpne2(w[1], 0u), 0x6420);
+                const uint32_t f23 = __byte_perm(__vcmpne2(w[2], 0u), __vcmpne2(w[3], 0u), 0x6420);
+                const uint32_t b01 = ((f01 & 0x08040201u) * 0x01010101u) >> 24;
+                const uint32_t b23 = ((f23 & 0x08040201u) * 0x01010101u) >> 24;
+                mm[i >> 2] |= (b01 | (b23 << 4)) << (8 * (i & 3));
+            }
+        }
+        mlo = mm[0], mhi = mm[1];
+    }
+    if constexpr (!FUSED) {
+        // the tile leaves as ONE contiguous, coalesced 12 KB run (16 MCUs x 6 blocks x 128 B in stream order)
+        __syncthreads();
         const size_t sblk0 = ((size_t)mrow * a.mcus_x + (size_t)tile_x * MPT) * BPM;
         uint4* out = reinterpret_cast<uint4*>(a.coef + (size_t)img * a.coef_img_stride + sblk0 * 64);
         const int n16 = mcus_here * BPM * 8;
         for (int i = threadIdx.x; i < n16; i += K1_THREADS) {
-            const int slot = i >> 3;
-            out[i] = s_stage[slot * 8 + ((i & 7) ^ (slot & 7))];
+            const int sl = i >> 3;
+            out[i] = s_stage[sl * 8 + ((i & 7) ^ (sl & 7))];
+        }
+    } else {
+        // ---------------- fused tokeniser (replaces K2 on this path) ----------------
+        // The quantised block never leaves the SM: its occupancy mask comes from the registers, the
+        // walk over the non-zero positions (categorize.rs:132-169) reads the block's own staged words,
+        // and the tokens (k2_entropy.cu format) are written compactly in stream order.  The three DC
+        // tokens whose predictor lives in the previous tile are left as place-holders carrying the raw
+        // DC for k2_fix_dc.
+        uint32_t* s_ctok = reinterpret_cast<uint32_t*>(s_planes);  // planes are dead after the barrier below
+        constexpr uint32_t S_CTOK_CAP = sizeof(s_planes) / 4;
+        for (int i = threadIdx.x; i < 1024; i += K1_THREADS) s_hist[i] = 0;
+        uint32_t cnt = 0;
+        if (active) {
+            // DC + one token per non-zero AC (ZRLs ride on it) + EOB unless coefficient 63 is non-zero
+            cnt = 1u + __popc(mlo & ~1u) + __popc(mhi) + ((mhi >> 31) ? 0u : 1u);
+            s_dc[slot] = (short)qv[0];
+        }
+        if (u < 96) s_cnt[u] = 0;
+        __syncthreads();  // everybody has read the planes; s_hist and s_cnt are zero
+        if (active) s_cnt[slot] = cnt;
+        __syncthreads();
+        if (threadIdx.x < 32) {  // exclusive scan of the 96 per-block counts in stream order
+            const int l = threadIdx.x;
+            const uint32_t c0 = s_cnt[3 * l], c1 = s_cnt[3 * l + 1], c2 = s_cnt[3 * l + 2];
+            uint32_t inc = c0 + c1 + c2;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (l >= d) inc += t;
+            }
+            const uint32_t ex = inc - (c0 + c1 + c2);
+            s_cnt[3 * l] = ex, s_cnt[3 * l + 1] = ex + c0, s_cnt[3 * l + 2] = ex + c0 + c1;
+            if (l == 31) s_cnt[96] = inc;
+        }
+        __syncthreads();
+        const uint32_t total = s_cnt[96];
+        const uint32_t tile = (uint32_t)mrow * a.fo.tiles_x + (uint32_t)tile_x;
+        uint32_t* g_tok = a.fo.tok + (size_t)img * a.fo.img_stride_words + (size_t)tile * a.fo.tile_cap;
+        const bool fits = total <= a.fo.tile_cap;          // else DMMT_E_OVERFLOW: host retries with the worst-case capacity
+        const bool in_smem = total <= S_CTOK_CAP;          // else (very dense tile) tokens go straight to global memory
+        if (active) {
+            uint32_t off = s_cnt[slot];
+            uint32_t* dst = in_smem ? s_ctok : g_tok;      // generic pointer, resolved once
+            const bool store = in_smem || fits;
+            const int tdc = comp ? T_CDC : T_YDC, tac = tdc + 1;
+            bool ok = true;
+            {   // DC (categorize.rs:157-161): predictor = previous block of the same component in stream order
+                const int ps = k == 0 ? slot - 3 : (k < 4 ? slot - 1 : slot - 6);
+                if ((k != 0 && k < 4) || m > 0) {
+                    const int diff = (int)(short)((short)qv[0] - s_dc[ps]);
+                    int cat = 0;
+                    uint32_t bits = 0;
+                    if (diff != 0) k1_cat_bits(diff, cat, bits);
+                    ok &= cat <= 15;
+                    atomicAdd(&s_hist[tdc * 256 + (cat & 15)], 1u);
+                    if (store) dst[off] = k1_token(tdc, cat & 15, 0, bits);
+                } else {
+                    // predictor is in the previous tile (or is the seed): k2_fix_dc finishes this token
+                    if (k >= 4) a.fo.dcpos[((size_t)img * a.fo.tiles + tile) * 2 + (k - 4)] = off;
+                    if (store) dst[off] = (uint32_t)qv[0] << 16;
+                }
+                ++off;
+            }
+            // AC (categorize.rs:132-151): run of zeros; one 0xF0 per 16 zeros; EOB 0x00 when the tail is zero
+            const int16_t* sb = reinterpret_cast<const int16_t*>(s_stage + slot * 8);
+            const int sw = slot & 7;
+            int prev = 0;
+            uint32_t nzrl_total = 0;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                uint32_t mk = half ? mhi : (mlo & ~1u);
+                while (mk) {
+                    const int pos = 32 * half + __ffs((int)mk) - 1;
+                    mk &= mk - 1;
+                    const int run = pos - prev - 1;
+                    prev = pos;
+                    const int v = sb[(((pos >> 3) ^ sw) << 3) | (pos & 7)];
+                    int cat;
+                    uint32_t bits;
+                    k1_cat_bits(v, cat, bits);
+                    ok &= cat <= 15;
+                    const int sym = ((run & 15) << 4) | (cat & 15);
+                    nzrl_total += (uint32_t)(run >> 4);
+                    atomicAdd(&s_hist[tac * 256 + sym], 1u);
+                    if (store) dst[off] = k1_token(tac, sym, run >> 4, bits);
+                    ++off;
+                }
+            }
+            if (nzrl_total) atomicAdd(&s_hist[tac * 256 + 0xF0], nzrl_total);
+            if (prev != 63) {
+                atomicAdd(&s_hist[tac * 256], 1u);
+                if (store) dst[off] = k1_token(tac, 0x00, 0, 0u);
+            }
+            if (!ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_RANGE);
+        }
+        __syncthreads();
+        if (in_smem && fits) {  // compact tile -> one coalesced run (tile_cap is a multiple of 8 words)
+            uint4* dst = reinterpret_cast<uint4*>(g_tok);
+            const uint4* src = reinterpret_cast<const uint4*>(s_ctok);
+            for (uint32_t i = threadIdx.x; i < (total + 3) / 4; i += K1_THREADS) dst[i] = src[i];
+        }
+        if (threadIdx.x == 0) {
+            a.fo.ntok[(size_t)img * a.fo.tiles + tile] = fits ? total : 0u;
+            if (!fits) atomicCAS(&a.meta[img].error, 0, DMMT_E_OVERFLOW);
+            short* ld = a.fo.last_dc + ((size_t)img * a.fo.tiles + tile) * 4;
+            const int lm = (mcus_here - 1) * BPM;
+            ld[0] = s_dc[lm + 3], ld[1] = s_dc[lm + 4], ld[2] = s_dc[lm + 5], ld[3] = 0;
+        }
+        unsigned int* gh = a.hist + (size_t)img * 1024;
+        for (int i = threadIdx.x; i < 1024; i += K1_THREADS) {
+            const unsigned int v = s_hist[i];
+            if (v) atomicAdd(&gh[i], v);
         }
     }
 }
+
+// K2 on the fused path: finishes the DC tokens whose predictor is the last DC of the previous tile
+// (tile 0: the seeds, 0 for a whole image -- categorize.rs:157) and counts their symbols.
+__global__ void k2_fix_dc(TileTok fo, unsigned int* hist, ImgMeta* meta, const int16_t* seed_dc) {
+    const int img = blockIdx.y;
+    const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= fo.tiles) return;
+    const size_t ti = (size_t)img * fo.tiles + tile;
+    if (fo.ntok[ti] == 0) return;  // overflowed tile (error already flagged)
+    uint32_t* tok = fo.tok + (size_t)img * fo.img_stride_words + (size_t)tile * fo.tile_cap;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int pred = tile ? (int)fo.last_dc[(ti - 1) * 4 + c] : (seed_dc ? (int)seed_dc[c] : 0);
+        const uint32_t pos = c == 0 ? 0u : fo.dcpos[ti * 2 + (c - 1)];
+        const int dc = (int)(short)(tok[pos] >> 16);
+        const int diff = (int)(short)(dc - pred);
+        int cat = 0;
+        uint32_t bits = 0;
+        if (diff != 0) k1_cat_bits(diff, cat, bits);
+        if (cat > 15) atomicCAS(&meta[img].error, 0, DMMT_E_RANGE);
+        const int tdc = c ? T_CDC : T_YDC;
+        tok[pos] = k1_token(tdc, cat & 15, 0, bits);
+        atomicAdd(&hist[(size_t)img * 1024 + tdc * 256 + (cat & 15)], 1u);
+    }
+}
+
 template <int HR, int VR, int FMT>
 cudaError_t launch_fmt(const K1Args& a, dim3 grid, bool dbg, bool exact, cudaStream_t st) {
     if constexpr (HR == 2 && VR == 2) {
         if (!dbg && !exact && !a.force_scalar) {
-            k1_transform_p420<FMT><<<grid, K1_THREADS, 0, st>>>(a);
+            if (a.fo.tok) k1_transform_p420<FMT, true><<<grid, K1_THREADS, 0, st>>>(a);
+            else k1_transform_p420<FMT, false><<<grid, K1_THREADS, 0, st>>>(a);
             return cudaGetLastError();
         }
     }
@@ -733,12 +904,28 @@ cudaError_t launch_sub(const K1Args& a, dim3 grid, int fmt, bool dbg, bool exact
 
 }  // namespace
 
+// The fused transform+tokenise kernel exists for 4:2:0 with the proven fast divisions.
+bool k1_fused_supported(const Geom& g, const K1Consts& c) {
+    static const bool scalar = [] { const char* e = getenv("DMMT_K1_SCALAR"); return e && e[0] == '1'; }();
+    return g.hr == 2 && g.vr == 2 && !c.exact && !scalar;
+}
+uint32_t k1_tiles_x(const Geom& g) { return (uint32_t)((g.mcus_x * 8 * g.hr + TILE_W - 1) / TILE_W); }
+
+cudaError_t launch_k2_fix_dc(const TileTok& fo, int n, unsigned int* hist, ImgMeta* meta, const int16_t* seed_dc,
+                             cudaStream_t st) {
+    k2_fix_dc<<<dim3((fo.tiles + 127) / 128, n), 128, 0, st>>>(fo, hist, meta, seed_dc);
+    return cudaGetLastError();
+}
+
 // Host launcher.  n_images equally sized images; dbg != nullptr selects the variant that also
 // writes the pre-quantisation coefficients of image 0.
 cudaError_t launch_k1(const Geom& g, int fmt, const K1Consts& c, int check_max, const void* d_pixels,
                       size_t img_stride_bytes, int n_images, int16_t* d_coef, size_t coef_img_stride,
-                      float* d_dbg, ImgMeta* meta, cudaStream_t st) {
+                      float* d_dbg, ImgMeta* meta, const TileTok* fused, unsigned int* hist, cudaStream_t st) {
     K1Args a;
+    a.fo = TileTok{};
+    a.hist = hist;
+    if (fused && k1_fused_supported(g, c) && !d_dbg) a.fo = *fused;
     a.pixels = static_cast<const uint8_t*>(d_pixels);
     a.img_stride_bytes = img_stride_bytes;
     a.W = g.W;

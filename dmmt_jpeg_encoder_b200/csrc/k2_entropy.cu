@@ -456,6 +456,7 @@ __global__ void k_zero_scan(uint32_t* scan, size_t scan_img_stride_words, const 
 // =========================================== K3 ===========================================
 struct K3Args {
     uint32_t n_chunks;
+    uint32_t n_segs;               // tile mode: token regions (tiles) per image, 8 per chunk, one per warp; else 0
     TokBuf tb;
     const EncTables* enc;          // [n]
     ImgMeta* meta;                 // [n]
@@ -606,12 +607,21 @@ __global__ void __launch_bounds__(EB) k3_pack(const K3Args a) {
         __syncthreads();
         const uint32_t chunk = s_chunk;
         if (chunk >= a.n_chunks) return;
-        const uint32_t ntok = a.tb.ntok[(size_t)img * a.n_chunks + chunk];
-        const uint32_t* __restrict__ tok =
-            a.tb.tok + (size_t)img * a.tb.img_stride_words + (size_t)chunk * a.tb.chunk_cap;
-        // contiguous token range of this warp (multiple of 256 so the 128-bit loads stay aligned)
-        const uint32_t per_warp = ((ntok + EB / 32 * K3_STEP - 1) / (EB / 32 * K3_STEP)) * K3_STEP;
-        const uint32_t begin = min(ntok, wid * per_warp), end = min(ntok, begin + per_warp);
+        // token range of this warp: generic mode = a slice (multiple of 256 tokens, so the 128-bit loads
+        // stay aligned) of the chunk's region; tile mode (fused K1) = the whole region of tile 8 * chunk + warp
+        const uint32_t* __restrict__ tok;
+        uint32_t begin, end;
+        if (a.n_segs) {
+            const uint32_t seg = chunk * (EB / 32) + wid;
+            tok = a.tb.tok + (size_t)img * a.tb.img_stride_words + (size_t)seg * a.tb.chunk_cap;
+            begin = 0;
+            end = seg < a.n_segs ? a.tb.ntok[(size_t)img * a.n_segs + seg] : 0u;
+        } else {
+            const uint32_t ntok = a.tb.ntok[(size_t)img * a.n_chunks + chunk];
+            tok = a.tb.tok + (size_t)img * a.tb.img_stride_words + (size_t)chunk * a.tb.chunk_cap;
+            const uint32_t per_warp = ((ntok + EB / 32 * K3_STEP - 1) / (EB / 32 * K3_STEP)) * K3_STEP;
+            begin = min(ntok, wid * per_warp), end = min(ntok, begin + per_warp);
+        }
 
         // ONE pass over the tokens: the warp packs its range into its private buffer from bit 0;
         // where the range starts in the scan is only known after the look-back below
@@ -999,10 +1009,10 @@ cudaError_t launch_zero_scan(uint32_t* scan, size_t stride_words, const ImgMeta*
 
 uint32_t k4_max_chunks(size_t scan_cap_bytes) { return (uint32_t)((scan_cap_bytes + K4_CHUNK - 1) / K4_CHUNK); }
 
-cudaError_t launch_k3(const Geom& g, int n, const TokBuf& tb, const EncTables* enc, ImgMeta* meta,
+cudaError_t launch_k3(uint32_t n_chunks, uint32_t n_segs, int n, const TokBuf& tb, const EncTables* enc, ImgMeta* meta,
                       unsigned long long* lb_state, unsigned int* ticket, uint32_t* scan, size_t scan_stride_words,
                       unsigned long long seed_bits, int pad_ones, cudaStream_t st) {
-    K3Args a{k3_chunks(g), tb, enc, meta, lb_state, ticket, scan, scan_stride_words, seed_bits, pad_ones};
+    K3Args a{n_chunks, n_segs, tb, enc, meta, lb_state, ticket, scan, scan_stride_words, seed_bits, pad_ones};
     // CTAs take chunks by ticket and keep their encoder LUT in shared memory: about 6 CTAs per SM
     uint32_t per_image = (uint32_t)((148 * 6 + n - 1) / n);
     if (per_image < 4) per_image = 4;

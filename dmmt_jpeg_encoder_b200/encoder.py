@@ -162,6 +162,9 @@ class Plan:
     def set_profiling(self, on: bool):
         F.check(F.lib().dmmt_plan_set_profiling(self._h, int(on)), "dmmt_plan_set_profiling")
 
+    def set_generic_path(self, on: bool):
+        F.check(F.lib().dmmt_plan_set_generic_path(self._h, int(on)), "dmmt_plan_set_generic_path")
+
     def last_timings(self) -> dict:
         ms = (C.c_float * F.T_COUNT)()
         F.check(F.lib().dmmt_plan_last_timings(self._h, ms, F.T_COUNT), "dmmt_plan_last_timings")

@@ -165,6 +165,10 @@ void dmmt_host_free(void *);
 #define DMMT_T_TOTAL 6
 #define DMMT_T_COUNT 7
 int dmmt_plan_set_profiling(dmmt_plan *, int enabled);
+/* 1: run the generic kernels (K1 writes the coefficient stream, K2 tokenises it) even where the fused
+ * 4:2:0 fast path (K1 tokenises in registers, no coefficient stream) applies; needed before
+ * dmmt_plan_fetch(DMMT_FETCH_COEF).  Default 0. */
+int dmmt_plan_set_generic_path(dmmt_plan *, int generic);
 int dmmt_plan_last_timings(dmmt_plan *, float *ms, int n);
 /* number of kernels launched by the last encode call on this plan */
 int dmmt_plan_last_launch_count(const dmmt_plan *);

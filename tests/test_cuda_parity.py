@@ -117,10 +117,16 @@ def test_every_stage_matches_oracle(D, ctx, O, pname, kind, w, h):
     d_out = torch.empty(plan.out_stride, dtype=torch.uint8, device="cuda")
     d_len = torch.zeros(1, dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
-    plan.encode_device(d_px.data_ptr(), 1, d_out.data_ptr(), d_len.data_ptr())
-    plan.status()
     assert plan.stream_blocks == r.n_stream_blocks
-    # K1: quantised zig-zag coefficients in stream order -- bit exact
+    # both kernel paths: the default one (4:2:0: K1 tokenises in registers, no coefficient stream) and the
+    # generic one (K1 writes the coefficient stream, K2 tokenises it); everything after K1 is compared for both
+    for generic in (False, True):
+        plan.set_generic_path(generic)
+        d_out.zero_()
+        plan.encode_device(d_px.data_ptr(), 1, d_out.data_ptr(), d_len.data_ptr())
+        plan.status()
+        check_entropy_stages(plan, r, d_out, d_len, O)
+    # K1 (generic path ran last): quantised zig-zag coefficients in stream order -- bit exact
     coef = plan.fetch(F.FETCH_COEF)
     np.testing.assert_array_equal(coef, r.stream)
     # K1 debug variant: pre-quantisation DCT coefficients
@@ -130,7 +136,13 @@ def test_every_stage_matches_oracle(D, ctx, O, pname, kind, w, h):
     scale = np.maximum(np.abs(want), 1.0)
     assert np.max(np.abs(dct - want) / scale) <= 1e-4          # north-star tolerance
     assert np.array_equal(dct == 0, want == 0) and np.array_equal(dct[want != 0], want[want != 0])  # and bit equality
-    # K2: histograms
+    plan.close()
+
+
+def check_entropy_stages(plan, r, d_out, d_len, O):
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    # K2 (or K1's fused tokeniser + k2_fix_dc): histograms
     hist = plan.fetch(F.FETCH_HIST)
     np.testing.assert_array_equal(hist.astype(np.uint64), r.hist)
     # K2b: length tables in the reference's Vec<SymbolCodeLength> order
@@ -149,7 +161,6 @@ def test_every_stage_matches_oracle(D, ctx, O, pname, kind, w, h):
     scan = plan.fetch(F.FETCH_SCAN)
     assert len(scan) == r.scan_bytes_unstuffed
     assert O.stuff_bytes(bytes(scan)) == r.jpeg[r.header_bytes:-2]
-    plan.close()
 
 
 @pytest.mark.parametrize("q", range(7))
@@ -200,6 +211,20 @@ def test_noise_reaches_16_bit_codes(D, ctx, O):
         r = O.encode(px, 255, preset)
         assert max(max(l) for _, l in r.tables) == 16      # 15 + the '+1' quirk (symbol_counting.rs:88)
         assert ctx.encode(px, 255, D.Options(preset, 8, 0)) == r.jpeg
+
+
+def test_generic_path_matches_on_420(D, ctx, O):
+    """4:2:0 through the generic kernels (scalar/packed K1 with a coefficient stream + K2) as well."""
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    for kind, w, h in (("photo", 300, 200), ("uniform", 130, 70), ("grad", 1000, 40)):
+        px = synth_image(kind, w, h, 3)
+        plan = D.Plan(ctx, w, h, F.FMT_U8, 255, D.Options(), 1)
+        want = O.encode(px, 255, O.P420).jpeg
+        assert plan.encode_host(px[None]) == [want]
+        plan.set_generic_path(True)
+        assert plan.encode_host(px[None]) == [want]
+        plan.close()
 
 
 def test_constant_and_extreme_images(D, ctx, O):
