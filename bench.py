@@ -327,9 +327,13 @@ def run_ours(args):
     coef_bytes = 2 * (pW * pH * 3 // 2)                     # i16 coefficients per image, 4:2:0
     scan_b = (file_bytes / n) - 330.0                       # ~ stuffed scan bytes per image
     n_blocks = (pW // 8) * (pH // 8) * 3 // 2
-    alg = {                                                 # algorithmic bytes per IMAGE
-        "k1_transform": img_bytes + coef_bytes,
-        "k2_histogram": coef_bytes,
+    fused = batch.uses_fused_path()
+    # algorithmic (compulsory) bytes per IMAGE, BASELINE.md section 3.  On the fused 4:2:0 path K1 also
+    # does K2's work on-chip (the coefficient stream is never written or re-read), so the fused kernel is
+    # credited with the per-stage figures of BOTH stages it replaces: 3 + 3 (K1) + 3 (K2) B/px.
+    alg = {
+        "k1_transform": img_bytes + coef_bytes + (coef_bytes if fused else 0),
+        "k2_histogram": 0 if fused else coef_bytes,
         "k3_pack": coef_bytes + scan_b + 4 * n_blocks / 256.0,
         "k4_stuff": 2 * scan_b,
         "k5_compact": 2 * (file_bytes / n),
@@ -337,23 +341,31 @@ def run_ours(args):
     kernels = {}
     for name, per_img in alg.items():
         ms = tm[name]
-        if ms <= 0:
+        if ms <= 0 or per_img <= 0:
             continue
         gbs = per_img * n / (ms / 1e3) / 1e9
         kernels[name] = {"ms_per_step": ms, "launches_per_step": n_sub * (2 if name in ("k3_pack", "k5_compact") else 1),
                          "avg_launch_ms": ms / n_sub, "algorithmic_bytes_per_launch": per_img * n / n_sub,
                          "achieved_gbs": gbs, "frac": gbs / peak}
     kernels["k2b_tables"] = {"ms_per_step": tm["k2b_tables"], "launches_per_step": 2 * n_sub}
+    if fused:
+        kernels["k2_histogram"] = {"ms_per_step": tm["k2_histogram"], "launches_per_step": n_sub,
+                                   "note": "fused path: only k2_fix_dc (tile-boundary DC tokens) runs here"}
+        kernels["k1_transform"]["note"] = ("fused transform + tokenise + histogram kernel (k1_transform_p420<FMT, true>); "
+                                           "algorithmic bytes = K1 6 B/px + K2 3 B/px (padded)")
+        kernels["k1_transform"]["frac_at_6_bytes_per_px"] = (img_bytes + coef_bytes) * n / (tm["k1_transform"] / 1e3) / 1e9 / peak
     dom = max((k for k in kernels if "achieved_gbs" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom, {}).get("dram_bytes_per_launch")
+    try:  # dram__bytes_read + write of one ncu --set full capture, rescaled to this run's images per launch
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+        if t:
+            traffic = t["dram_bytes_per_launch"] / t["images_per_launch"] * (n / n_sub)
     except Exception:
         pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "share_of_step": kernels[dom]["ms_per_step"] / tm["total"] if tm["total"] > 0 else None,
-                "k1_frac": kernels.get("k1_transform", {}).get("frac")}
+                "k1_frac": kernels.get("k1_transform", {}).get("frac"), "fused_k1_k2": fused}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None

@@ -91,6 +91,8 @@ SIGNATURES = {
     "dmmt_host_free": (None, [_VP]),
     "dmmt_plan_set_profiling": (C.c_int, [_VP, C.c_int]),
     "dmmt_plan_set_generic_path": (C.c_int, [_VP, C.c_int]),
+    "dmmt_plan_uses_fused_path": (C.c_int, [_VP]),
+    "dmmt_batch_uses_fused_path": (C.c_int, [_VP]),
     "dmmt_plan_last_timings": (C.c_int, [_VP, C.POINTER(C.c_float), C.c_int]),
     "dmmt_plan_last_launch_count": (C.c_int, [_VP]),
     "dmmt_plan_fetch": (C.c_int, [_VP, C.c_int, C.c_int, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -309,6 +309,8 @@ extern "C" int dmmt_plan_set_scan_capacity(dmmt_plan* p, size_t bytes_per_image)
     return plan_alloc_scan(p, bytes_per_image);
 }
 
+extern "C" int dmmt_plan_uses_fused_path(const dmmt_plan* p) { return p && p->fused ? 1 : 0; }
+
 extern "C" int dmmt_plan_set_generic_path(dmmt_plan* p, int generic) {
     if (!p) return DMMT_E_INVALID;
     DMMT_CUDA(cudaSetDevice(p->ctx->device));

@@ -112,6 +112,7 @@ extern "C" int dmmt_batch_set_profiling(dmmt_batch* b, int enabled) {
 }
 
 extern "C" int dmmt_batch_last_launch_count(const dmmt_batch* b) { return b ? b->last_launches : 0; }
+extern "C" int dmmt_batch_uses_fused_path(const dmmt_batch* b) { return b && !b->slots.empty() && b->slots[0]->fused ? 1 : 0; }
 
 extern "C" int dmmt_batch_last_timings(dmmt_batch* b, float* ms, int n) {
     if (!b || !ms || n < DMMT_T_COUNT || !b->profiling) return DMMT_E_INVALID;

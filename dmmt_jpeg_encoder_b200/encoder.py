@@ -271,6 +271,9 @@ class Batch:
     def last_launch_count(self) -> int:
         return F.lib().dmmt_batch_last_launch_count(self._h)
 
+    def uses_fused_path(self) -> bool:
+        return bool(F.lib().dmmt_batch_uses_fused_path(self._h))
+
     def encode_device(self, d_pixels: int, n: int, d_dense: int, dense_cap: int, d_offsets: int, d_lens: int):
         """Asynchronous; all pointers are device pointers (offsets: n + 1 u64, lens: n u64)."""
         F.check(F.lib().dmmt_batch_encode_device(self._h, C.c_void_p(d_pixels), n, C.c_void_p(d_dense), dense_cap,

@@ -146,6 +146,7 @@ int dmmt_batch_status(dmmt_batch *);              /* synchronises all slots; fir
 int dmmt_batch_set_scan_capacity(dmmt_batch *, size_t bytes_per_image);
 size_t dmmt_batch_worst_case_scan_bytes(const dmmt_batch *);
 int dmmt_batch_last_launch_count(const dmmt_batch *);
+int dmmt_batch_uses_fused_path(const dmmt_batch *);
 /* per-kernel timings (DMMT_T_*) summed over the sub-batches of the last dmmt_batch_encode_device
  * call; profiling serialises the slots. */
 int dmmt_batch_set_profiling(dmmt_batch *, int enabled);
@@ -169,6 +170,7 @@ int dmmt_plan_set_profiling(dmmt_plan *, int enabled);
  * 4:2:0 fast path (K1 tokenises in registers, no coefficient stream) applies; needed before
  * dmmt_plan_fetch(DMMT_FETCH_COEF).  Default 0. */
 int dmmt_plan_set_generic_path(dmmt_plan *, int generic);
+int dmmt_plan_uses_fused_path(const dmmt_plan *);  /* 1 when the fused 4:2:0 kernels run */
 int dmmt_plan_last_timings(dmmt_plan *, float *ms, int n);
 /* number of kernels launched by the last encode call on this plan */
 int dmmt_plan_last_launch_count(const dmmt_plan *);
