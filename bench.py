@@ -179,6 +179,26 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def bind_to_gpu_cpus(index: int):
+    """Restricts this process to the CPUs NVML reports as local to GPU `index`, so that first-touch
+    places the pinned host buffers of the e2e path on that GPU's NUMA node (one process per GPU)."""
+    try:
+        import pynvml as N
+
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 64
+        words = N.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to gpu {index}"
+    except Exception as e:  # no NVML / not permitted: keep the inherited affinity
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
 def free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -199,10 +219,16 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL prints its version there)
+    # are routed to stderr until the line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available() or F.lib().dmmt_device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: the encode path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_cpus(local)                         # pinned staging buffers land on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -288,7 +314,8 @@ def run_ours(args):
         torch.from_numpy(h_in.array).view(n, H, W, 3).copy_(d_px)      # stage the inputs on the host once
         torch.cuda.synchronize()
         h_offs, h_lens = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
-        batch_h = D.Batch(ctx, W, H, F.FMT_U8, 255, D.Options(F.P420, 8, 0), min(args.sub_batch, n), args.depth)
+        e2e_sub = max(1, min(args.sub_batch, max(8, n // 8)))   # enough sub-batches to overlap H2D, kernels, D2H
+        batch_h = D.Batch(ctx, W, H, F.FMT_U8, 255, D.Options(F.P420, 8, 0), e2e_sub, args.depth)
 
         def estep():
             batch_h.encode_host(h_in.ptr, n, h_out.ptr, h_out_cap, h_offs, h_lens)
@@ -307,12 +334,13 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         barrier()
         dt = reduce(dt, dist.ReduceOp.MAX if world > 1 else None)
-        d2h = reduce(float(int(h_offs[-1] + (h_lens[-1] + 15) // 16 * 16) + 16 * n + 8 * (n + (n + args.sub_batch - 1) // args.sub_batch)),
+        d2h = reduce(float(int(h_offs[-1] + (h_lens[-1] + 15) // 16 * 16) + 16 * n + 8 * (n + (n + e2e_sub - 1) // e2e_sub)),
                      dist.ReduceOp.SUM if world > 1 else None)
         e2e = {"value": total_px * K / dt / 1e6, "unit": UNIT, "ms_per_step": dt / K * 1e3,
                "h2d_bytes_per_step": int(reduce(float(n * img_bytes), dist.ReduceOp.SUM if world > 1 else None)),
                "d2h_bytes_per_step": int(d2h),
-               "api": "dmmt_batch_encode_host (pinned host pixels -> packed host files), all ranks"}
+               "api": "dmmt_batch_encode_host (pinned host pixels -> packed host files), all ranks",
+               "sub_batch": e2e_sub, "host_binding": numa}
         batch_h.close()
         h_in.close(), h_out.close()
 
@@ -387,6 +415,8 @@ def run_ours(args):
             "roofline": roofline, "kernels": kernels, "kernel_pass_total_ms": tm["total"],
             "cpu_baseline": cpu,
         }
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
     batch.close()
     ctx.close()
