@@ -79,9 +79,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         os.remove(AR)
     subprocess.check_call(["ar", "rcs", AR, *objs])
     if have_cli:
-        subprocess.check_call([nvcc, "-O2", "-std=c++17", "-I", os.path.join(HERE, "..", "include"),
-                               os.path.join(CSRC, "cli_main.cpp"), "-o", CLI, "-L", LIB, "-ldmmt_cuda",
-                               "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(CSRC, "cli_main.cpp"), "-o", CLI,
+                               "-L" + LIB, "-ldmmt_cuda", "-Wl,-rpath,$ORIGIN", "-pthread"])
     return SO
 
 

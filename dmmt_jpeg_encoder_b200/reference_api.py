@@ -311,12 +311,12 @@ def convert_ppm_to_jpeg(arguments: Arguments, context: Context | None = None) ->
     try:
         fin = open(arguments.input_file, "rb")
     except OSError as e:
-        raise UnableToOpenInputFileForReading(arguments.input_file, e.strerror) from e
+        raise UnableToOpenInputFileForReading(arguments.input_file, f"{e.strerror} (os error {e.errno})") from e
     with fin:
         try:
             fout = open(arguments.output_file, "wb")
         except OSError as e:
-            raise UnableToOpenOutputFileForWriting(arguments.output_file, e.strerror) from e
+            raise UnableToOpenOutputFileForWriting(arguments.output_file, f"{e.strerror} (os error {e.errno})") from e
         with fout:
             image = PPMImageReader(fin).read_image()
             options = JpegTransformationOptions.from_arguments(arguments)

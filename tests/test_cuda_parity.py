@@ -92,6 +92,22 @@ def test_reference_api_convert_ppm_to_jpeg(D, tmp_path, name):
     assert dst.read_bytes() == open(os.path.join(GOLDEN, "jpeg", f"{name}_P420.jpg"), "rb").read()
 
 
+@pytest.mark.parametrize("name", FIXTURES)
+@pytest.mark.parametrize("pname", list(PRESETS))
+def test_cpp_cli_binary_writes_golden_files(tmp_path, name, pname):
+    """The C++ front-end (dmmt-jpeg-encoder, mirror of src/main.rs + src/lib.rs:59-77) end to end."""
+    import subprocess
+
+    from dmmt_jpeg_encoder_b200 import build as B
+
+    text, _, _ = load_fixture(name)
+    src, dst = tmp_path / f"{name}.ppm", tmp_path / f"{name}.jpg"
+    src.write_bytes(text)
+    r = subprocess.run([B.build() and B.CLI, "-p", pname, str(src), str(dst)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "Conversion successful", r.stderr
+    assert dst.read_bytes() == open(os.path.join(GOLDEN, "jpeg", f"{name}_{pname}.jpg"), "rb").read()
+
+
 def test_jpeg_image_writer_f32_image_equals_sample_image(D, O):
     """Image<f32> (already normalised dots) and raw samples + max give the same bytes."""
     px = synth_image("photo", 77, 45, 5)

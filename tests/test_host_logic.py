@@ -138,9 +138,48 @@ def test_convert_reports_unopenable_input(tmp_path, capsys):
     missing = str(tmp_path / "nope.ppm")
     with pytest.raises(R.UnableToOpenInputFileForReading) as e:
         R.convert_ppm_to_jpeg(R.Arguments(missing, str(tmp_path / "o.jpg")))
-    assert str(e.value).startswith(f"Unable to open input file '{missing}' for reading: ")
+    assert str(e.value) == f"Unable to open input file '{missing}' for reading: No such file or directory (os error 2)"
     assert R.main(["prog", missing, str(tmp_path / "o.jpg")]) == 0          # main.rs: exit 0 either way
     assert "Conversion failed because of: Unable to open input file" in capsys.readouterr().err
+
+
+# ------------------------------------------------------------------------------ C++ front-end
+def _cli():
+    from dmmt_jpeg_encoder_b200 import build as B
+
+    B.build()
+    return B.CLI
+
+
+def test_cpp_cli_usage_errors_and_messages(tmp_path):
+    """dmmt-jpeg-encoder (csrc/cli_main.cpp + dmmt_host.hpp) mirrors src/main.rs + src/cli.rs: clap-style
+    usage errors exit 2; conversion failures print the reference's Display text and exit 0."""
+    import subprocess
+
+    cli = _cli()
+    r = subprocess.run([cli], capture_output=True, text=True)
+    assert r.returncode == 2 and "<input_file>" in r.stderr
+    for bad in (["-b", "12", "a", "b"], ["-q", "3", "a", "b"], ["-p", "p420", "a", "b"], ["-t", "x", "a", "b"], ["a", "b", "c"]):
+        assert subprocess.run([cli, *bad], capture_output=True).returncode == 2, bad
+    missing = str(tmp_path / "nope.ppm")
+    r = subprocess.run([cli, missing, str(tmp_path / "o.jpg")], capture_output=True, text=True)
+    assert r.returncode == 0
+    assert r.stderr.strip() == (f"Conversion failed because of: Unable to open input file '{missing}' for reading: "
+                                "No such file or directory (os error 2)")
+    # the P3 parse (host I/O) runs before any CUDA call, so its errors are testable without a GPU
+    cases = {"P6 1 1 255 0 0 0": "Expected token 'P3 Header' not found in PPM file",
+             "P3 x 1 255 0 0 0": "Parsing of token 'Width Header' failed",
+             "P3 1 1 255 0 0 70000": "Parsing of token 'Color Component Value' failed",
+             "P3 1 1 255 0 0 0 9 9": "Incomplete pixel parsed. Expected 3 components, but got 2.",
+             "P3 2 1 255 0 0 0": "Nubmer of pixels do not match the size, provided in header"}
+    for text, msg in cases.items():
+        src = tmp_path / "in.ppm"
+        src.write_text(text)
+        r = subprocess.run([cli, str(src), str(tmp_path / "o.jpg")], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stderr.strip() == "Conversion failed because of: " + msg, (text, r.stderr)
+        assert (tmp_path / "o.jpg").exists()          # created/truncated before parsing (lib.rs:60-61)
+    r = subprocess.run([cli, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--chroma_subsampling_preset" in r.stdout
 
 
 # --------------------------------------------------------------------------- sharded exchange
