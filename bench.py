@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--kind", default="photo", choices=["photo", "grad", "uniform"])
-    ap.add_argument("--sub-batch", type=int, default=64)
+    ap.add_argument("--sub-batch", type=int, default=128)
     ap.add_argument("--depth", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=64, help="images of the batch timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -257,7 +257,8 @@ def run_ours(args):
 
     stream = torch.cuda.Stream(device=dev)
     ctx = D.Context(local, stream.cuda_stream)
-    batch = D.Batch(ctx, W, H, F.FMT_U8, 255, D.Options(F.P420, 8, 0), min(args.sub_batch, n), args.depth)
+    dev_sub = max(1, min(args.sub_batch, max(16, n // 4)))   # at least 4 sub-batches so the streams overlap
+    batch = D.Batch(ctx, W, H, F.FMT_U8, 255, D.Options(F.P420, 8, 0), dev_sub, args.depth)
     dense_cap = n * (img_bytes // 4)
     d_dense = torch.empty(dense_cap, dtype=torch.uint8, device=dev)
     d_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)

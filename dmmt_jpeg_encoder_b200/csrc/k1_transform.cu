@@ -750,12 +750,13 @@ __global__ void __launch_bounds__(K1_THREADS, 5) k1_transform_p420(const __grid_
             cnt = 1u + __popc(mlo & ~1u) + __popc(mhi) + ((mhi >> 31) ? 0u : 1u);
             s_dc[slot] = (short)qv[0];
         }
-        if (u < 96) s_cnt[u] = 0;
-        __syncthreads();  // everybody has read the planes; s_hist and s_cnt are zero
-        if (active) s_cnt[slot] = cnt;
-        __syncthreads();
-        if (threadIdx.x < 32) {  // exclusive scan of the 96 per-block counts in stream order
-            const int l = threadIdx.x;
+        if (u < NUNITS) s_cnt[slot] = cnt;  // every slot is written: blocks beyond the padded image count 0
+        __syncthreads();  // everybody has read the planes; s_hist is zero; the 96 counts are complete
+        // exclusive scan of the 96 per-block counts in stream order, done redundantly by every warp
+        // (3 counts per lane + shuffles) so that no second barrier is needed
+        uint32_t my_off, total;
+        {
+            const int l = threadIdx.x & 31;
             const uint32_t c0 = s_cnt[3 * l], c1 = s_cnt[3 * l + 1], c2 = s_cnt[3 * l + 2];
             uint32_t inc = c0 + c1 + c2;
 #pragma unroll
@@ -763,18 +764,19 @@ __global__ void __launch_bounds__(K1_THREADS, 5) k1_transform_p420(const __grid_
                 const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
                 if (l >= d) inc += t;
             }
+            total = __shfl_sync(0xffffffffu, inc, 31);
             const uint32_t ex = inc - (c0 + c1 + c2);
-            s_cnt[3 * l] = ex, s_cnt[3 * l + 1] = ex + c0, s_cnt[3 * l + 2] = ex + c0 + c1;
-            if (l == 31) s_cnt[96] = inc;
+            // offset of `slot`: lane slot / 3 holds the prefix of its three slots
+            const uint32_t e0 = __shfl_sync(0xffffffffu, ex, slot / 3);
+            const uint32_t a0 = __shfl_sync(0xffffffffu, c0, slot / 3), a1 = __shfl_sync(0xffffffffu, c1, slot / 3);
+            my_off = e0 + (slot % 3 > 0 ? a0 : 0u) + (slot % 3 > 1 ? a1 : 0u);
         }
-        __syncthreads();
-        const uint32_t total = s_cnt[96];
         const uint32_t tile = (uint32_t)mrow * a.fo.tiles_x + (uint32_t)tile_x;
         uint32_t* g_tok = a.fo.tok + (size_t)img * a.fo.img_stride_words + (size_t)tile * a.fo.tile_cap;
         const bool fits = total <= a.fo.tile_cap;          // else DMMT_E_OVERFLOW: host retries with the worst-case capacity
         const bool in_smem = total <= S_CTOK_CAP;          // else (very dense tile) tokens go straight to global memory
         if (active) {
-            uint32_t off = s_cnt[slot];
+            uint32_t off = my_off;
             uint32_t* dst = in_smem ? s_ctok : g_tok;      // generic pointer, resolved once
             const bool store = in_smem || fits;
             const int tdc = comp ? T_CDC : T_YDC, tac = tdc + 1;
