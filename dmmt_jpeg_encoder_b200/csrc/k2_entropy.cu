@@ -513,6 +513,36 @@ __device__ __forceinline__ void load_run(const uint32_t* __restrict__ tok, uint3
 //   Shared: `words` is shared memory (host byte order), else the global big-endian stream.
 //   cap_bits: emission stops (counting continues) once the range would run past it -> *overflow.
 // Returns the bits of the whole range.
+// appends `len` (<= 31) bits to a lane's 64-bit accumulator; finished 32-bit words are OR-ed out
+template <bool Shared>
+struct LaneSink {
+    uint32_t* w;
+    unsigned long long acc;  // left-aligned pending bits
+    int fill;                // valid bits in acc (< 32 between appends)
+    __device__ __forceinline__ void init(uint32_t* words, unsigned long long pos) {
+        w = words + (pos >> 5);
+        acc = 0ull;
+        fill = (int)(pos & 31);
+    }
+    __device__ __forceinline__ void put(uint32_t code, int len) {
+        acc |= (unsigned long long)code << (64 - fill - len);
+        fill += len;
+        if (fill >= 32) {
+            const uint32_t v = (uint32_t)(acc >> 32);
+            if (v) atomicOr(w, Shared ? v : bswap32(v));
+            ++w;
+            acc <<= 32;
+            fill -= 32;
+        }
+    }
+    __device__ __forceinline__ void flush() {
+        if (fill > 0) {
+            const uint32_t v = (uint32_t)(acc >> 32);
+            if (v) atomicOr(w, Shared ? v : bswap32(v));
+        }
+    }
+};
+
 template <bool Shared>
 __device__ __forceinline__ unsigned long long emit_range(const uint32_t* __restrict__ tok, uint32_t begin,
                                                          uint32_t end, const uint32_t* s_enc, uint32_t zl_y,
@@ -522,16 +552,26 @@ __device__ __forceinline__ unsigned long long emit_range(const uint32_t* __restr
     const unsigned long long start = bitpos;
     for (uint32_t wbase = begin; wbase < end; wbase += K3_STEP) {
         const uint32_t base = wbase + lane * K3_RUN;
-        uint32_t t[K3_RUN], e[K3_RUN];
+        const int n = base < end ? (int)min((uint32_t)K3_RUN, end - base) : 0;  // valid tokens of this lane's run
+        uint32_t t[K3_RUN], val[K3_RUN], ln[K3_RUN];
         load_run(tok, base, end, t);
-        uint32_t nb = 0;
+        // code word + category bits of every token (encoder.rs:356-404); ZRLs are added below (rare)
+        uint32_t nb = 0, nzf = 0, lo = 0xFFFFFFFFu;
 #pragma unroll
         for (int i = 0; i < K3_RUN; i++) {
-            e[i] = s_enc[t[i] & 0x3FFu];
-            if (base + i < end) {
-                if ((e[i] >> 16) == 0u) sym_ok = false;  // Error::HuffmanSymbolNotPresentInTranslator
-                nb += token_bits(t[i], e[i], zl_y, zl_c);
-            }
+            const uint32_t e = s_enc[t[i] & 0x3FFu];
+            const uint32_t cat = t[i] & 15u;
+            ln[i] = i < n ? (e >> 16) + cat : 0u;
+            val[i] = ((e & 0xFFFFu) << cat) | (t[i] >> 16);
+            if (i < n) lo = min(lo, e), nzf |= t[i];
+            nb += ln[i];
+        }
+        if ((lo >> 16) == 0u) sym_ok = false;  // Error::HuffmanSymbolNotPresentInTranslator
+        nzf &= 0xC00u;
+        if (nzf) {
+#pragma unroll
+            for (int i = 0; i < K3_RUN; i++)
+                if (i < n) nb += ((t[i] >> 10) & 3u) * ((t[i] & 0x200u) ? zl_c : zl_y);
         }
         uint32_t inc = nb;
 #pragma unroll
@@ -542,37 +582,26 @@ __device__ __forceinline__ unsigned long long emit_range(const uint32_t* __restr
         const uint32_t step_bits = __shfl_sync(0xffffffffu, inc, 31);
         if (bitpos + step_bits > cap_bits) overflow = true;  // warp-uniform
         if (nb && !overflow) {
-            const unsigned long long pos = bitpos + (inc - nb);
-            uint32_t* w = words + (pos >> 5);
-            unsigned long long acc = 0ull;     // left-aligned pending bits
-            int fill = (int)(pos & 31);        // valid bits in acc (< 32 between appends)
-            auto put = [&](uint32_t code, int len) {  // len <= 31
-                acc |= (unsigned long long)code << (64 - fill - len);
-                fill += len;
-                if (fill >= 32) {
-                    const uint32_t v = (uint32_t)(acc >> 32);
-                    if (v) atomicOr(w, Shared ? v : bswap32(v));
-                    ++w;
-                    acc <<= 32;
-                    fill -= 32;
-                }
-            };
+            LaneSink<Shared> sink;
+            sink.init(words, bitpos + (inc - nb));
+            if (!nzf) {
 #pragma unroll
-            for (int i = 0; i < K3_RUN; i++) {
-                if (base + i < end) {
-                    uint32_t nz = (t[i] >> 10) & 3u;
-                    if (nz) {  // ZRL codes first (categorize.rs:139-142)
-                        const uint32_t z = s_enc[(t[i] & 0x300u) | 0xF0u];
-                        for (; nz; --nz) put(z & 0xFFFFu, (int)(z >> 16));
+                for (int i = 0; i < K3_RUN; i++)
+                    if (ln[i]) sink.put(val[i], (int)ln[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < K3_RUN; i++) {
+                    if (ln[i]) {
+                        uint32_t nz = (t[i] >> 10) & 3u;
+                        if (nz) {  // ZRL codes first (categorize.rs:139-142)
+                            const uint32_t z = s_enc[(t[i] & 0x300u) | 0xF0u];
+                            for (; nz; --nz) sink.put(z & 0xFFFFu, (int)(z >> 16));
+                        }
+                        sink.put(val[i], (int)ln[i]);
                     }
-                    const int cat = (int)(t[i] & 15u);
-                    put(((e[i] & 0xFFFFu) << cat) | (t[i] >> 16), (int)(e[i] >> 16) + cat);
                 }
             }
-            if (fill > 0) {
-                const uint32_t v = (uint32_t)(acc >> 32);
-                if (v) atomicOr(w, Shared ? v : bswap32(v));
-            }
+            sink.flush();
         }
         bitpos += step_bits;
     }
