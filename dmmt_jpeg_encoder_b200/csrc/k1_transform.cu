@@ -609,6 +609,64 @@ __device__ __forceinline__ uint32_t k1_token(int table, int sym, int nzrl, uint3
     return (uint32_t)sym | ((uint32_t)table << 8) | ((uint32_t)nzrl << 10) | (extra << 16);
 }
 
+// Tokens of one block (fused path): DC difference against the previous block of the same component
+// inside the tile (categorize.rs:157-161), then the walk over the non-zero AC positions of the staged
+// block (categorize.rs:132-151: run of zeros, one 0xF0 per 16 zeros, EOB 0x00 when the tail is zero).
+__device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, bool store, uint32_t off, unsigned short dcq,
+                                                    int slot, int m, int k, int comp, uint32_t mlo, uint32_t mhi,
+                                                    const short* s_dc, const uint4* s_stage, unsigned int* s_hist,
+                                                    uint32_t* dcpos) {
+    const int tdc = comp ? T_CDC : T_YDC, tac = tdc + 1;
+    bool ok = true;
+    {
+        const int ps = k == 0 ? slot - 3 : (k < 4 ? slot - 1 : slot - 6);
+        if ((k != 0 && k < 4) || m > 0) {
+            const int diff = (int)(short)((short)dcq - s_dc[ps]);
+            int cat = 0;
+            uint32_t bits = 0;
+            if (diff != 0) k1_cat_bits(diff, cat, bits);
+            ok &= cat <= 15;
+            atomicAdd(&s_hist[tdc * 256 + (cat & 15)], 1u);
+            if (store) dst[off] = k1_token(tdc, cat & 15, 0, bits);
+        } else {
+            // predictor is in the previous tile (or is the seed): k2_fix_dc finishes this token
+            if (k >= 4) dcpos[k - 4] = off;
+            if (store) dst[off] = (uint32_t)dcq << 16;
+        }
+        ++off;
+    }
+    const int16_t* sb = reinterpret_cast<const int16_t*>(s_stage + slot * 8);
+    const int sw = slot & 7;
+    int prev = 0;
+    uint32_t nzrl_total = 0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        uint32_t mk = half ? mhi : (mlo & ~1u);
+        while (mk) {
+            const int pos = 32 * half + __ffs((int)mk) - 1;
+            mk &= mk - 1;
+            const int run = pos - prev - 1;
+            prev = pos;
+            const int v = sb[(((pos >> 3) ^ sw) << 3) | (pos & 7)];
+            int cat;
+            uint32_t bits;
+            k1_cat_bits(v, cat, bits);
+            ok &= cat <= 15;
+            const int sym = ((run & 15) << 4) | (cat & 15);
+            nzrl_total += (uint32_t)(run >> 4);
+            atomicAdd(&s_hist[tac * 256 + sym], 1u);
+            if (store) dst[off] = k1_token(tac, sym, run >> 4, bits);
+            ++off;
+        }
+    }
+    if (nzrl_total) atomicAdd(&s_hist[tac * 256 + 0xF0], nzrl_total);
+    if (prev != 63) {
+        atomicAdd(&s_hist[tac * 256], 1u);
+        if (store) dst[off] = k1_token(tac, 0x00, 0, 0u);
+    }
+    return ok;
+}
+
 template <int FMT, bool FUSED>
 __global__ void __launch_bounds__(K1_THREADS, 5) k1_transform_p420(const __grid_constant__ K1Args a) {
     // planes as ROW-PAIR interleaved float4 = {v(x,2j), v(x,2j+1), v(x+1,2j), v(x+1,2j+1)}:
@@ -776,58 +834,11 @@ __global__ void __launch_bounds__(K1_THREADS, 5) k1_transform_p420(const __grid_
         const bool fits = total <= a.fo.tile_cap;          // else DMMT_E_OVERFLOW: host retries with the worst-case capacity
         const bool in_smem = total <= S_CTOK_CAP;          // else (very dense tile) tokens go straight to global memory
         if (active) {
-            uint32_t off = my_off;
-            uint32_t* dst = in_smem ? s_ctok : g_tok;      // generic pointer, resolved once
-            const bool store = in_smem || fits;
-            const int tdc = comp ? T_CDC : T_YDC, tac = tdc + 1;
-            bool ok = true;
-            {   // DC (categorize.rs:157-161): predictor = previous block of the same component in stream order
-                const int ps = k == 0 ? slot - 3 : (k < 4 ? slot - 1 : slot - 6);
-                if ((k != 0 && k < 4) || m > 0) {
-                    const int diff = (int)(short)((short)qv[0] - s_dc[ps]);
-                    int cat = 0;
-                    uint32_t bits = 0;
-                    if (diff != 0) k1_cat_bits(diff, cat, bits);
-                    ok &= cat <= 15;
-                    atomicAdd(&s_hist[tdc * 256 + (cat & 15)], 1u);
-                    if (store) dst[off] = k1_token(tdc, cat & 15, 0, bits);
-                } else {
-                    // predictor is in the previous tile (or is the seed): k2_fix_dc finishes this token
-                    if (k >= 4) a.fo.dcpos[((size_t)img * a.fo.tiles + tile) * 2 + (k - 4)] = off;
-                    if (store) dst[off] = (uint32_t)qv[0] << 16;
-                }
-                ++off;
-            }
-            // AC (categorize.rs:132-151): run of zeros; one 0xF0 per 16 zeros; EOB 0x00 when the tail is zero
-            const int16_t* sb = reinterpret_cast<const int16_t*>(s_stage + slot * 8);
-            const int sw = slot & 7;
-            int prev = 0;
-            uint32_t nzrl_total = 0;
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                uint32_t mk = half ? mhi : (mlo & ~1u);
-                while (mk) {
-                    const int pos = 32 * half + __ffs((int)mk) - 1;
-                    mk &= mk - 1;
-                    const int run = pos - prev - 1;
-                    prev = pos;
-                    const int v = sb[(((pos >> 3) ^ sw) << 3) | (pos & 7)];
-                    int cat;
-                    uint32_t bits;
-                    k1_cat_bits(v, cat, bits);
-                    ok &= cat <= 15;
-                    const int sym = ((run & 15) << 4) | (cat & 15);
-                    nzrl_total += (uint32_t)(run >> 4);
-                    atomicAdd(&s_hist[tac * 256 + sym], 1u);
-                    if (store) dst[off] = k1_token(tac, sym, run >> 4, bits);
-                    ++off;
-                }
-            }
-            if (nzrl_total) atomicAdd(&s_hist[tac * 256 + 0xF0], nzrl_total);
-            if (prev != 63) {
-                atomicAdd(&s_hist[tac * 256], 1u);
-                if (store) dst[off] = k1_token(tac, 0x00, 0, 0u);
-            }
+            const uint32_t dcp = ((uint32_t)img * a.fo.tiles + tile) * 2;
+            bool ok;
+            // CTA-uniform choice of the token destination, so the stores are plain STS / STG
+            if (in_smem) ok = p420_tokenize_block(s_ctok, true, my_off, qv[0], slot, m, k, comp, mlo, mhi, s_dc, s_stage, s_hist, a.fo.dcpos + dcp);
+            else ok = p420_tokenize_block(g_tok, fits, my_off, qv[0], slot, m, k, comp, mlo, mhi, s_dc, s_stage, s_hist, a.fo.dcpos + dcp);
             if (!ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_RANGE);
         }
         __syncthreads();
