@@ -531,14 +531,18 @@ __device__ __forceinline__ void quantize_block_packed(const K1Args& a, const f2 
 
 // Phase B of the P420 kernels: block `u` of the tile (stream slot m * 6 + k) -> 64 quantised
 // coefficients in NATURAL order.  Returns false for blocks of MCUs beyond the padded image.
-template <int FMT>
+// SYNC: all threads of the CTA call this; a barrier after the plane loads frees the plane storage
+// for reuse (staging area + token buffer of the fused path).
+template <int FMT, bool SYNC>
 __device__ __forceinline__ bool p420_block_coefs(const K1Args& a, int u, int mcus_here, const float4 (*sY)[8][16],
                                                  const float4 (*sCb)[4][16], const float4 (*sCr)[4][16],
                                                  const int* s_flag_p, unsigned short (&qv)[64], int& m, int& k,
                                                  int& comp) {
     constexpr int NYU = 64, NCU = 16;
     f2 P[4][8];  // P[j][c] = {d[2j][c], d[2j+1][c]}
-    if (u < NYU) {
+    if (SYNC && u >= NYU + 2 * NCU) {
+        // idle warp: only takes part in the barrier
+    } else if (u < NYU) {
         const int q = u >> 4, sx = u & 15;
         const int byl = q >> 1, p = q & 1;
         comp = 0, m = sx, k = byl * 2 + p;
@@ -561,6 +565,10 @@ __device__ __forceinline__ bool p420_block_coefs(const K1Args& a, int u, int mcu
                 const float4 t = pl[j][cc][sx];
                 P[j][2 * cc] = pk(t.x, t.y), P[j][2 * cc + 1] = pk(t.z, t.w);
             }
+    }
+    if constexpr (SYNC) {
+        __syncthreads();
+        if (u >= NYU + 2 * NCU) return false;
     }
     if (m >= mcus_here) return false;  // tile overhangs the padded image
 
@@ -668,14 +676,17 @@ __device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, 
 }
 
 template <int FMT, bool FUSED>
-__global__ void __launch_bounds__(K1_THREADS, 5) k1_transform_p420(const __grid_constant__ K1Args a) {
+__global__ void __launch_bounds__(K1_THREADS, FUSED ? 6 : 5) k1_transform_p420(const __grid_constant__ K1Args a) {
     // planes as ROW-PAIR interleaved float4 = {v(x,2j), v(x,2j+1), v(x+1,2j), v(x+1,2j+1)}:
     //   sY[row pair][16-byte chunk: 2 columns][strip], sC*[row pair][chunk][strip]
     __shared__ __align__(16) float4 s_planes[8 * 8 * 16 + 2 * 4 * 4 * 16];  // 24 KB: Y | Cb | Cr (reused for tokens)
     float4(*sY)[8][16] = reinterpret_cast<float4(*)[8][16]>(s_planes);
     float4(*sCb)[4][16] = reinterpret_cast<float4(*)[4][16]>(s_planes + 1024);
     float4(*sCr)[4][16] = reinterpret_cast<float4(*)[4][16]>(s_planes + 1280);
-    __shared__ uint4 s_stage[96 * 8];                    // quantised blocks of the tile in stream order (zig-zag, swizzled)
+    // quantised blocks of the tile in stream order (zig-zag, swizzled): own array on the coefficient path,
+    // the first half of the (dead) plane storage on the fused path
+    __shared__ uint4 s_stage_own[FUSED ? 1 : 96 * 8];
+    uint4* s_stage = FUSED ? reinterpret_cast<uint4*>(s_planes) : s_stage_own;
     __shared__ unsigned int s_hist[FUSED ? 1024 : 1];   // fused path: symbol counts of the tile
     __shared__ uint32_t s_cnt[FUSED ? 100 : 1];         // tokens per block, then exclusive offsets (+ total)
     __shared__ short s_dc[FUSED ? 96 : 1];
@@ -733,8 +744,15 @@ __global__ void __launch_bounds__(K1_THREADS, 5) k1_transform_p420(const __grid_
                 constexpr float kShift = 128.0f / 255.0f;
                 yy[q] = mul2(add2(add2(add2(mul2s(n[0], 0.299f), mul2s(n[1], 0.587f)), mul2s(n[2], 0.114f)), bc(-kShift)),
                              bc(255.0f));
-                cb[q] = mul2(add2(add2(mul2s(n[0], -0.1687f), mul2s(n[1], -0.3312f)), mul2s(n[2], 0.5f)), bc(255.0f));
-                cr[q] = mul2(add2(add2(mul2s(n[0], 0.5f), mul2s(n[1], -0.4186f)), mul2s(n[2], -0.0813f)), bc(255.0f));
+                if constexpr (FMT == DMMT_RGB_F32_NORM) {
+                    cb[q] = mul2(add2(add2(mul2s(n[0], -0.1687f), mul2s(n[1], -0.3312f)), mul2s(n[2], 0.5f)), bc(255.0f));
+                    cr[q] = mul2(add2(add2(mul2s(n[0], 0.5f), mul2s(n[1], -0.4186f)), mul2s(n[2], -0.0813f)), bc(255.0f));
+                } else {
+                    // x * 0.5 is exact for normalised integer samples, so s + x * 0.5 == fma(x, 0.5, s) bit for bit:
+                    // the two halvings ride on the additions they feed (one packed FFMA2 instead of 2 FMUL + FADD2)
+                    cb[q] = mul2(fma2(n[2], bc(0.5f), add2(mul2s(n[0], -0.1687f), mul2s(n[1], -0.3312f))), bc(255.0f));
+                    cr[q] = mul2(add2(fma2(n[0], bc(0.5f), mul2s(n[1], -0.4186f)), mul2s(n[2], -0.0813f)), bc(255.0f));
+                }
             }
             sY[sy][c][sx] = make_float4(lo_of(yy[0]), hi_of(yy[0]), lo_of(yy[1]), hi_of(yy[1]));
             // window (x,y),(x,y+1),(x+1,y),(x+1,y+1), f32 sum from 0, / 4 (subsampling.rs:108-122,231-236)
@@ -757,7 +775,8 @@ __global__ void __launch_bounds__(K1_THREADS, 5) k1_transform_p420(const __grid_
     unsigned short qv[64];
     int m = 0, k = 0, comp = 0;
     bool active = false;
-    if (u < NUNITS) active = p420_block_coefs<FMT>(a, u, mcus_here, sY, sCb, sCr, &s_flag, qv, m, k, comp);
+    if constexpr (FUSED) active = p420_block_coefs<FMT, true>(a, u, mcus_here, sY, sCb, sCr, &s_flag, qv, m, k, comp);
+    else if (u < NUNITS) active = p420_block_coefs<FMT, false>(a, u, mcus_here, sY, sCb, sCr, &s_flag, qv, m, k, comp);
     const int slot = m * BPM + k;
 
     // zig-zag by register renaming, two i16 per word, into the tile's staging area (slot = stream order)
@@ -799,8 +818,8 @@ __global__ void __launch_bounds__(K1_THREADS, 5) k1_transform_p420(const __grid_
         // and the tokens (k2_entropy.cu format) are written compactly in stream order.  The three DC
         // tokens whose predictor lives in the previous tile are left as place-holders carrying the raw
         // DC for k2_fix_dc.
-        uint32_t* s_ctok = reinterpret_cast<uint32_t*>(s_planes);  // planes are dead after the barrier below
-        constexpr uint32_t S_CTOK_CAP = sizeof(s_planes) / 4;
+        uint32_t* s_ctok = reinterpret_cast<uint32_t*>(s_planes) + 96 * 8 * 4;  // second half of the plane storage
+        constexpr uint32_t S_CTOK_CAP = sizeof(s_planes) / 4 - 96 * 8 * 4;
         for (int i = threadIdx.x; i < 1024; i += K1_THREADS) s_hist[i] = 0;
         uint32_t cnt = 0;
         if (active) {
@@ -809,7 +828,7 @@ __global__ void __launch_bounds__(K1_THREADS, 5) k1_transform_p420(const __grid_
             s_dc[slot] = (short)qv[0];
         }
         if (u < NUNITS) s_cnt[slot] = cnt;  // every slot is written: blocks beyond the padded image count 0
-        __syncthreads();  // everybody has read the planes; s_hist is zero; the 96 counts are complete
+        __syncthreads();  // s_hist is zero; the 96 counts are complete
         // exclusive scan of the 96 per-block counts in stream order, done redundantly by every warp
         // (3 counts per lane + shuffles) so that no second barrier is needed
         uint32_t my_off, total;
