@@ -438,3 +438,54 @@ def test_large_image_sharded_equals_unsharded(D, ctx, O):
     assert ctx.encode_sharded(px, 4, 255) == whole
     assert ctx.encode_sharded(px, 7, 255) == whole
     assert whole[:2] == b"\xff\xd8" and whole[-2:] == b"\xff\xd9"
+
+
+def test_random_fuzz_against_oracle(D, ctx, O):
+    """Seeded fuzz: random geometry, content, subsampling, quantisation preset, sample format and max value."""
+    rng = np.random.default_rng(20261018)
+    kinds = ("photo", "uniform", "grad")
+    for case in range(80):
+        w, h = int(rng.integers(1, 420)), int(rng.integers(1, 260))
+        preset, q = int(rng.integers(0, 3)), int(rng.integers(0, 7))
+        px = synth_image(kinds[case % 3], w, h, case)
+        if case % 7 == 3:                       # sparse content: mostly black with a few bright pixels
+            px = (px * (rng.random((h, w, 1)) > 0.97)).astype(np.uint8)
+        fmt = case % 4
+        if fmt == 0:
+            arr, mx = px, 255
+        elif fmt == 1:
+            mx = int(rng.choice([255, 1023, 4095, 65535]))
+            arr = (px.astype(np.uint32) * mx // 255).astype(np.uint16)
+        elif fmt == 2:
+            arr, mx = px.astype(np.float32) / np.float32(255), 1
+        else:
+            mx = int(rng.integers(16, 255))
+            arr = (px.astype(np.uint32) * mx // 255).astype(np.uint8)
+        got = ctx.encode(arr, mx, D.Options(preset, 8, q))
+        want = O.encode(arr, mx if fmt != 2 else 255, preset, 8, q).jpeg
+        assert got == want, (case, w, h, preset, q, fmt, mx)
+
+
+def test_config5_full_size_shards_equal_single_chain(D, ctx):
+    """BASELINE config 5 at FULL size (32768 x 32768, 3.2 GB of pixels): the MCU-row-sharded encode
+    (8 shards, here all on one GPU) is byte-identical to the single launch chain, the file is well formed
+    and every 0xFF of the scan is stuffed.  (The oracle would need ~50 GB and minutes at this size.)"""
+    import hashlib
+
+    from dmmt_jpeg_encoder_b200 import synth
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~60 GB of free device memory")
+    n = 32768
+    px = np.empty((n, n, 3), np.uint8)
+    for y0 in range(0, n, 2048):                 # generated on the device in slabs, staged on the host
+        px[y0:y0 + 2048] = synth.make("smooth", 5, 2048, n, "cuda", y0=y0).cpu().numpy()
+    whole = ctx.encode(px, 255)
+    assert whole[:2] == b"\xff\xd8" and whole[-2:] == b"\xff\xd9"
+    sof = whole.index(b"\xff\xc0")
+    assert whole[sof + 5:sof + 9] == bytes([n >> 8, n & 255, n >> 8, n & 255])
+    body = whole[whole.index(b"\xff\xda") + 14:-2]
+    assert b"\xff" not in body.replace(b"\xff\x00", b"")
+    sharded = ctx.encode_sharded(px, 8, 255)
+    assert hashlib.sha256(sharded).digest() == hashlib.sha256(whole).digest() and len(sharded) == len(whole)
