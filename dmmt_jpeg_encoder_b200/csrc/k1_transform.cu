@@ -644,7 +644,7 @@ __device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, 
         ++off;
     }
     const int16_t* sb = reinterpret_cast<const int16_t*>(s_stage + slot * 8);
-    const int sw = slot & 7;
+    const int sw8 = (slot & 7) << 3;
     int prev = 0;
     uint32_t nzrl_total = 0;
 #pragma unroll
@@ -655,7 +655,7 @@ __device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, 
             mk &= mk - 1;
             const int run = pos - prev - 1;
             prev = pos;
-            const int v = sb[(((pos >> 3) ^ sw) << 3) | (pos & 7)];
+            const int v = sb[pos ^ sw8];  // chunk (pos >> 3) lives at slot (pos >> 3) ^ (slot & 7)
             int cat;
             uint32_t bits;
             k1_cat_bits(v, cat, bits);
@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(K1_THREADS, FUSED ? 6 : 5) k1_transform_p420(c
     // the first half of the (dead) plane storage on the fused path
     __shared__ uint4 s_stage_own[FUSED ? 1 : 96 * 8];
     uint4* s_stage = FUSED ? reinterpret_cast<uint4*>(s_planes) : s_stage_own;
-    __shared__ unsigned int s_hist[FUSED ? 1024 : 1];   // fused path: symbol counts of the tile
+    __shared__ __align__(16) unsigned int s_hist[FUSED ? 1024 : 4];   // fused path: symbol counts of the tile
     __shared__ uint32_t s_cnt[FUSED ? 100 : 1];         // tokens per block, then exclusive offsets (+ total)
     __shared__ short s_dc[FUSED ? 96 : 1];
     __shared__ int s_flag;
@@ -820,7 +820,8 @@ __global__ void __launch_bounds__(K1_THREADS, FUSED ? 6 : 5) k1_transform_p420(c
         // DC for k2_fix_dc.
         uint32_t* s_ctok = reinterpret_cast<uint32_t*>(s_planes) + 96 * 8 * 4;  // second half of the plane storage
         constexpr uint32_t S_CTOK_CAP = sizeof(s_planes) / 4 - 96 * 8 * 4;
-        for (int i = threadIdx.x; i < 1024; i += K1_THREADS) s_hist[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 2; i++) reinterpret_cast<uint4*>(s_hist)[i * K1_THREADS + threadIdx.x] = make_uint4(0, 0, 0, 0);
         uint32_t cnt = 0;
         if (active) {
             // DC + one token per non-zero AC (ZRLs ride on it) + EOB unless coefficient 63 is non-zero
@@ -831,7 +832,7 @@ __global__ void __launch_bounds__(K1_THREADS, FUSED ? 6 : 5) k1_transform_p420(c
         __syncthreads();  // s_hist is zero; the 96 counts are complete
         // exclusive scan of the 96 per-block counts in stream order, done redundantly by every warp
         // (3 counts per lane + shuffles) so that no second barrier is needed
-        uint32_t my_off, total;
+        uint32_t my_off = 0, total;
         {
             const int l = threadIdx.x & 31;
             const uint32_t c0 = s_cnt[3 * l], c1 = s_cnt[3 * l + 1], c2 = s_cnt[3 * l + 2];
@@ -874,9 +875,16 @@ __global__ void __launch_bounds__(K1_THREADS, FUSED ? 6 : 5) k1_transform_p420(c
             ld[0] = s_dc[lm + 3], ld[1] = s_dc[lm + 4], ld[2] = s_dc[lm + 5], ld[3] = 0;
         }
         unsigned int* gh = a.hist + (size_t)img * 1024;
-        for (int i = threadIdx.x; i < 1024; i += K1_THREADS) {
-            const unsigned int v = s_hist[i];
-            if (v) atomicAdd(&gh[i], v);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {  // 4 bins per 128-bit load; most bins of a tile are empty
+            const int q4 = i * K1_THREADS + threadIdx.x;
+            const uint4 v = reinterpret_cast<const uint4*>(s_hist)[q4];
+            if (v.x | v.y | v.z | v.w) {
+                if (v.x) atomicAdd(&gh[4 * q4], v.x);
+                if (v.y) atomicAdd(&gh[4 * q4 + 1], v.y);
+                if (v.z) atomicAdd(&gh[4 * q4 + 2], v.z);
+                if (v.w) atomicAdd(&gh[4 * q4 + 3], v.w);
+            }
         }
     }
 }
