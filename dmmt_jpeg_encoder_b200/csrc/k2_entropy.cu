@@ -535,6 +535,21 @@ struct LaneSink {
             fill -= 32;
         }
     }
+    // same, without a branch: the OR is a predicated shared-memory reduction (1 <= len <= 31)
+    __device__ __forceinline__ void put_nobranch(uint32_t code, int len) {
+        static_assert(Shared, "shared-memory sink only");
+        acc |= (unsigned long long)code << (64 - fill - len);
+        fill += len;
+        const uint32_t hi = (uint32_t)(acc >> 32);
+        const uint32_t full = fill >= 32 ? 1u : 0u;
+        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(w);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.or.b32 [%0], %1;\n\t}" ::"r"(addr), "r"(hi),
+                     "r"(full ? hi : 0u)
+                     : "memory");
+        w += full;
+        acc = full ? acc << 32 : acc;
+        fill -= 32 * (int)full;
+    }
     __device__ __forceinline__ void flush() {
         if (fill > 0) {
             const uint32_t v = (uint32_t)(acc >> 32);
@@ -584,7 +599,13 @@ __device__ __forceinline__ unsigned long long emit_range(const uint32_t* __restr
         if (nb && !overflow) {
             LaneSink<Shared> sink;
             sink.init(words, bitpos + (inc - nb));
-            if (!nzf) {
+            if (Shared && !nzf && n == K3_RUN) {
+                // common case (full run, no ZRL): eight branch-free appends
+                if constexpr (Shared) {
+#pragma unroll
+                    for (int i = 0; i < K3_RUN; i++) sink.put_nobranch(val[i], (int)ln[i]);
+                }
+            } else if (!nzf) {
 #pragma unroll
                 for (int i = 0; i < K3_RUN; i++)
                     if (ln[i]) sink.put(val[i], (int)ln[i]);
