@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--kind", default="photo", choices=["photo", "grad", "uniform"])
     ap.add_argument("--sub-batch", type=int, default=128)
     ap.add_argument("--depth", type=int, default=3)
+    ap.add_argument("--exact-sub-batch", action="store_true", help="use --sub-batch as given (no per-rank heuristic)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="images of the batch timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -257,7 +258,9 @@ def run_ours(args):
 
     stream = torch.cuda.Stream(device=dev)
     ctx = D.Context(local, stream.cuda_stream)
-    dev_sub = max(1, min(args.sub_batch, max(16, n // 4)))   # at least 4 sub-batches so the streams overlap
+    dev_sub = max(1, min(args.sub_batch, max(16, (n + 1) // 2)))   # at least 2 sub-batches so the streams overlap
+    if args.exact_sub_batch:
+        dev_sub = max(1, min(args.sub_batch, n))
     batch = D.Batch(ctx, W, H, F.FMT_U8, 255, D.Options(F.P420, 8, 0), dev_sub, args.depth)
     dense_cap = n * (img_bytes // 4)
     d_dense = torch.empty(dense_cap, dtype=torch.uint8, device=dev)
