@@ -3,19 +3,21 @@
 //                                            (categorize.rs:21-169, symbol_counting.rs:55-74)
 //   K2b Huffman table construction + headers (symbol_counting.rs:85-94, huffman/length_limited.rs:37-134,
 //                                             huffman/encoder.rs:37-157, jpeg/encoder.rs:137-262)
-//   K3  token bit lengths -> decoupled look-back exclusive scan -> bit packing, one lane per token
+//   K3  tokens -> per-warp private bit buffers (one pass) -> decoupled look-back exclusive scan over
+//       chunks -> funnel-shift copy to the final bit phase
 //                                            (jpeg/encoder.rs:264-404, binary_stream.rs:38-96)
 //   K4  0xFF byte stuffing as a scan-compaction (segment_marker_injector.rs:13-30) + EOI
 // All file:line citations are relative to /root/reference/src.
 //
-// Input is K1's coefficient stream: int16 [n_blocks][64], zig-zag inside a block, MCU-interleaved
-// stream order.  K2 stages 256 blocks (32 KB) per CTA into shared memory with a 16-byte-chunk XOR
+// Generic path: the input is K1's coefficient stream: int16 [n_blocks][64], zig-zag inside a block,
+// MCU-interleaved stream order.  (On the fused 4:2:0 path K1 tokenises on-chip and K2 is replaced by
+// k2_fix_dc in k1_transform.cu; K2b..K5 are shared.)  K2 stages 256 blocks (32 KB) per CTA into shared memory with a 16-byte-chunk XOR
 // swizzle (chunk c of block b at slot c ^ (b & 7)), so the coalesced global loads AND the
 // thread-per-block 128-bit shared loads are both conflict-free; each thread then walks only the
 // NON-ZERO coefficients of its block (occupancy mask + ffs) ONCE, emitting one 32-bit token per
 // coded coefficient (the reference's CategorizedBlock, categorize.rs:101-104, flattened) and counting
-// symbols.  K3 never sees coefficients: it maps one lane to one token, so the serial, divergent walk
-// happens once per image and the bit packing is perfectly balanced.
+// symbols.  K3 never sees coefficients: every lane owns runs of 8 consecutive tokens, so the serial,
+// divergent walk happens once per image and the bit packing is balanced.
 //
 // Token word: bits 0-7 symbol, 8-9 table (T_*), 10-11 number of ZRL (0xF0) codes that precede the
 // symbol (categorize.rs:139-142), 16-31 the category's extra bits.  bits 0-9 index the encoder LUT.

@@ -158,9 +158,9 @@ void dmmt_host_free(void *);
 /* per-kernel CUDA-event timings of the last dmmt_plan_encode_* call (profiling must be enabled
  * first; it adds event records between the kernels).  ms[] order: DMMT_T_* */
 #define DMMT_T_K1_TRANSFORM 0 /* fused normalise/pad/YCbCr/subsample/DCT/quantise/zig-zag */
-#define DMMT_T_K2_HISTOGRAM 1
+#define DMMT_T_K2_HISTOGRAM 1 /* tokenise + histogram (generic path) / tile-boundary DC fix-up (fused path) */
 #define DMMT_T_K2B_TABLES 2
-#define DMMT_T_K3_PACK 3      /* bit-length + decoupled look-back scan + pack (incl. scan zeroing) */
+#define DMMT_T_K3_PACK 3      /* token packing + decoupled look-back scan (incl. scan zeroing) */
 #define DMMT_T_K4_STUFF 4
 #define DMMT_T_K5_COMPACT 5 /* packing of the output arena (0 when not run) */
 #define DMMT_T_TOTAL 6
