@@ -243,6 +243,18 @@ def test_generic_path_matches_on_420(D, ctx, O):
         plan.close()
 
 
+def test_zrl_heavy_blocks(D, ctx, O):
+    """(7,7) basis function: coefficient 63 is the only non-zero AC -> 3 ZRL codes per block, no EOB."""
+    y, x = np.mgrid[0:64, 0:80]
+    v = 128 + 60 * np.cos((2 * (x % 8) + 1) * 7 * np.pi / 16) * np.cos((2 * (y % 8) + 1) * 7 * np.pi / 16)
+    px = np.clip(np.rint(v), 0, 255).astype(np.uint8)[..., None].repeat(3, -1)
+    px[16:32, 16:48] = 40
+    for preset in (0, 1, 2):
+        r = O.encode(px, 255, preset, 8, 1)
+        assert r.hist[1][0xF0] > 0
+        assert ctx.encode(px, 255, D.Options(preset, 8, 1)) == r.jpeg
+
+
 def test_constant_and_extreme_images(D, ctx, O):
     for val in (0, 255, 128):
         px = np.full((40, 56, 3), val, np.uint8)
