@@ -531,18 +531,14 @@ __device__ __forceinline__ void quantize_block_packed(const K1Args& a, const f2 
 
 // Phase B of the P420 kernels: block `u` of the tile (stream slot m * 6 + k) -> 64 quantised
 // coefficients in NATURAL order.  Returns false for blocks of MCUs beyond the padded image.
-// SYNC: all threads of the CTA call this; a barrier after the plane loads frees the plane storage
-// for reuse (staging area + token buffer of the fused path).
-template <int FMT, bool SYNC>
+template <int FMT>
 __device__ __forceinline__ bool p420_block_coefs(const K1Args& a, int u, int mcus_here, const float4 (*sY)[8][16],
                                                  const float4 (*sCb)[4][16], const float4 (*sCr)[4][16],
                                                  const int* s_flag_p, unsigned short (&qv)[64], int& m, int& k,
                                                  int& comp) {
     constexpr int NYU = 64, NCU = 16;
     f2 P[4][8];  // P[j][c] = {d[2j][c], d[2j+1][c]}
-    if (SYNC && u >= NYU + 2 * NCU) {
-        // idle warp: only takes part in the barrier
-    } else if (u < NYU) {
+    if (u < NYU) {
         const int q = u >> 4, sx = u & 15;
         const int byl = q >> 1, p = q & 1;
         comp = 0, m = sx, k = byl * 2 + p;
@@ -565,10 +561,6 @@ __device__ __forceinline__ bool p420_block_coefs(const K1Args& a, int u, int mcu
                 const float4 t = pl[j][cc][sx];
                 P[j][2 * cc] = pk(t.x, t.y), P[j][2 * cc + 1] = pk(t.z, t.w);
             }
-    }
-    if constexpr (SYNC) {
-        __syncthreads();
-        if (u >= NYU + 2 * NCU) return false;
     }
     if (m >= mcus_here) return false;  // tile overhangs the padded image
 
@@ -775,12 +767,14 @@ __global__ void __launch_bounds__(K1_THREADS, FUSED ? 6 : 5) k1_transform_p420(c
     unsigned short qv[64];
     int m = 0, k = 0, comp = 0;
     bool active = false;
-    if constexpr (FUSED) active = p420_block_coefs<FMT, true>(a, u, mcus_here, sY, sCb, sCr, &s_flag, qv, m, k, comp);
-    else if (u < NUNITS) active = p420_block_coefs<FMT, false>(a, u, mcus_here, sY, sCb, sCr, &s_flag, qv, m, k, comp);
+    if (u < NUNITS) active = p420_block_coefs<FMT>(a, u, mcus_here, sY, sCb, sCr, &s_flag, qv, m, k, comp);
     const int slot = m * BPM + k;
 
-    // zig-zag by register renaming, two i16 per word, into the tile's staging area (slot = stream order)
+    // zig-zag by register renaming, two i16 per word.  Coefficient path: straight into the tile's staging
+    // area (slot = stream order).  Fused path: the words stay in registers until the plane storage, which
+    // the staging area and the token buffer reuse, is dead (after the barrier on the block counts).
     uint32_t mlo = 0, mhi = 0;  // occupancy mask of the block (fused path)
+    uint32_t wq[FUSED ? 32 : 1];
     if (active) {
         uint32_t mm[2] = {0u, 0u};
 #pragma unroll
@@ -789,14 +783,17 @@ __global__ void __launch_bounds__(K1_THREADS, FUSED ? 6 : 5) k1_transform_p420(c
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 asm("mov.b32 %0, {%1, %2};" : "=r"(w[j]) : "h"(qv[zz_at(8 * i + 2 * j)]), "h"(qv[zz_at(8 * i + 2 * j + 1)]));
-            s_stage[slot * 8 + (i ^ (slot & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
             if constexpr (FUSED) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) wq[4 * i + j] = w[j];
                 // 0xFFFF per non-zero half -> one flag byte per coefficient -> 8 mask bits (as in K2)
                 const uint32_t f01 = __byte_perm(__vcmpne2(w[0], 0u), __vcmpne2(w[1], 0u), 0x6420);
                 const uint32_t f23 = __byte_perm(__vcmpne2(w[2], 0u), __vcmpne2(w[3], 0u), 0x6420);
                 const uint32_t b01 = ((f01 & 0x08040201u) * 0x01010101u) >> 24;
                 const uint32_t b23 = ((f23 & 0x08040201u) * 0x01010101u) >> 24;
                 mm[i >> 2] |= (b01 | (b23 << 4)) << (8 * (i & 3));
+            } else {
+                s_stage[slot * 8 + (i ^ (slot & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
         mlo = mm[0], mhi = mm[1];
@@ -829,7 +826,12 @@ __global__ void __launch_bounds__(K1_THREADS, FUSED ? 6 : 5) k1_transform_p420(c
             s_dc[slot] = (short)qv[0];
         }
         if (u < NUNITS) s_cnt[slot] = cnt;  // every slot is written: blocks beyond the padded image count 0
-        __syncthreads();  // s_hist is zero; the 96 counts are complete
+        __syncthreads();  // everybody has read the planes; s_hist is zero; the 96 counts are complete
+        if (active) {  // now the plane storage is free: stage the block for the walk (read back by this thread only)
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                s_stage[slot * 8 + (i ^ (slot & 7))] = make_uint4(wq[4 * i], wq[4 * i + 1], wq[4 * i + 2], wq[4 * i + 3]);
+        }
         // exclusive scan of the 96 per-block counts in stream order, done redundantly by every warp
         // (3 counts per lane + shuffles) so that no second barrier is needed
         uint32_t my_off = 0, total;
