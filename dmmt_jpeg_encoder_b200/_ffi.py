@@ -110,6 +110,12 @@ SIGNATURES = {
     "dmmt_shard_pack": (C.c_int, [_VP, C.c_uint64, C.c_int, _U8P, C.POINTER(C.c_int)]),
     "dmmt_shard_stuff": (C.c_int, [_VP, C.c_uint8, C.c_int, C.c_int, C.c_int, C.POINTER(_VP), _U64P]),
     "dmmt_shard_launch_count": (C.c_int, [_VP]),
+    "dmmt_shard_launch_transform": (C.c_int, [_VP, _VP, _VP]),
+    "dmmt_shard_launch_histogram": (C.c_int, [_VP, _VP, _VP]),
+    "dmmt_shard_launch_tables": (C.c_int, [_VP, _VP, _VP]),
+    "dmmt_shard_launch_pack": (C.c_int, [_VP, _VP, C.c_int, _VP]),
+    "dmmt_shard_launch_stuff": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.POINTER(_VP), _VP]),
+    "dmmt_shard_status": (C.c_int, [_VP]),
 }
 
 _lib = None

@@ -61,7 +61,8 @@ struct K2bHostArgs {
 cudaError_t launch_k2b(const Geom& g, const K2bHostArgs& h, int n, cudaStream_t st);
 
 cudaError_t launch_zero_scan(uint32_t* scan, size_t stride_words, const ImgMeta* meta, int n,
-                             unsigned long long seed_bits, int blocks_per_image, cudaStream_t st);
+                             unsigned long long seed_bits, int blocks_per_image, cudaStream_t st,
+                             const unsigned long long* seed_src = nullptr);
 
 uint32_t k3_chunks(const Geom& g);
 uint32_t k4_max_chunks(size_t scan_cap_bytes);
@@ -70,7 +71,8 @@ uint32_t k4_max_chunks(size_t scan_cap_bytes);
 // n_segs > 0 (fused K1): region = tile, chunk c = tiles [8c, 8c + 8), one warp per tile.
 cudaError_t launch_k3(uint32_t n_chunks, uint32_t n_segs, int n, const TokBuf& tb, const EncTables* enc, ImgMeta* meta,
                       unsigned long long* lb_state, unsigned int* ticket, uint32_t* scan, size_t scan_stride_words,
-                      unsigned long long seed_bits, int pad_ones, cudaStream_t st);
+                      unsigned long long seed_bits, int pad_ones, cudaStream_t st,
+                      const unsigned long long* seed_src = nullptr);
 
 struct K4HostArgs {
     const uint8_t* scan;
@@ -87,10 +89,21 @@ struct K4HostArgs {
     unsigned long long seed_bits;
     int prepend_header, append_eoi;
     uint8_t or_first_byte;
+    const unsigned long long* seed_src = nullptr;  // device-resident shard exchange (see K4Args)
+    int owned_mode = 0;
+    const int* or_first_src = nullptr;
 };
 cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStream_t st);
 
 cudaError_t launch_last_dc(const Geom& g, const int16_t* coef, int16_t* d_out3, cudaStream_t st);
+// device-resident shard exchange helpers
+cudaError_t launch_shard_widen(const int16_t* last_dc3, int* out4, const unsigned int* hist, long long* hist64,
+                               const ImgMeta* meta, long long* bits_out, cudaStream_t st);
+cudaError_t launch_shard_narrow_seed(const int* seed4, int16_t* seed3, cudaStream_t st);
+cudaError_t launch_shard_tail(const uint8_t* scan, const ImgMeta* meta, const unsigned long long* bit_offset, int is_last,
+                              int* tail2, cudaStream_t st);
+cudaError_t launch_shard_prev_tail(const int* all_tail2, const long long* all_offs, const long long* all_bits, int rank,
+                                   int* out, cudaStream_t st);
 
 // K5: packs the n files of an output arena ([n][out_stride]) back to back (16-byte aligned
 // starts) into `dense`; offsets[0..n) and offsets[n] (= end) are written on the device.  chained:

@@ -27,6 +27,7 @@ struct dmmt_shard {
     unsigned long long seed_bits = 0;
     bool have_seed = false;
     unsigned int* h_hist = nullptr;  // pinned [1024]
+    int* d_prev_tail = nullptr;      // device-resident exchange: tail bits to OR into this shard's first byte
 };
 
 static int mcu_rows_of(int H, int subsampling) {
@@ -46,6 +47,7 @@ extern "C" void dmmt_shard_destroy(dmmt_shard* s) {
         dmmt_plan_destroy(s->plan);
     }
     if (s->h_hist) (void)cudaFreeHost(s->h_hist);
+    (void)cudaFree(s->d_prev_tail);
     delete s;
 }
 
@@ -74,6 +76,7 @@ extern "C" int dmmt_shard_create(dmmt_ctx* ctx, uint16_t full_width, uint16_t fu
                                    &s->plan);
     if (rc == DMMT_OK && cudaHostAlloc(&s->h_hist, 1024 * sizeof(unsigned int), cudaHostAllocDefault) != cudaSuccess)
         rc = DMMT_E_NOMEM;
+    if (rc == DMMT_OK && cudaMalloc(&s->d_prev_tail, sizeof(int)) != cudaSuccess) rc = DMMT_E_NOMEM;
     if (rc != DMMT_OK) {
         dmmt_shard_destroy(s);
         return rc;
@@ -253,6 +256,103 @@ extern "C" int dmmt_shard_stuff(dmmt_shard* s, uint8_t prev_tail_byte, int prev_
     if ((unsigned long long)(prev_tail_nbits & 7) != s->seed_bits) return DMMT_E_INVALID;  // exchange out of step
     DMMT_TRY(shard_stuff_launch(s, prev_tail_byte, is_first, is_last));
     return shard_stuff_collect(s, d_bytes, n_bytes);
+}
+
+// ---- device-resident exchange: the same five phases, asynchronous, every exchanged value in device
+// memory, so the caller can run its collectives (NCCL through torch.distributed) on the same stream
+// without a single host round trip between the phases.  Layouts: last_dc / seed_dc int32[4] (Y, Cb, Cr,
+// pad), hist int64[1024], bits / bit_offset int64, tail int32[2] = {byte, valid leading bits}.
+extern "C" int dmmt_shard_launch_transform(dmmt_shard* s, const void* d_pixels, int32_t* d_last_dc4) {
+    if (!s || !d_pixels || !d_last_dc4) return DMMT_E_INVALID;
+    DMMT_TRY(shard_transform_launch(s, d_pixels));
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(launch_shard_widen(p->d_last_dc, d_last_dc4, nullptr, nullptr, nullptr, nullptr, p->stream));
+    return DMMT_OK;
+}
+
+extern "C" int dmmt_shard_launch_histogram(dmmt_shard* s, const int32_t* d_seed_dc4, int64_t* d_hist1024) {
+    if (!s || !d_hist1024) return DMMT_E_INVALID;
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    DMMT_CUDA(launch_shard_narrow_seed(d_seed_dc4, p->d_seed_dc, p->stream));  // null: first shard, seeds 0
+    s->have_seed = true;
+    if (p->fused) DMMT_CUDA(launch_k2_fix_dc(p->fo, 1, p->hist, p->meta, p->d_seed_dc, p->stream));
+    else DMMT_CUDA(launch_k2(p->g, p->coef, p->coef_stride, 1, p->hist, p->meta, p->d_seed_dc, p->tb, p->stream));
+    DMMT_CUDA(launch_shard_widen(nullptr, nullptr, p->hist, reinterpret_cast<long long*>(d_hist1024), nullptr, nullptr,
+                                 p->stream));
+    p->last_launches += 3;
+    return DMMT_OK;
+}
+
+extern "C" int dmmt_shard_launch_tables(dmmt_shard* s, const int64_t* d_global_hist, int64_t* d_local_bits) {
+    if (!s || !d_global_hist || !d_local_bits) return DMMT_E_INVALID;
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    if (!p->d_out_own) DMMT_CUDA(cudaMalloc(&p->d_out_own, p->out_stride));
+    K2bHostArgs b{};
+    b.hist = p->hist, b.ghist = reinterpret_cast<const unsigned long long*>(d_global_hist), b.enc = p->enc, b.lens = p->lens;
+    b.meta = p->meta, b.out = p->d_out_own, b.out_stride = p->out_stride;
+    b.scan_cap_bits = (unsigned long long)p->scan_cap_bytes * 8 - 8;
+    b.W = p->sof_W, b.H = p->sof_H, b.bits_per_channel = p->opt.bits_per_channel;
+    b.qtab_luma = kQuantPresets[p->opt.qtable_preset][0];
+    b.qtab_chroma = kQuantPresets[p->opt.qtable_preset][1];
+    b.write_header = 1;
+    DMMT_CUDA(launch_k2b(p->g, b, 1, p->stream));
+    DMMT_CUDA(launch_shard_widen(nullptr, nullptr, nullptr, nullptr, p->meta, reinterpret_cast<long long*>(d_local_bits),
+                                 p->stream));
+    p->last_launches += 3;
+    return DMMT_OK;
+}
+
+extern "C" int dmmt_shard_launch_pack(dmmt_shard* s, const int64_t* d_global_bit_offset, int is_last, int32_t* d_tail2) {
+    if (!s || !d_global_bit_offset || !d_tail2) return DMMT_E_INVALID;
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    const auto* off = reinterpret_cast<const unsigned long long*>(d_global_bit_offset);
+    const int zero_blocks = (int)std::min<size_t>(std::max<size_t>(p->scan_cap_bytes / 65536, 1), 1024);
+    DMMT_CUDA(launch_zero_scan(p->scan, p->scan_stride_words, p->meta, 1, 0ull, zero_blocks, p->stream, off));
+    TokBuf tb = p->tb;
+    if (p->fused) tb.chunk_cap = p->fo.tile_cap;
+    DMMT_CUDA(launch_k3(p->fused ? p->n_chunks3f : p->n_chunks3, p->fused ? p->fo.tiles : 0u, 1, tb, p->enc, p->meta, p->lb3,
+                        p->tk3, p->scan, p->scan_stride_words, 0ull, is_last ? 1 : 0, p->stream, off));
+    DMMT_CUDA(launch_shard_tail(reinterpret_cast<const uint8_t*>(p->scan), p->meta, off, is_last, d_tail2, p->stream));
+    p->last_launches += 3;
+    return DMMT_OK;
+}
+
+extern "C" int dmmt_shard_launch_stuff(dmmt_shard* s, const int32_t* d_all_tail2, const int64_t* d_all_bit_offsets,
+                                       const int64_t* d_all_bits, int rank, int world, const uint8_t** d_bytes,
+                                       int64_t* d_n_bytes) {
+    if (!s || !d_all_tail2 || !d_all_bit_offsets || !d_all_bits || !d_bytes || !d_n_bytes || rank < 0 || rank >= world)
+        return DMMT_E_INVALID;
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    DMMT_CUDA(launch_shard_prev_tail(d_all_tail2, reinterpret_cast<const long long*>(d_all_bit_offsets),
+                                     reinterpret_cast<const long long*>(d_all_bits), rank, s->d_prev_tail, p->stream));
+    K4HostArgs k{};
+    k.scan = reinterpret_cast<const uint8_t*>(p->scan), k.scan_stride_bytes = p->scan_stride_words * 4;
+    k.meta = p->meta, k.lb_state = p->lb4, k.ticket = p->tk4, k.max_chunks = p->max_chunks4;
+    k.out = p->d_out_own, k.out_stride = p->out_stride, k.out_lens = reinterpret_cast<unsigned long long*>(d_n_bytes);
+    k.first_byte = 0, k.n_bytes_override = -1, k.seed_bits = 0;
+    k.prepend_header = rank == 0, k.append_eoi = rank == world - 1, k.or_first_byte = 0;
+    k.seed_src = reinterpret_cast<const unsigned long long*>(d_all_bit_offsets) + rank;
+    k.owned_mode = rank == world - 1 ? 2 : 1;
+    k.or_first_src = s->d_prev_tail;
+    DMMT_CUDA(launch_k4(k, 1, p->max_chunks4, p->stream));
+    p->last_launches += 2;
+    *d_bytes = p->d_out_own;
+    return DMMT_OK;
+}
+
+// device-side error flag of the shard's phases so far (synchronises)
+extern "C" int dmmt_shard_status(dmmt_shard* s) {
+    if (!s) return DMMT_E_INVALID;
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    ImgMeta m{};
+    DMMT_CUDA(cudaMemcpyAsync(&m, p->meta, sizeof m, cudaMemcpyDeviceToHost, p->stream));
+    DMMT_CUDA(cudaStreamSynchronize(p->stream));
+    return m.error;
 }
 
 extern "C" int dmmt_shard_launch_count(const dmmt_shard* s) { return s ? s->plan->last_launches : 0; }

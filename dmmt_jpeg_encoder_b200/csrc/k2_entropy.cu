@@ -445,7 +445,8 @@ __global__ void k_check_capacity(ImgMeta* meta, int n, unsigned long long cap_bi
 // Zeroes the words of the unstuffed scan buffers that K3 will OR into (sizes are only known on
 // the device): grid (Z, n), each row strides over that image's words.
 __global__ void k_zero_scan(uint32_t* scan, size_t scan_img_stride_words, const ImgMeta* meta,
-                            unsigned long long seed_bits) {
+                            unsigned long long seed_bits, const unsigned long long* seed_src) {
+    if (seed_src) seed_bits = *seed_src & 7ull;  // device-resident shard exchange
     const int img = blockIdx.y;
     if (meta[img].error) return;
     const unsigned long long words = (meta[img].scan_bits + seed_bits + 8 + 31) / 32 + 1;
@@ -468,6 +469,7 @@ struct K3Args {
     size_t scan_img_stride_words;
     unsigned long long seed_bits;  // bit offset of this shard's first bit inside its first byte/word (< 32)
     int pad_ones;                  // append the 1-padding after the last block (binary_stream.rs:89-96)
+    const unsigned long long* seed_src;  // optional: global bit offset of the shard in device memory (its low 3 bits are the seed)
 };
 
 // code bits of one token: ZRL codes + symbol code + category bits (encoder.rs:356-404)
@@ -699,7 +701,7 @@ __global__ void __launch_bounds__(EB) k3_pack(const K3Args a) {
         }
         if (tid == 0) s_prefix = lookback_exclusive(a.lb_state + (size_t)img * a.n_chunks, (int)chunk, chunk_bits);
         __syncthreads();
-        const unsigned long long g0 = a.seed_bits + s_prefix;        // global bit position of the chunk
+        const unsigned long long g0 = (a.seed_src ? (*a.seed_src & 7ull) : a.seed_bits) + s_prefix;  // global bit position of the chunk
         const unsigned long long p0 = g0 + wbase;                    // ... and of this warp's range
         if (!s_ovf) {
             // shifted copy of the private buffer to its place: destination word k holds relative bits
@@ -755,6 +757,11 @@ struct K4Args {
     int prepend_header;            // output starts after the header written by K2b
     int append_eoi;
     uint8_t or_first_byte;         // previous shard's tail bits, OR-ed into the first owned byte
+    // device-resident shard exchange: seed from the shard's global bit offset, owned bytes from the
+    // seed + scan bits (1: whole bytes only, 2: including the padded last byte), tail byte from memory
+    const unsigned long long* seed_src;
+    int owned_mode;
+    const int* or_first_src;
 };
 
 constexpr int K4_ROW = K4_BYTES_PER_THREAD + 16;              // padded row: conflict-free 128-bit access
@@ -772,9 +779,13 @@ __global__ void __launch_bounds__(K4_THREADS) k4_stuff(const K4Args a) {
         if (blockIdx.x == 0 && tid == 0 && a.out_lens) a.out_lens[img] = 0ull;
         return;
     }
+    const unsigned long long seed = a.seed_src ? (*a.seed_src & 7ull) : a.seed_bits;
     const unsigned long long total_bytes =
-        a.n_bytes_override >= 0 ? (unsigned long long)a.n_bytes_override
-                                : (a.seed_bits + meta->scan_bits + 7) / 8 - a.first_byte;
+        a.owned_mode == 1 ? (seed + meta->scan_bits) / 8
+        : a.owned_mode == 2 ? (seed + meta->scan_bits + 7) / 8
+        : a.n_bytes_override >= 0 ? (unsigned long long)a.n_bytes_override
+                                  : (seed + meta->scan_bits + 7) / 8 - a.first_byte;
+    const uint32_t or_first = a.or_first_src ? (uint32_t)(*a.or_first_src & 0xFF) : (uint32_t)a.or_first_byte;
     const uint32_t n_chunks = (uint32_t)((total_bytes + K4_CHUNK - 1) / K4_CHUNK);
     const uint32_t hdr = a.prepend_header ? meta->header_len : 0u;
     uint8_t* out = a.out + (size_t)img * a.out_stride;
@@ -830,7 +841,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_stuff(const K4Args a) {
         }
         const int tbase = tid * K4_BYTES_PER_THREAD;
         const int nvalid = max(0, min(K4_BYTES_PER_THREAD, (int)cvalid - tbase));
-        if (chunk == 0 && tid == 0 && a.or_first_byte) w[0] |= a.or_first_byte;
+        if (chunk == 0 && tid == 0 && or_first) w[0] |= or_first;
         uint32_t nff = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -1054,8 +1065,9 @@ cudaError_t launch_k2b(const Geom& g, const K2bHostArgs& h, int n, cudaStream_t 
 }
 
 cudaError_t launch_zero_scan(uint32_t* scan, size_t stride_words, const ImgMeta* meta, int n,
-                             unsigned long long seed_bits, int blocks_per_image, cudaStream_t st) {
-    k_zero_scan<<<dim3(blocks_per_image, n), 256, 0, st>>>(scan, stride_words, meta, seed_bits);
+                             unsigned long long seed_bits, int blocks_per_image, cudaStream_t st,
+                             const unsigned long long* seed_src) {
+    k_zero_scan<<<dim3(blocks_per_image, n), 256, 0, st>>>(scan, stride_words, meta, seed_bits, seed_src);
     return cudaGetLastError();
 }
 
@@ -1063,8 +1075,8 @@ uint32_t k4_max_chunks(size_t scan_cap_bytes) { return (uint32_t)((scan_cap_byte
 
 cudaError_t launch_k3(uint32_t n_chunks, uint32_t n_segs, int n, const TokBuf& tb, const EncTables* enc, ImgMeta* meta,
                       unsigned long long* lb_state, unsigned int* ticket, uint32_t* scan, size_t scan_stride_words,
-                      unsigned long long seed_bits, int pad_ones, cudaStream_t st) {
-    K3Args a{n_chunks, n_segs, tb, enc, meta, lb_state, ticket, scan, scan_stride_words, seed_bits, pad_ones};
+                      unsigned long long seed_bits, int pad_ones, cudaStream_t st, const unsigned long long* seed_src) {
+    K3Args a{n_chunks, n_segs, tb, enc, meta, lb_state, ticket, scan, scan_stride_words, seed_bits, pad_ones, seed_src};
     // CTAs take chunks by ticket and keep their encoder LUT in shared memory: about 6 CTAs per SM
     uint32_t per_image = (uint32_t)((148 * 6 + n - 1) / n);
     if (per_image < 4) per_image = 4;
@@ -1076,7 +1088,7 @@ cudaError_t launch_k3(uint32_t n_chunks, uint32_t n_segs, int n, const TokBuf& t
 cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStream_t st) {
     K4Args a{h.scan, h.scan_stride_bytes, h.meta, h.lb_state, h.ticket, h.max_chunks, h.out, h.out_stride,
              h.out_lens, h.first_byte, h.n_bytes_override, h.seed_bits, h.prepend_header, h.append_eoi,
-             h.or_first_byte};
+             h.or_first_byte, h.seed_src, h.owned_mode, h.or_first_src};
     // CTAs take chunks by ticket, so the grid only has to keep the device busy: about 8 CTAs per SM
     // over all images, never more than the chunks an image can have
     uint32_t per_image = (uint32_t)((148 * 8 + n - 1) / n);
@@ -1084,6 +1096,59 @@ cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStre
     if (grid_chunks == 0) grid_chunks = 1;
     if (per_image > grid_chunks) per_image = grid_chunks;
     k4_stuff<<<dim3(per_image, n), K4_THREADS, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ---- device-resident shard exchange helpers (dmmt_shard.cu) ------------------------------------
+namespace {
+__global__ void k_shard_widen(const int16_t* last_dc3, int* out4, const unsigned int* hist, long long* hist64,
+                              const ImgMeta* meta, long long* bits_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (last_dc3 && i < 4) out4[i] = i < 3 ? (int)last_dc3[i] : 0;
+    if (hist && i < 1024) hist64[i] = (long long)hist[i];
+    if (bits_out && i == 0) *bits_out = (long long)meta->scan_bits;
+}
+__global__ void k_shard_narrow_seed(const int* seed4, int16_t* seed3) {
+    if (threadIdx.x < 3) seed3[threadIdx.x] = seed4 ? (int16_t)seed4[threadIdx.x] : (int16_t)0;
+}
+// trailing partial byte of the shard: {byte, number of valid leading bits} (0 bits on the last shard)
+__global__ void k_shard_tail(const uint8_t* scan, const ImgMeta* meta, const unsigned long long* bit_offset, int is_last,
+                             int* tail2) {
+    const unsigned long long end = (*bit_offset & 7ull) + meta->scan_bits;
+    const int nb = is_last ? 0 : (int)(end & 7ull);
+    tail2[0] = nb ? (int)scan[end / 8] : 0;
+    tail2[1] = nb;
+}
+// tail bits this shard must OR into its first byte: the previous shard's, plus those of earlier shards
+// that did not complete a byte (a shard with fewer than 8 bits hands its predecessor's bits on)
+__global__ void k_shard_prev_tail(const int* all_tail2, const long long* all_offs, const long long* all_bits, int rank,
+                                  int* out) {
+    int acc = 0;
+    for (int r = 0; r < rank; r++) {
+        const bool incomplete = ((all_offs[r] & 7) + all_bits[r]) < 8;
+        acc = all_tail2[2 * r] | (incomplete ? acc : 0);
+    }
+    *out = acc;
+}
+}  // namespace
+
+cudaError_t launch_shard_widen(const int16_t* last_dc3, int* out4, const unsigned int* hist, long long* hist64,
+                               const ImgMeta* meta, long long* bits_out, cudaStream_t st) {
+    k_shard_widen<<<4, 256, 0, st>>>(last_dc3, out4, hist, hist64, meta, bits_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_shard_narrow_seed(const int* seed4, int16_t* seed3, cudaStream_t st) {
+    k_shard_narrow_seed<<<1, 32, 0, st>>>(seed4, seed3);
+    return cudaGetLastError();
+}
+cudaError_t launch_shard_tail(const uint8_t* scan, const ImgMeta* meta, const unsigned long long* bit_offset, int is_last,
+                              int* tail2, cudaStream_t st) {
+    k_shard_tail<<<1, 1, 0, st>>>(scan, meta, bit_offset, is_last, tail2);
+    return cudaGetLastError();
+}
+cudaError_t launch_shard_prev_tail(const int* all_tail2, const long long* all_offs, const long long* all_bits, int rank,
+                                   int* out, cudaStream_t st) {
+    k_shard_prev_tail<<<1, 1, 0, st>>>(all_tail2, all_offs, all_bits, rank, out);
     return cudaGetLastError();
 }
 

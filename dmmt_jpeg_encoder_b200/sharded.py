@@ -106,6 +106,33 @@ class CudaShardBackend(ShardBackend):
             return torch.empty(0, dtype=torch.uint8, device=f"cuda:{self.ctx.device}")
         return torch.as_tensor(_DevPtr(p.value, n.value), device=f"cuda:{self.ctx.device}")
 
+    # ---- device-resident exchange (asynchronous launches, device pointers) ----
+    def launch_transform(self, d_last_dc4: int):
+        F.check(F.lib().dmmt_shard_launch_transform(self._h, C.c_void_p(self.d_pixels), C.c_void_p(d_last_dc4)),
+                "dmmt_shard_launch_transform")
+
+    def launch_histogram(self, d_seed_dc4: int, d_hist: int):
+        F.check(F.lib().dmmt_shard_launch_histogram(self._h, C.c_void_p(d_seed_dc4) if d_seed_dc4 else None,
+                                                    C.c_void_p(d_hist)), "dmmt_shard_launch_histogram")
+
+    def launch_tables(self, d_global_hist: int, d_local_bits: int):
+        F.check(F.lib().dmmt_shard_launch_tables(self._h, C.c_void_p(d_global_hist), C.c_void_p(d_local_bits)),
+                "dmmt_shard_launch_tables")
+
+    def launch_pack(self, d_bit_offset: int, is_last: bool, d_tail2: int):
+        F.check(F.lib().dmmt_shard_launch_pack(self._h, C.c_void_p(d_bit_offset), int(is_last), C.c_void_p(d_tail2)),
+                "dmmt_shard_launch_pack")
+
+    def launch_stuff(self, d_all_tail2: int, d_all_offs: int, d_all_bits: int, rank: int, world: int, d_n_bytes: int) -> int:
+        p = C.c_void_p()
+        F.check(F.lib().dmmt_shard_launch_stuff(self._h, C.c_void_p(d_all_tail2), C.c_void_p(d_all_offs),
+                                                C.c_void_p(d_all_bits), rank, world, C.byref(p), C.c_void_p(d_n_bytes)),
+                "dmmt_shard_launch_stuff")
+        return p.value
+
+    def status(self):
+        F.check(F.lib().dmmt_shard_status(self._h), "dmmt_shard_status")
+
     def close(self):
         if self._h:
             F.lib().dmmt_shard_destroy(self._h)
@@ -119,8 +146,9 @@ class CudaShardBackend(ShardBackend):
 
 
 def encode_sharded(backend: ShardBackend, device: torch.device, group=None, dst: int = 0,
-                   timings: dict | None = None) -> bytes | None:
-    """Runs the phases of this rank's shard with the four exchanges; returns the file on `dst`."""
+                   timings: dict | None = None, to_host: bool = True):
+    """Runs the phases of this rank's shard with the four exchanges; returns the file on `dst`
+    (bytes, or the uint8 tensor on `device` when to_host is False) and None on the other ranks."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     is_first, is_last = rank == 0, rank == world - 1
 
@@ -176,7 +204,60 @@ def encode_sharded(backend: ShardBackend, device: torch.device, group=None, dst:
                 else:
                     dist.recv(out[off:off + all_n[r]], src=r, group=group)
             off += all_n[r]
-        return out.cpu().numpy().tobytes()
+        return out.cpu().numpy().tobytes() if to_host else out
+    if mine.numel():
+        dist.send(mine.contiguous(), dst=dst, group=group)
+    return None
+
+
+def encode_sharded_device(backend: CudaShardBackend, group=None, dst: int = 0, to_host: bool = True):
+    """Same result as encode_sharded, but every exchanged value stays in device memory: the five phases are
+    asynchronous launches on the context's stream (which must be torch's current stream) and the collectives
+    are NCCL calls on device tensors, so there is ONE host synchronisation in the whole encode (the byte
+    counts, needed to size the final send / recv)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", backend.ctx.device)
+    i32, i64 = dict(dtype=torch.int32, device=dev), dict(dtype=torch.int64, device=dev)
+
+    last = torch.empty(4, **i32)
+    backend.launch_transform(last.data_ptr())
+    all_dc = torch.empty(4 * world, **i32)
+    dist.all_gather_into_tensor(all_dc, last, group=group)                       # exchange 1: last DCs
+
+    hist = torch.empty(1024, **i64)
+    backend.launch_histogram(all_dc[4 * (rank - 1):].data_ptr() if rank else 0, hist.data_ptr())
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)                     # exchange 2: global histograms
+
+    bits = torch.empty(1, **i64)
+    backend.launch_tables(hist.data_ptr(), bits.data_ptr())
+    all_bits = torch.empty(world, **i64)
+    dist.all_gather_into_tensor(all_bits, bits, group=group)                     # exchange 3: bit counts
+    offs = torch.cumsum(all_bits, 0) - all_bits                                  # exclusive global bit offsets
+
+    tail = torch.empty(2, **i32)
+    backend.launch_pack(offs[rank:].data_ptr(), rank == world - 1, tail.data_ptr())
+    all_tail = torch.empty(2 * world, **i32)
+    dist.all_gather_into_tensor(all_tail, tail, group=group)                     # trailing partial bytes
+
+    n_bytes = torch.empty(1, **i64)
+    d_bytes = backend.launch_stuff(all_tail.data_ptr(), offs.data_ptr(), all_bits.data_ptr(), rank, world, n_bytes.data_ptr())
+    all_n = torch.empty(world, **i64)
+    dist.all_gather_into_tensor(all_n, n_bytes, group=group)                     # exchange 4: byte counts
+    sizes = [int(v) for v in all_n.cpu()]                                        # the only host synchronisation
+    backend.status()
+    mine = (torch.as_tensor(_DevPtr(d_bytes, sizes[rank]), device=dev) if sizes[rank]
+            else torch.empty(0, dtype=torch.uint8, device=dev))
+    if rank == dst:
+        out = torch.empty(sum(sizes), dtype=torch.uint8, device=dev)
+        off = 0
+        for r in range(world):
+            if sizes[r]:
+                if r == rank:
+                    out[off:off + sizes[r]].copy_(mine)
+                else:
+                    dist.recv(out[off:off + sizes[r]], src=r, group=group)
+            off += sizes[r]
+        return out.cpu().numpy().tobytes() if to_host else out
     if mine.numel():
         dist.send(mine.contiguous(), dst=dst, group=group)
     return None

@@ -227,6 +227,19 @@ int dmmt_shard_stuff(dmmt_shard *, uint8_t prev_tail_byte, int prev_tail_nbits, 
                      int is_last, const uint8_t **d_bytes, uint64_t *n_bytes);
 
 int dmmt_shard_launch_count(const dmmt_shard *);  /* kernels launched by the phases so far */
+/* Device-resident exchange: the same five phases, ASYNCHRONOUS on the context's stream, with every exchanged
+ * value in device memory, so the caller's collectives (NCCL all-gather / all-reduce on the same stream) need
+ * no host round trip between the phases.  Layouts: last_dc / seed_dc int32[4] (Y, Cb, Cr, pad), hist
+ * int64[1024], local bits / global bit offset int64, tail int32[2] = {byte, valid leading bits};
+ * dmmt_shard_launch_stuff takes the all-gathered tails [world][2], exclusive bit offsets [world] and bit
+ * counts [world] and writes this shard's stuffed byte count; *d_bytes is where the bytes will be. */
+int dmmt_shard_launch_transform(dmmt_shard *, const void *d_pixels, int32_t *d_last_dc4);
+int dmmt_shard_launch_histogram(dmmt_shard *, const int32_t *d_seed_dc4 /* NULL on the first shard */, int64_t *d_hist1024);
+int dmmt_shard_launch_tables(dmmt_shard *, const int64_t *d_global_hist1024, int64_t *d_local_bits);
+int dmmt_shard_launch_pack(dmmt_shard *, const int64_t *d_global_bit_offset, int is_last, int32_t *d_tail2);
+int dmmt_shard_launch_stuff(dmmt_shard *, const int32_t *d_all_tail2, const int64_t *d_all_bit_offsets,
+                            const int64_t *d_all_bits, int rank, int world, const uint8_t **d_bytes, int64_t *d_n_bytes);
+int dmmt_shard_status(dmmt_shard *);              /* synchronises; device-side error of the phases so far or 0 */
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    ctx = D.Context(local)
+    ctx = D.Context(local, torch.cuda.current_stream().cuda_stream)   # launches and NCCL share torch's stream
     failures = 0
     for (w, h, preset, use_oracle) in [(1000, 650, F.P420, True), (333, 97, F.P444, True), (640, 360, F.P422, True),
                                         (8192, 4096, F.P420, False)]:
@@ -34,10 +34,11 @@ def main():
         be = S.CudaShardBackend(ctx, d_px.data_ptr(), w, h, F.FMT_U8, 255, opts, b, e)
         assert be.pixel_bytes == d_px.numel(), (be.pixel_bytes, d_px.numel())
         out = S.encode_sharded(be, dev)
+        out_dev = S.encode_sharded_device(be)                          # device-resident exchange: same bytes
         if rank == 0:
             full = synth.make("smooth", 7, h, w, "cpu").numpy()
             whole = ctx.encode(full, 255, opts)
-            ok = out == whole
+            ok = out == whole and out_dev == whole
             if use_oracle:
                 from oracle import oracle as O
 
