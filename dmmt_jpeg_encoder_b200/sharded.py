@@ -210,54 +210,64 @@ def encode_sharded(backend: ShardBackend, device: torch.device, group=None, dst:
     return None
 
 
-def encode_sharded_device(backend: CudaShardBackend, group=None, dst: int = 0, to_host: bool = True):
+def encode_sharded_device(backend: CudaShardBackend, group=None, dst: int = 0, to_host: bool = True, mark=None):
     """Same result as encode_sharded, but every exchanged value stays in device memory: the five phases are
     asynchronous launches on the context's stream (which must be torch's current stream) and the collectives
     are NCCL calls on device tensors, so there is ONE host synchronisation in the whole encode (the byte
-    counts, needed to size the final send / recv)."""
+    counts, needed to size the final send / recv).  The small exchange tensors are cached on the backend."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = torch.device("cuda", backend.ctx.device)
-    i32, i64 = dict(dtype=torch.int32, device=dev), dict(dtype=torch.int64, device=dev)
-
-    last = torch.empty(4, **i32)
-    backend.launch_transform(last.data_ptr())
-    all_dc = torch.empty(4 * world, **i32)
-    dist.all_gather_into_tensor(all_dc, last, group=group)                       # exchange 1: last DCs
-
-    hist = torch.empty(1024, **i64)
-    backend.launch_histogram(all_dc[4 * (rank - 1):].data_ptr() if rank else 0, hist.data_ptr())
-    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)                     # exchange 2: global histograms
-
-    bits = torch.empty(1, **i64)
-    backend.launch_tables(hist.data_ptr(), bits.data_ptr())
-    all_bits = torch.empty(world, **i64)
-    dist.all_gather_into_tensor(all_bits, bits, group=group)                     # exchange 3: bit counts
-    offs = torch.cumsum(all_bits, 0) - all_bits                                  # exclusive global bit offsets
-
-    tail = torch.empty(2, **i32)
-    backend.launch_pack(offs[rank:].data_ptr(), rank == world - 1, tail.data_ptr())
-    all_tail = torch.empty(2 * world, **i32)
-    dist.all_gather_into_tensor(all_tail, tail, group=group)                     # trailing partial bytes
-
-    n_bytes = torch.empty(1, **i64)
-    d_bytes = backend.launch_stuff(all_tail.data_ptr(), offs.data_ptr(), all_bits.data_ptr(), rank, world, n_bytes.data_ptr())
-    all_n = torch.empty(world, **i64)
-    dist.all_gather_into_tensor(all_n, n_bytes, group=group)                     # exchange 4: byte counts
-    sizes = [int(v) for v in all_n.cpu()]                                        # the only host synchronisation
-    backend.status()
+    buf = getattr(backend, "_xbuf", None)
+    if buf is None or buf["world"] != world:
+        i32, i64 = dict(dtype=torch.int32, device=dev), dict(dtype=torch.int64, device=dev)
+        buf = backend._xbuf = {"world": world, "last": torch.empty(4, **i32), "all_dc": torch.empty(4 * world, **i32),
+                               "hist": torch.empty(1024, **i64), "bits": torch.empty(1, **i64),
+                               "all_bits": torch.empty(world, **i64), "offs": torch.empty(world, **i64),
+                               "tail": torch.empty(2, **i32), "all_tail": torch.empty(2 * world, **i32),
+                               "n_bytes": torch.empty(1, **i64), "all_n": torch.empty(world, **i64)}
+    b = buf
+    mark = mark or (lambda name: None)                                           # optional phase probe (tools/bench_sharded.py)
+    backend.launch_transform(b["last"].data_ptr())
+    dist.all_gather_into_tensor(b["all_dc"], b["last"], group=group)             # exchange 1: last DCs
+    mark("transform")
+    backend.launch_histogram(b["all_dc"].data_ptr() + 16 * (rank - 1) if rank else 0, b["hist"].data_ptr())
+    dist.all_reduce(b["hist"], op=dist.ReduceOp.SUM, group=group)                # exchange 2: global histograms
+    mark("histogram")
+    backend.launch_tables(b["hist"].data_ptr(), b["bits"].data_ptr())
+    dist.all_gather_into_tensor(b["all_bits"], b["bits"], group=group)           # exchange 3: bit counts
+    mark("tables")
+    torch.cumsum(b["all_bits"], 0, out=b["offs"])
+    b["offs"].sub_(b["all_bits"])                                                # exclusive global bit offsets
+    backend.launch_pack(b["offs"].data_ptr() + 8 * rank, rank == world - 1, b["tail"].data_ptr())
+    dist.all_gather_into_tensor(b["all_tail"], b["tail"], group=group)           # trailing partial bytes
+    mark("pack")
+    d_bytes = backend.launch_stuff(b["all_tail"].data_ptr(), b["offs"].data_ptr(), b["all_bits"].data_ptr(), rank, world,
+                                   b["n_bytes"].data_ptr())
+    dist.all_gather_into_tensor(b["all_n"], b["n_bytes"], group=group)           # exchange 4: byte counts
+    mark("stuff")
+    sizes = b["all_n"].tolist()                                                  # the only host synchronisation
+    mark("sync")
+    if min(sizes) <= 0:
+        backend.status()                                                         # a shard failed: raise its error
     mine = (torch.as_tensor(_DevPtr(d_bytes, sizes[rank]), device=dev) if sizes[rank]
             else torch.empty(0, dtype=torch.uint8, device=dev))
     if rank == dst:
         out = torch.empty(sum(sizes), dtype=torch.uint8, device=dev)
-        off = 0
+        ops, off = [], 0
         for r in range(world):
             if sizes[r]:
                 if r == rank:
                     out[off:off + sizes[r]].copy_(mine)
                 else:
-                    dist.recv(out[off:off + sizes[r]], src=r, group=group)
+                    ops.append(dist.P2POp(dist.irecv, out[off:off + sizes[r]], r, group))
             off += sizes[r]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):                                # all shards arrive concurrently
+                w.wait()
+        mark("gather")
         return out.cpu().numpy().tobytes() if to_host else out
     if mine.numel():
-        dist.send(mine.contiguous(), dst=dst, group=group)
+        for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, mine, dst, group)]):
+            w.wait()
+    mark("gather")
     return None

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--size", type=int, default=32768)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--phases", action="store_true", help="also report per-phase device and enqueue times (device exchange only)")
     ap.add_argument("--host-exchange", action="store_true", help="exchange through host values (dmmt_shard_* phases)")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -49,18 +50,35 @@ def main():
     be = S.CudaShardBackend(ctx, d_px.data_ptr(), n, n, F.FMT_U8, 255, opts, b, e)
     out = None
     times = []
+    phase_dev, phase_cpu = {}, {}
     for it in range(a.warmup + a.steps):
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         # the file stays in rank 0's HBM, like bench.py's `value`
-        out = S.encode_sharded(be, dev, to_host=False) if a.host_exchange else S.encode_sharded_device(be, to_host=False)
+        marks = []
+
+        def mark(name):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev, time.perf_counter()))
+        if a.phases and not a.host_exchange:
+            mark("start")
+        out = (S.encode_sharded(be, dev, to_host=False) if a.host_exchange
+               else S.encode_sharded_device(be, to_host=False, mark=mark if a.phases else None))
         torch.cuda.synchronize()
+        if marks and it >= a.warmup:
+            for (_, e0, c0), (name, e1, c1) in zip(marks, marks[1:]):
+                phase_dev[name] = phase_dev.get(name, 0.0) + e0.elapsed_time(e1) / a.steps
+                phase_cpu[name] = phase_cpu.get(name, 0.0) + (c1 - c0) * 1e3 / a.steps
         dist.barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         if it >= a.warmup:
             times.append(float(dt.item()))
+    if a.phases and not a.host_exchange:
+        allp = [None] * world
+        dist.all_gather_object(allp, {"device_ms": phase_dev, "enqueue_ms": phase_cpu})
     if rank == 0:
         ms = sum(times) / len(times) * 1e3
         line = {"metric": "encoded MPixel/s", "config": {"workload": f"one synthetic {n}x{n} RGB u8 image ('smooth'), 4:2:0, "
@@ -68,6 +86,8 @@ def main():
                 "exchange": "host values" if a.host_exchange else "device-resident (one host sync)", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "value": n * n / ms / 1e3,
                 "unit": "MPixel/s", "file_bytes": out.numel(), "bytes_per_pixel": out.numel() / (n * n),
                 "timing": "wall clock between barriers, device synchronised, max over ranks"}
+        if a.phases and not a.host_exchange:
+            line["phases_per_rank"] = [{k: {n_: round(v, 3) for n_, v in d.items()} for k, d in p_.items()} for p_ in allp]
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
