@@ -116,6 +116,14 @@ SIGNATURES = {
     "dmmt_shard_launch_pack": (C.c_int, [_VP, _VP, C.c_int, _VP]),
     "dmmt_shard_launch_stuff": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.POINTER(_VP), _VP]),
     "dmmt_shard_status": (C.c_int, [_VP]),
+    "dmmt_shard_out_stride": (C.c_size_t, [_VP]),
+    "dmmt_device_alloc": (C.c_int, [_VP, C.c_size_t, C.POINTER(_VP)]),
+    "dmmt_device_free": (C.c_int, [_VP, _VP]),
+    "dmmt_peer_export": (C.c_int, [_VP, _VP, C.c_char_p]),
+    "dmmt_peer_open": (C.c_int, [_VP, C.c_char_p, C.POINTER(_VP)]),
+    "dmmt_peer_close": (C.c_int, [_VP, _VP]),
+    "dmmt_shard_launch_count_bytes": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
+    "dmmt_shard_launch_stuff_into": (C.c_int, [_VP, _VP, C.c_int, C.c_int, _VP, C.c_size_t, _VP, _VP]),
 }
 
 _lib = None

@@ -92,6 +92,7 @@ struct K4HostArgs {
     const unsigned long long* seed_src = nullptr;  // device-resident shard exchange (see K4Args)
     int owned_mode = 0;
     const int* or_first_src = nullptr;
+    const unsigned long long* base_src = nullptr;  // peer-memory gather: byte offset of the shard in the file
 };
 cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStream_t st);
 
@@ -99,6 +100,12 @@ cudaError_t launch_last_dc(const Geom& g, const int16_t* coef, int16_t* d_out3, 
 // device-resident shard exchange helpers
 cudaError_t launch_shard_widen(const int16_t* last_dc3, int* out4, const unsigned int* hist, long long* hist64,
                                const ImgMeta* meta, long long* bits_out, cudaStream_t st);
+cudaError_t launch_shard_count_bytes(const uint8_t* scan, const ImgMeta* meta, const unsigned long long* seed_src,
+                                     int owned_mode, const int* or_first_src, int is_first, int is_last,
+                                     unsigned long long* ctr2, long long* n_bytes, cudaStream_t st);
+cudaError_t launch_shard_copy_header(const uint8_t* own_out, const ImgMeta* meta, uint8_t* file, size_t capacity,
+                                     cudaStream_t st);
+cudaError_t launch_shard_result(const ImgMeta* meta, long long* out2, cudaStream_t st);
 cudaError_t launch_shard_narrow_seed(const int* seed4, int16_t* seed3, cudaStream_t st);
 cudaError_t launch_shard_tail(const uint8_t* scan, const ImgMeta* meta, const unsigned long long* bit_offset, int is_last,
                               int* tail2, cudaStream_t st);

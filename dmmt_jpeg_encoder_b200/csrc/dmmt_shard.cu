@@ -28,6 +28,7 @@ struct dmmt_shard {
     bool have_seed = false;
     unsigned int* h_hist = nullptr;  // pinned [1024]
     int* d_prev_tail = nullptr;      // device-resident exchange: tail bits to OR into this shard's first byte
+    unsigned long long* d_count_ctr = nullptr;  // [2] self-resetting counters of k_shard_count_bytes
 };
 
 static int mcu_rows_of(int H, int subsampling) {
@@ -48,6 +49,7 @@ extern "C" void dmmt_shard_destroy(dmmt_shard* s) {
     }
     if (s->h_hist) (void)cudaFreeHost(s->h_hist);
     (void)cudaFree(s->d_prev_tail);
+    (void)cudaFree(s->d_count_ctr);
     delete s;
 }
 
@@ -77,6 +79,9 @@ extern "C" int dmmt_shard_create(dmmt_ctx* ctx, uint16_t full_width, uint16_t fu
     if (rc == DMMT_OK && cudaHostAlloc(&s->h_hist, 1024 * sizeof(unsigned int), cudaHostAllocDefault) != cudaSuccess)
         rc = DMMT_E_NOMEM;
     if (rc == DMMT_OK && cudaMalloc(&s->d_prev_tail, sizeof(int)) != cudaSuccess) rc = DMMT_E_NOMEM;
+    if (rc == DMMT_OK && (cudaMalloc(&s->d_count_ctr, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+                          cudaMemset(s->d_count_ctr, 0, 2 * sizeof(unsigned long long)) != cudaSuccess))
+        rc = DMMT_E_NOMEM;
     if (rc != DMMT_OK) {
         dmmt_shard_destroy(s);
         return rc;
@@ -86,6 +91,7 @@ extern "C" int dmmt_shard_create(dmmt_ctx* ctx, uint16_t full_width, uint16_t fu
 }
 
 extern "C" size_t dmmt_shard_pixel_bytes(const dmmt_shard* s) { return s ? s->plan->pixel_bytes : 0; }
+extern "C" size_t dmmt_shard_out_stride(const dmmt_shard* s) { return s ? s->plan->out_stride : 0; }
 extern "C" size_t dmmt_shard_pixel_offset(const dmmt_shard* s) {
     if (!s) return 0;
     const size_t pb = s->plan->fmt == DMMT_RGB_U8 ? 3 : (s->plan->fmt == DMMT_RGB_U16 ? 6 : 12);
@@ -341,6 +347,94 @@ extern "C" int dmmt_shard_launch_stuff(dmmt_shard* s, const int32_t* d_all_tail2
     DMMT_CUDA(launch_k4(k, 1, p->max_chunks4, p->stream));
     p->last_launches += 2;
     *d_bytes = p->d_out_own;
+    return DMMT_OK;
+}
+
+// ---- peer-memory gather: K4 of every shard writes straight into the destination rank's file --------------
+// The file buffer is plain cudaMalloc memory on the destination device; the other ranks (one process per GPU)
+// map it through CUDA IPC and their K4 stores travel over NVLink, so there is no separate gather step.
+extern "C" int dmmt_device_alloc(dmmt_ctx* ctx, size_t bytes, void** d_ptr) {
+    if (!ctx || !d_ptr || bytes == 0) return DMMT_E_INVALID;
+    *d_ptr = nullptr;
+    DMMT_CUDA(cudaSetDevice(ctx->device));
+    if (cudaMalloc(d_ptr, bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return DMMT_E_NOMEM;
+    }
+    return DMMT_OK;
+}
+extern "C" int dmmt_device_free(dmmt_ctx* ctx, void* d_ptr) {
+    if (!ctx) return DMMT_E_INVALID;
+    DMMT_CUDA(cudaSetDevice(ctx->device));
+    DMMT_CUDA(cudaFree(d_ptr));
+    return DMMT_OK;
+}
+static_assert(sizeof(cudaIpcMemHandle_t) == DMMT_PEER_HANDLE_BYTES, "peer handle size");
+extern "C" int dmmt_peer_export(dmmt_ctx* ctx, void* d_ptr, uint8_t handle[DMMT_PEER_HANDLE_BYTES]) {
+    if (!ctx || !d_ptr || !handle) return DMMT_E_INVALID;
+    DMMT_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    DMMT_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+    std::memcpy(handle, &h, sizeof h);
+    return DMMT_OK;
+}
+extern "C" int dmmt_peer_open(dmmt_ctx* ctx, const uint8_t handle[DMMT_PEER_HANDLE_BYTES], void** d_ptr) {
+    if (!ctx || !handle || !d_ptr) return DMMT_E_INVALID;
+    *d_ptr = nullptr;
+    DMMT_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    DMMT_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DMMT_OK;
+}
+extern "C" int dmmt_peer_close(dmmt_ctx* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return DMMT_E_INVALID;
+    DMMT_CUDA(cudaSetDevice(ctx->device));
+    DMMT_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return DMMT_OK;
+}
+
+// phase 5a: the stuffed size of this shard's bytes, known BEFORE K4 runs, so that the byte offsets of all
+// shards in the file can be exchanged first and K4 can write to its final place
+extern "C" int dmmt_shard_launch_count_bytes(dmmt_shard* s, const int32_t* d_all_tail2, const int64_t* d_all_bit_offsets,
+                                             const int64_t* d_all_bits, int rank, int world, int64_t* d_n_bytes) {
+    if (!s || !d_all_tail2 || !d_all_bit_offsets || !d_all_bits || !d_n_bytes || rank < 0 || rank >= world)
+        return DMMT_E_INVALID;
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    DMMT_CUDA(launch_shard_prev_tail(d_all_tail2, reinterpret_cast<const long long*>(d_all_bit_offsets),
+                                     reinterpret_cast<const long long*>(d_all_bits), rank, s->d_prev_tail, p->stream));
+    DMMT_CUDA(launch_shard_count_bytes(reinterpret_cast<const uint8_t*>(p->scan), p->meta,
+                                       reinterpret_cast<const unsigned long long*>(d_all_bit_offsets) + rank,
+                                       rank == world - 1 ? 2 : 1, s->d_prev_tail, rank == 0, rank == world - 1,
+                                       s->d_count_ctr, reinterpret_cast<long long*>(d_n_bytes), p->stream));
+    p->last_launches += 2;
+    return DMMT_OK;
+}
+
+// phase 5b: K4 straight into the file at *d_byte_offset (exclusive sum of the all-gathered counts of 5a);
+// d_file may be another device's memory (dmmt_peer_open).  d_result2 = {end offset in the file, error}.
+extern "C" int dmmt_shard_launch_stuff_into(dmmt_shard* s, const int64_t* d_all_bit_offsets, int rank, int world,
+                                            uint8_t* d_file, size_t file_capacity, const int64_t* d_byte_offset,
+                                            int64_t* d_result2) {
+    if (!s || !d_all_bit_offsets || !d_file || !d_byte_offset || !d_result2 || rank < 0 || rank >= world)
+        return DMMT_E_INVALID;
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    if (rank == 0) DMMT_CUDA(launch_shard_copy_header(p->d_out_own, p->meta, d_file, file_capacity, p->stream));
+    K4HostArgs k{};
+    k.scan = reinterpret_cast<const uint8_t*>(p->scan), k.scan_stride_bytes = p->scan_stride_words * 4;
+    k.meta = p->meta, k.lb_state = p->lb4, k.ticket = p->tk4, k.max_chunks = p->max_chunks4;
+    k.out = d_file, k.out_stride = file_capacity, k.out_lens = nullptr;
+    k.first_byte = 0, k.n_bytes_override = -1, k.seed_bits = 0;
+    k.prepend_header = rank == 0, k.append_eoi = rank == world - 1, k.or_first_byte = 0;
+    k.seed_src = reinterpret_cast<const unsigned long long*>(d_all_bit_offsets) + rank;
+    k.owned_mode = rank == world - 1 ? 2 : 1;
+    k.or_first_src = s->d_prev_tail;
+    k.base_src = reinterpret_cast<const unsigned long long*>(d_byte_offset);
+    DMMT_CUDA(launch_k4(k, 1, p->max_chunks4, p->stream));
+    DMMT_CUDA(launch_shard_result(p->meta, reinterpret_cast<long long*>(d_result2), p->stream));
+    p->last_launches += rank == 0 ? 3 : 2;
     return DMMT_OK;
 }
 

@@ -762,6 +762,9 @@ struct K4Args {
     const unsigned long long* seed_src;
     int owned_mode;
     const int* or_first_src;
+    // peer-memory gather: `out` is the whole file (possibly another device's memory) and the shard's
+    // bytes start *base_src bytes into it (after the header on the first shard)
+    const unsigned long long* base_src;
 };
 
 constexpr int K4_ROW = K4_BYTES_PER_THREAD + 16;              // padded row: conflict-free 128-bit access
@@ -787,7 +790,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_stuff(const K4Args a) {
                                   : (seed + meta->scan_bits + 7) / 8 - a.first_byte;
     const uint32_t or_first = a.or_first_src ? (uint32_t)(*a.or_first_src & 0xFF) : (uint32_t)a.or_first_byte;
     const uint32_t n_chunks = (uint32_t)((total_bytes + K4_CHUNK - 1) / K4_CHUNK);
-    const uint32_t hdr = a.prepend_header ? meta->header_len : 0u;
+    const unsigned long long hdr = (a.prepend_header ? meta->header_len : 0u) + (a.base_src ? *a.base_src : 0ull);
     uint8_t* out = a.out + (size_t)img * a.out_stride;
     if (n_chunks == 0) {  // nothing owned (possible for a shard); still terminate the file
         if (blockIdx.x == 0 && tid == 0) {
@@ -1088,7 +1091,7 @@ cudaError_t launch_k3(uint32_t n_chunks, uint32_t n_segs, int n, const TokBuf& t
 cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStream_t st) {
     K4Args a{h.scan, h.scan_stride_bytes, h.meta, h.lb_state, h.ticket, h.max_chunks, h.out, h.out_stride,
              h.out_lens, h.first_byte, h.n_bytes_override, h.seed_bits, h.prepend_header, h.append_eoi,
-             h.or_first_byte, h.seed_src, h.owned_mode, h.or_first_src};
+             h.or_first_byte, h.seed_src, h.owned_mode, h.or_first_src, h.base_src};
     // CTAs take chunks by ticket, so the grid only has to keep the device busy: about 8 CTAs per SM
     // over all images, never more than the chunks an image can have
     uint32_t per_image = (uint32_t)((148 * 8 + n - 1) / n);
@@ -1130,7 +1133,78 @@ __global__ void k_shard_prev_tail(const int* all_tail2, const long long* all_off
     }
     *out = acc;
 }
+// Stuffed size of the bytes this shard owns (what K4 will write), before K4 runs: header (first shard) + owned
+// bytes + one 0x00 per 0xFF + EOI (last shard).  ctr[0] = 0xFF count, ctr[1] = finished CTAs; the last CTA
+// writes the result and resets both, so the counters are zero again for the next encode.
+__global__ void __launch_bounds__(256) k_shard_count_bytes(const uint8_t* __restrict__ scan, const ImgMeta* meta,
+                                                           const unsigned long long* seed_src, int owned_mode,
+                                                           const int* or_first_src, int is_first, int is_last,
+                                                           unsigned long long* ctr, long long* n_bytes) {
+    __shared__ uint32_t s_w[8];
+    const unsigned long long seed = *seed_src & 7ull;
+    const unsigned long long total = meta->error ? 0ull
+                                   : owned_mode == 1 ? (seed + meta->scan_bits) / 8 : (seed + meta->scan_bits + 7) / 8;
+    const unsigned long long units = (total + 15) / 16;
+    uint32_t nff = 0;
+    for (unsigned long long u = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; u < units;
+         u += (unsigned long long)gridDim.x * blockDim.x) {
+        uint4 v = reinterpret_cast<const uint4*>(scan)[u];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        if (u == 0) w[0] |= (uint32_t)(*or_first_src & 0xFF);
+        const long long left = (long long)(total - u * 16);  // valid bytes in this unit (may exceed 16)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const long long vw = left - 4 * i;
+            if (vw < 4) w[i] &= vw <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - (int)vw)));
+            nff += __popc(__vcmpeq4(w[i], 0xFFFFFFFFu)) >> 3;
+        }
+    }
+    nff = __reduce_add_sync(0xFFFFFFFFu, nff);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = nff;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; i++) t += s_w[i];
+        if (t) atomicAdd(&ctr[0], (unsigned long long)t);
+        __threadfence();
+        if (atomicAdd(&ctr[1], 1ull) == gridDim.x - 1) {
+            __threadfence();
+            const unsigned long long ff = atomicExch(&ctr[0], 0ull);
+            ctr[1] = 0ull;
+            *n_bytes = meta->error ? 0ll
+                                   : (long long)((is_first ? meta->header_len : 0u) + total + ff + (is_last ? 2u : 0u));
+        }
+    }
+}
+// the header K2b wrote in front of the shard's own output, copied to the start of the (peer) file
+__global__ void k_shard_copy_header(const uint8_t* own_out, const ImgMeta* meta, uint8_t* file, size_t capacity) {
+    const uint32_t n = meta->error ? 0u : meta->header_len;
+    for (uint32_t i = threadIdx.x; i < n && i < capacity; i += blockDim.x) file[i] = own_out[i];
+}
+// {end offset of this shard's bytes in the file, device-side error}: the value of the closing all-gather,
+// which is also what tells the destination rank that every peer's K4 has finished writing
+__global__ void k_shard_result(const ImgMeta* meta, long long* out2) {
+    out2[0] = (long long)meta->out_len;
+    out2[1] = (long long)meta->error;
+}
 }  // namespace
+
+cudaError_t launch_shard_count_bytes(const uint8_t* scan, const ImgMeta* meta, const unsigned long long* seed_src,
+                                     int owned_mode, const int* or_first_src, int is_first, int is_last,
+                                     unsigned long long* ctr2, long long* n_bytes, cudaStream_t st) {
+    k_shard_count_bytes<<<148 * 2, 256, 0, st>>>(scan, meta, seed_src, owned_mode, or_first_src, is_first, is_last, ctr2,
+                                                 n_bytes);
+    return cudaGetLastError();
+}
+cudaError_t launch_shard_copy_header(const uint8_t* own_out, const ImgMeta* meta, uint8_t* file, size_t capacity,
+                                     cudaStream_t st) {
+    k_shard_copy_header<<<1, 256, 0, st>>>(own_out, meta, file, capacity);
+    return cudaGetLastError();
+}
+cudaError_t launch_shard_result(const ImgMeta* meta, long long* out2, cudaStream_t st) {
+    k_shard_result<<<1, 1, 0, st>>>(meta, out2);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_shard_widen(const int16_t* last_dc3, int* out4, const unsigned int* hist, long long* hist64,
                                const ImgMeta* meta, long long* bits_out, cudaStream_t st) {

@@ -130,6 +130,21 @@ class CudaShardBackend(ShardBackend):
                 "dmmt_shard_launch_stuff")
         return p.value
 
+    def launch_count_bytes(self, d_all_tail2: int, d_all_offs: int, d_all_bits: int, rank: int, world: int, d_n_bytes: int):
+        F.check(F.lib().dmmt_shard_launch_count_bytes(self._h, C.c_void_p(d_all_tail2), C.c_void_p(d_all_offs),
+                                                      C.c_void_p(d_all_bits), rank, world, C.c_void_p(d_n_bytes)),
+                "dmmt_shard_launch_count_bytes")
+
+    def launch_stuff_into(self, d_all_offs: int, rank: int, world: int, d_file: int, capacity: int, d_byte_offset: int,
+                          d_result2: int):
+        F.check(F.lib().dmmt_shard_launch_stuff_into(self._h, C.c_void_p(d_all_offs), rank, world, C.c_void_p(d_file),
+                                                     capacity, C.c_void_p(d_byte_offset), C.c_void_p(d_result2)),
+                "dmmt_shard_launch_stuff_into")
+
+    @property
+    def out_stride(self) -> int:
+        return F.lib().dmmt_shard_out_stride(self._h)
+
     def status(self):
         F.check(F.lib().dmmt_shard_status(self._h), "dmmt_shard_status")
 
@@ -271,3 +286,105 @@ def encode_sharded_device(backend: CudaShardBackend, group=None, dst: int = 0, t
             w.wait()
     mark("gather")
     return None
+
+
+class PeerFile:
+    """The whole output file in the destination rank's HBM, mapped into every other rank's process through
+    CUDA IPC (dmmt_peer_export / dmmt_peer_open), so that K4 of every shard stores its bytes at their final
+    place over NVLink.  Collective: every rank of `group` constructs it once, after its CudaShardBackend."""
+
+    def __init__(self, backend: CudaShardBackend, group=None, dst: int = 0, capacity: int | None = None):
+        self.ctx, self.group, self.dst = backend.ctx, group, dst
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        strides = [None] * self.world
+        dist.all_gather_object(strides, int(backend.out_stride), group=group)
+        self.capacity = int(capacity) if capacity else sum(strides)
+        self._ptr = C.c_void_p()
+        box = [None]
+        if self.rank == dst:
+            F.check(F.lib().dmmt_device_alloc(self.ctx.handle, self.capacity, C.byref(self._ptr)), "dmmt_device_alloc")
+            h = C.create_string_buffer(64)
+            F.check(F.lib().dmmt_peer_export(self.ctx.handle, self._ptr, h), "dmmt_peer_export")
+            box[0] = h.raw
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+        if self.rank != dst:
+            F.check(F.lib().dmmt_peer_open(self.ctx.handle, box[0], C.byref(self._ptr)), "dmmt_peer_open")
+
+    @property
+    def ptr(self) -> int:
+        return self._ptr.value
+
+    def tensor(self, n: int) -> torch.Tensor:
+        """first n bytes of the file as a uint8 tensor on the destination rank's device (no copy)"""
+        if self.rank != self.dst:
+            raise RuntimeError("the file lives on the destination rank")
+        return torch.as_tensor(_DevPtr(self._ptr.value, n), device=f"cuda:{self.ctx.device}")
+
+    def close(self):
+        if self._ptr:
+            if self.rank == self.dst:
+                F.lib().dmmt_device_free(self.ctx.handle, self._ptr)
+            else:
+                F.lib().dmmt_peer_close(self.ctx.handle, self._ptr)
+            self._ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def encode_sharded_peer(backend: CudaShardBackend, file: PeerFile, to_host: bool = True, mark=None):
+    """encode_sharded_device without the gather: after the tail exchange every shard counts its stuffed bytes
+    (phase 5a), the counts are all-gathered and summed, and K4 (phase 5b) writes straight into `file` at the
+    shard's final offset -- on the destination rank's own memory or, from the other ranks, over NVLink.  The
+    closing all-gather of {end offset, error} is the completion barrier and the one host synchronisation.
+    Returns the file on the destination rank (bytes, or a view of `file` when to_host is False), None elsewhere."""
+    group, dst = file.group, file.dst
+    rank, world = file.rank, file.world
+    dev = torch.device("cuda", backend.ctx.device)
+    b = getattr(backend, "_pbuf", None)
+    if b is None or b["world"] != world:
+        i32, i64 = dict(dtype=torch.int32, device=dev), dict(dtype=torch.int64, device=dev)
+        b = backend._pbuf = {"world": world, "last": torch.empty(4, **i32), "all_dc": torch.empty(4 * world, **i32),
+                             "hist": torch.empty(1024, **i64), "bits": torch.empty(1, **i64),
+                             "all_bits": torch.empty(world, **i64), "offs": torch.empty(world, **i64),
+                             "tail": torch.empty(2, **i32), "all_tail": torch.empty(2 * world, **i32),
+                             "n_bytes": torch.empty(1, **i64), "all_n": torch.empty(world, **i64),
+                             "byte_offs": torch.empty(world, **i64), "res": torch.empty(2, **i64),
+                             "all_res": torch.empty(2 * world, **i64)}
+    mark = mark or (lambda name: None)
+    backend.launch_transform(b["last"].data_ptr())
+    dist.all_gather_into_tensor(b["all_dc"], b["last"], group=group)             # exchange 1: last DCs
+    mark("transform")
+    backend.launch_histogram(b["all_dc"].data_ptr() + 16 * (rank - 1) if rank else 0, b["hist"].data_ptr())
+    dist.all_reduce(b["hist"], op=dist.ReduceOp.SUM, group=group)                # exchange 2: global histograms
+    mark("histogram")
+    backend.launch_tables(b["hist"].data_ptr(), b["bits"].data_ptr())
+    dist.all_gather_into_tensor(b["all_bits"], b["bits"], group=group)           # exchange 3: bit counts
+    mark("tables")
+    torch.cumsum(b["all_bits"], 0, out=b["offs"])
+    b["offs"].sub_(b["all_bits"])                                                # exclusive global bit offsets
+    backend.launch_pack(b["offs"].data_ptr() + 8 * rank, rank == world - 1, b["tail"].data_ptr())
+    dist.all_gather_into_tensor(b["all_tail"], b["tail"], group=group)           # trailing partial bytes
+    mark("pack")
+    backend.launch_count_bytes(b["all_tail"].data_ptr(), b["offs"].data_ptr(), b["all_bits"].data_ptr(), rank, world,
+                               b["n_bytes"].data_ptr())
+    dist.all_gather_into_tensor(b["all_n"], b["n_bytes"], group=group)           # exchange 4: byte counts, BEFORE K4
+    torch.cumsum(b["all_n"], 0, out=b["byte_offs"])
+    b["byte_offs"].sub_(b["all_n"])                                              # exclusive byte offsets in the file
+    mark("count")
+    backend.launch_stuff_into(b["offs"].data_ptr(), rank, world, file.ptr, file.capacity,
+                              b["byte_offs"].data_ptr() + 8 * rank, b["res"].data_ptr())
+    dist.all_gather_into_tensor(b["all_res"], b["res"], group=group)             # completion barrier + status
+    mark("stuff")
+    res = b["all_res"].tolist()                                                  # the only host synchronisation
+    mark("sync")
+    errs = [int(e) for e in res[1::2] if e]
+    if errs:
+        F.check(errs[0], "sharded encode (peer gather)")
+    if rank != dst:
+        return None
+    out = file.tensor(int(res[2 * (world - 1)]))
+    return out.cpu().numpy().tobytes() if to_host else out

@@ -241,6 +241,27 @@ int dmmt_shard_launch_stuff(dmmt_shard *, const int32_t *d_all_tail2, const int6
                             const int64_t *d_all_bits, int rank, int world, const uint8_t **d_bytes, int64_t *d_n_bytes);
 int dmmt_shard_status(dmmt_shard *);              /* synchronises; device-side error of the phases so far or 0 */
 
+/* Peer-memory gather (one process per GPU on one NVLink / NVSwitch node): instead of dmmt_shard_launch_stuff +
+ * a send / recv of the shard outputs, the destination rank allocates the whole file once
+ * (dmmt_device_alloc, plain device memory) and exports it (dmmt_peer_export -> 64 opaque bytes the caller
+ * hands to the other processes); they map it (dmmt_peer_open) and K4 of every shard stores its bytes at their
+ * final place in that file over NVLink.  Phase 5 splits in two around one more tiny exchange:
+ *   5a dmmt_shard_launch_count_bytes: stuffed size of this shard (header on rank 0, EOI on the last) ->
+ *      all-gather + exclusive sum = byte offset of every shard in the file;
+ *   5b dmmt_shard_launch_stuff_into:  K4 into d_file + *d_byte_offset; d_result2 = {end offset, error}, whose
+ *      all-gather is both the completion barrier for the destination rank and the status of the encode. */
+#define DMMT_PEER_HANDLE_BYTES 64
+size_t dmmt_shard_out_stride(const dmmt_shard *); /* most bytes this shard can write: sum over shards = a safe file size */
+int dmmt_device_alloc(dmmt_ctx *, size_t bytes, void **d_ptr);
+int dmmt_device_free(dmmt_ctx *, void *d_ptr);
+int dmmt_peer_export(dmmt_ctx *, void *d_ptr, uint8_t handle[DMMT_PEER_HANDLE_BYTES]);
+int dmmt_peer_open(dmmt_ctx *, const uint8_t handle[DMMT_PEER_HANDLE_BYTES], void **d_ptr);
+int dmmt_peer_close(dmmt_ctx *, void *d_ptr);
+int dmmt_shard_launch_count_bytes(dmmt_shard *, const int32_t *d_all_tail2, const int64_t *d_all_bit_offsets,
+                                  const int64_t *d_all_bits, int rank, int world, int64_t *d_n_bytes);
+int dmmt_shard_launch_stuff_into(dmmt_shard *, const int64_t *d_all_bit_offsets, int rank, int world, uint8_t *d_file,
+                                 size_t file_capacity, const int64_t *d_byte_offset, int64_t *d_result2);
+
 #ifdef __cplusplus
 }
 #endif

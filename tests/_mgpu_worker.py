@@ -35,10 +35,14 @@ def main():
         assert be.pixel_bytes == d_px.numel(), (be.pixel_bytes, d_px.numel())
         out = S.encode_sharded(be, dev)
         out_dev = S.encode_sharded_device(be)                          # device-resident exchange: same bytes
+        pf = S.PeerFile(be)                                            # K4 of every rank writes into rank 0's file
+        out_peer = S.encode_sharded_peer(be, pf)
+        out_peer2 = S.encode_sharded_peer(be, pf)                      # buffers and counters are reusable
+        pf.close()
         if rank == 0:
             full = synth.make("smooth", 7, h, w, "cpu").numpy()
             whole = ctx.encode(full, 255, opts)
-            ok = out == whole and out_dev == whole
+            ok = out == whole and out_dev == whole and out_peer == whole and out_peer2 == whole
             if use_oracle:
                 from oracle import oracle as O
 

@@ -404,6 +404,94 @@ def test_shards_with_tiny_bit_counts(D, ctx, O):
             assert ctx.encode_sharded(px, n, 255, D.Options(preset, 8, 0)) == want, (preset, n)
 
 
+def _encode_shards_device_exchange(D, px, n_shards, opts, peer):
+    """All shards on ONE GPU, the launch_* phases of every shard with the collectives replaced by torch ops
+    on the same stream: what sharded.encode_sharded_device / encode_sharded_peer do over NCCL."""
+    import torch
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+    from dmmt_jpeg_encoder_b200 import sharded as S
+
+    h, w = px.shape[:2]
+    dev = torch.device("cuda", 0)
+    ctx = D.Context(0, torch.cuda.current_stream().cuda_stream)
+    rows = S.mcu_rows_total(h, opts)
+    world = min(n_shards, rows)
+    bes, keep = [], []
+    for r in range(world):
+        b, e = S.shard_rows(rows, world, r)
+        y0, y1 = S.pixel_row_range(h, opts, b, e)
+        d = torch.from_numpy(np.ascontiguousarray(px[y0:y1])).to(dev)
+        keep.append(d)
+        bes.append(S.CudaShardBackend(ctx, d.data_ptr(), w, h, F.FMT_U8, 255, opts, b, e))
+    i32, i64 = dict(dtype=torch.int32, device=dev), dict(dtype=torch.int64, device=dev)
+    all_dc, hists = torch.zeros(4 * world, **i32), torch.zeros(world, 1024, **i64)
+    for r, be in enumerate(bes):
+        be.launch_transform(all_dc.data_ptr() + 16 * r)
+    for r, be in enumerate(bes):
+        be.launch_histogram(all_dc.data_ptr() + 16 * (r - 1) if r else 0, hists[r].data_ptr())
+    hist = hists.sum(0)
+    all_bits = torch.zeros(world, **i64)
+    for r, be in enumerate(bes):
+        be.launch_tables(hist.data_ptr(), all_bits.data_ptr() + 8 * r)
+    offs = torch.cumsum(all_bits, 0) - all_bits
+    all_tail = torch.zeros(2 * world, **i32)
+    for r, be in enumerate(bes):
+        be.launch_pack(offs.data_ptr() + 8 * r, r == world - 1, all_tail.data_ptr() + 8 * r)
+    all_n = torch.zeros(world, **i64)
+    if peer:
+        cap = sum(be.out_stride for be in bes)
+        file = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        for r, be in enumerate(bes):
+            be.launch_count_bytes(all_tail.data_ptr(), offs.data_ptr(), all_bits.data_ptr(), r, world, all_n.data_ptr() + 8 * r)
+        byte_offs = torch.cumsum(all_n, 0) - all_n
+        res = torch.zeros(2 * world, **i64)
+        for r, be in enumerate(bes):
+            be.launch_stuff_into(offs.data_ptr(), r, world, file.data_ptr(), cap, byte_offs.data_ptr() + 8 * r,
+                                 res.data_ptr() + 16 * r)
+        res = res.tolist()
+        assert not any(res[1::2]), res
+        assert res[0::2] == (byte_offs + all_n).tolist()            # counted sizes == written sizes
+        out = file[:res[-2]].cpu().numpy().tobytes()
+    else:
+        ptrs = [be.launch_stuff(all_tail.data_ptr(), offs.data_ptr(), all_bits.data_ptr(), r, world, all_n.data_ptr() + 8 * r)
+                for r, be in enumerate(bes)]
+        sizes = all_n.tolist()
+        for be in bes:
+            be.status()
+        out = b"".join(torch.as_tensor(S._DevPtr(p, n), device=dev).cpu().numpy().tobytes() for p, n in zip(ptrs, sizes) if n)
+    for be in bes:
+        be.close()
+    ctx.close()
+    return out
+
+
+@pytest.mark.parametrize("peer", [False, True], ids=["gather", "peer-file"])
+@pytest.mark.parametrize("pname", list(PRESETS))
+def test_shards_device_resident_exchange(D, O, pname, peer):
+    """The asynchronous phases with every exchanged value in device memory (and, for `peer-file`, K4 writing
+    straight into the final file at the pre-counted byte offsets) give the unsharded file byte for byte."""
+    px = synth_image("photo", 210, 333, 43)
+    want = O.encode(px, 255, PRESETS[pname]).jpeg
+    for n in (1, 2, 5):
+        assert _encode_shards_device_exchange(D, px, n, D.Options(PRESETS[pname], 8, 0), peer) == want, n
+
+
+def test_shards_peer_file_tiny_bit_counts_and_ff_runs(D, O):
+    """peer-file path on the nasty cases: shards that do not complete a byte, and scans full of 0xFF bytes
+    (the count of phase 5a must equal what K4 writes, including a first byte that becomes 0xFF through the
+    predecessor's tail bits)."""
+    for preset in (0, 2):
+        px = np.full((72, 8, 3), 77, np.uint8)
+        want = O.encode(px, 255, preset).jpeg
+        for n in (2, 4, 9):
+            assert _encode_shards_device_exchange(D, px, n, D.Options(preset, 8, 0), True) == want, (preset, n)
+    px = synth_image("uniform", 160, 480, 5)
+    want = O.encode(px, 255, O.P420).jpeg
+    assert want.count(b"\xff\x00") > 10
+    for n in (3, 7, 30):
+        assert _encode_shards_device_exchange(D, px, n, D.Options(), True) == want, n
+
+
 # ------------------------------------------------------------------------------- full sizes
 def test_4k_frame_matches_oracle_and_decodes(D, ctx, O):
     """BASELINE config 3 geometry (3840x2160)."""

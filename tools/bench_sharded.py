@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--phases", action="store_true", help="also report per-phase device and enqueue times (device exchange only)")
+    ap.add_argument("--peer", action="store_true", help="no gather: K4 of every rank writes into rank 0's file over NVLink (CUDA IPC)")
     ap.add_argument("--host-exchange", action="store_true", help="exchange through host values (dmmt_shard_* phases)")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -48,6 +49,7 @@ def main():
     torch.cuda.synchronize()
     ctx = D.Context(local, torch.cuda.current_stream().cuda_stream)
     be = S.CudaShardBackend(ctx, d_px.data_ptr(), n, n, F.FMT_U8, 255, opts, b, e)
+    pf = S.PeerFile(be) if a.peer else None
     out = None
     times = []
     phase_dev, phase_cpu = {}, {}
@@ -64,8 +66,12 @@ def main():
             marks.append((name, ev, time.perf_counter()))
         if a.phases and not a.host_exchange:
             mark("start")
-        out = (S.encode_sharded(be, dev, to_host=False) if a.host_exchange
-               else S.encode_sharded_device(be, to_host=False, mark=mark if a.phases else None))
+        if a.host_exchange:
+            out = S.encode_sharded(be, dev, to_host=False)
+        elif a.peer:
+            out = S.encode_sharded_peer(be, pf, to_host=False, mark=mark if a.phases else None)
+        else:
+            out = S.encode_sharded_device(be, to_host=False, mark=mark if a.phases else None)
         torch.cuda.synchronize()
         if marks and it >= a.warmup:
             for (_, e0, c0), (name, e1, c1) in zip(marks, marks[1:]):
@@ -83,7 +89,7 @@ def main():
         ms = sum(times) / len(times) * 1e3
         line = {"metric": "encoded MPixel/s", "config": {"workload": f"one synthetic {n}x{n} RGB u8 image ('smooth'), 4:2:0, "
                                                                      f"MCU-row shards over {world} GPU(s), NCCL exchanges, file gathered in rank 0's HBM"},
-                "exchange": "host values" if a.host_exchange else "device-resident (one host sync)", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "value": n * n / ms / 1e3,
+                "exchange": "host values" if a.host_exchange else ("device-resident, K4 writes into rank 0's file over NVLink (no gather)" if a.peer else "device-resident (one host sync)"), "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "value": n * n / ms / 1e3,
                 "unit": "MPixel/s", "file_bytes": out.numel(), "bytes_per_pixel": out.numel() / (n * n),
                 "timing": "wall clock between barriers, device synchronised, max over ranks"}
         if a.phases and not a.host_exchange:
@@ -91,6 +97,8 @@ def main():
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+    if pf is not None:
+        pf.close()
     be.close()
     ctx.close()
     dist.destroy_process_group()
