@@ -105,6 +105,43 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long l
     return excl;
 }
 
+// The same, called by ALL 32 lanes of one warp: the lanes inspect 32 predecessors at once, so the walk costs one
+// memory round trip per 32 chunks instead of one per chunk (the chunks of an image are packed by CTAs that
+// run in lock step, so the nearest inclusive prefix is usually many chunks back).  Returns the exclusive
+// prefix in every lane.
+__device__ __forceinline__ unsigned long long lookback_exclusive_warp(unsigned long long* state, int chunk,
+                                                                      unsigned long long aggregate) {
+    const int lane = threadIdx.x & 31;
+    if (chunk == 0) {
+        if (lane == 0) st_relaxed_u64(&state[0], LB_INC | aggregate);
+        return 0ull;
+    }
+    if (lane == 0) st_relaxed_u64(&state[chunk], LB_AGG | aggregate);
+    unsigned long long excl = 0ull;
+    int base = chunk - 1;
+    while (true) {
+        const int j = base - lane;
+        const unsigned long long s = j >= 0 ? ld_relaxed_u64(&state[j]) : LB_INC;  // before chunk 0: inclusive 0
+        const unsigned long long flag = s & ~LB_VAL;
+        const unsigned int inc_mask = __ballot_sync(0xffffffffu, flag == LB_INC);
+        const unsigned int wait_mask = __ballot_sync(0xffffffffu, flag == 0ull);
+        const int f = inc_mask ? __ffs(inc_mask) - 1 : 32;                // nearest inclusive prefix in this window
+        const unsigned int needed = f >= 31 ? 0xffffffffu : ((2u << f) - 1u);  // lanes 0..f (all when there is none)
+        if (wait_mask & needed) {
+            __nanosleep(20);
+            continue;
+        }
+        unsigned long long v = lane <= f ? (s & LB_VAL) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        excl += v;
+        if (inc_mask) break;
+        base -= 32;
+    }
+    if (lane == 0) st_relaxed_u64(&state[chunk], LB_INC | (excl + aggregate));
+    return excl;
+}
+
 // ------------------------------------------------------------------------------------------
 // Block-wide exclusive scan of one u32 per thread (blockDim.x == NT, multiple of 32, <= 1024).
 // Returns the exclusive prefix; *total receives the block sum.  `warp_sums` = NT/32 + 1 u32 of smem.

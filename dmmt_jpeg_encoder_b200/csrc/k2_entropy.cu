@@ -470,6 +470,7 @@ struct K3Args {
     unsigned long long seed_bits;  // bit offset of this shard's first bit inside its first byte/word (< 32)
     int pad_ones;                  // append the 1-padding after the last block (binary_stream.rs:89-96)
     const unsigned long long* seed_src;  // optional: global bit offset of the shard in device memory (its low 3 bits are the seed)
+    uint32_t n_items;              // n * n_chunks work items (see k3_pack)
 };
 
 // code bits of one token: ZRL codes + symbol code + category bits (encoder.rs:356-404)
@@ -539,21 +540,6 @@ struct LaneSink {
             fill -= 32;
         }
     }
-    // same, without a branch: the OR is a predicated shared-memory reduction (1 <= len <= 31)
-    __device__ __forceinline__ void put_nobranch(uint32_t code, int len) {
-        static_assert(Shared, "shared-memory sink only");
-        acc |= (unsigned long long)code << (64 - fill - len);
-        fill += len;
-        const uint32_t hi = (uint32_t)(acc >> 32);
-        const uint32_t full = fill >= 32 ? 1u : 0u;
-        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(w);
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.or.b32 [%0], %1;\n\t}" ::"r"(addr), "r"(hi),
-                     "r"(full ? hi : 0u)
-                     : "memory");
-        w += full;
-        acc = full ? acc << 32 : acc;
-        fill -= 32 * (int)full;
-    }
     __device__ __forceinline__ void flush() {
         if (fill > 0) {
             const uint32_t v = (uint32_t)(acc >> 32);
@@ -562,9 +548,70 @@ struct LaneSink {
     }
 };
 
+// LUT entry per (table, symbol): {code << cat, len + cat}; a symbol without a code has bit 31 of .x set (and .y = 0),
+// except the pad token's entry, which is {0, 0}
+constexpr uint32_t K3_PAD_TOKEN = T_YDC * 256u + 255u;  // DC symbols are categories (<= 15): never a real token
+
+// one warp step of the general path: t[] = the lane's run (n valid tokens); returns the bits of the step
+template <bool Shared>
+__device__ __forceinline__ uint32_t emit_step(const uint32_t (&t)[K3_RUN], int n, const uint2* s_enc2, uint32_t zl_y,
+                                              uint32_t zl_c, uint32_t* words, unsigned long long bitpos,
+                                              unsigned long long cap_bits, bool& sym_ok, bool& overflow) {
+    const int lane = threadIdx.x & 31;
+    uint32_t val[K3_RUN], ln[K3_RUN];
+    // code word + category bits of every token (encoder.rs:356-404); ZRLs are added below (rare)
+    uint32_t nb = 0, nzf = 0, flags = 0;
+#pragma unroll
+    for (int i = 0; i < K3_RUN; i++) {
+        const uint2 e = s_enc2[t[i] & 0x3FFu];
+        ln[i] = i < n ? e.y : 0u;
+        val[i] = (e.x & 0x7FFFFFFFu) | (t[i] >> 16);
+        if (i < n) flags |= e.x, nzf |= t[i];
+        nb += ln[i];
+    }
+    if (flags >> 31) sym_ok = false;  // Error::HuffmanSymbolNotPresentInTranslator
+    nzf &= 0xC00u;
+    if (nzf) {
+#pragma unroll
+        for (int i = 0; i < K3_RUN; i++)
+            if (i < n) nb += ((t[i] >> 10) & 3u) * ((t[i] & 0x200u) ? zl_c : zl_y);
+    }
+    uint32_t inc = nb;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += u;
+    }
+    const uint32_t step_bits = __shfl_sync(0xffffffffu, inc, 31);
+    if (bitpos + step_bits > cap_bits) overflow = true;  // warp-uniform
+    if (nb && !overflow) {
+        LaneSink<Shared> sink;
+        sink.init(words, bitpos + (inc - nb));
+        if (!nzf) {
+#pragma unroll
+            for (int i = 0; i < K3_RUN; i++)
+                if (ln[i]) sink.put(val[i], (int)ln[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < K3_RUN; i++) {
+                if (ln[i]) {
+                    uint32_t nz = (t[i] >> 10) & 3u;
+                    if (nz) {  // ZRL codes first (categorize.rs:139-142); symbol 0xF0 has category 0
+                        const uint2 z = s_enc2[(t[i] & 0x300u) | 0xF0u];
+                        for (; nz; --nz) sink.put(z.x & 0xFFFFu, (int)z.y);
+                    }
+                    sink.put(val[i], (int)ln[i]);
+                }
+            }
+        }
+        sink.flush();
+    }
+    return step_bits;
+}
+
 template <bool Shared>
 __device__ __forceinline__ unsigned long long emit_range(const uint32_t* __restrict__ tok, uint32_t begin,
-                                                         uint32_t end, const uint32_t* s_enc, uint32_t zl_y,
+                                                         uint32_t end, const uint2* s_enc2, uint32_t zl_y,
                                                          uint32_t zl_c, uint32_t* words, unsigned long long bitpos,
                                                          unsigned long long cap_bits, bool& sym_ok, bool& overflow) {
     const int lane = threadIdx.x & 31;
@@ -572,95 +619,141 @@ __device__ __forceinline__ unsigned long long emit_range(const uint32_t* __restr
     for (uint32_t wbase = begin; wbase < end; wbase += K3_STEP) {
         const uint32_t base = wbase + lane * K3_RUN;
         const int n = base < end ? (int)min((uint32_t)K3_RUN, end - base) : 0;  // valid tokens of this lane's run
-        uint32_t t[K3_RUN], val[K3_RUN], ln[K3_RUN];
+        uint32_t t[K3_RUN];
         load_run(tok, base, end, t);
-        // code word + category bits of every token (encoder.rs:356-404); ZRLs are added below (rare)
-        uint32_t nb = 0, nzf = 0, lo = 0xFFFFFFFFu;
-#pragma unroll
-        for (int i = 0; i < K3_RUN; i++) {
-            const uint32_t e = s_enc[t[i] & 0x3FFu];
-            const uint32_t cat = t[i] & 15u;
-            ln[i] = i < n ? (e >> 16) + cat : 0u;
-            val[i] = ((e & 0xFFFFu) << cat) | (t[i] >> 16);
-            if (i < n) lo = min(lo, e), nzf |= t[i];
-            nb += ln[i];
-        }
-        if ((lo >> 16) == 0u) sym_ok = false;  // Error::HuffmanSymbolNotPresentInTranslator
-        nzf &= 0xC00u;
-        if (nzf) {
-#pragma unroll
-            for (int i = 0; i < K3_RUN; i++)
-                if (i < n) nb += ((t[i] >> 10) & 3u) * ((t[i] & 0x200u) ? zl_c : zl_y);
-        }
-        uint32_t inc = nb;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += u;
-        }
-        const uint32_t step_bits = __shfl_sync(0xffffffffu, inc, 31);
-        if (bitpos + step_bits > cap_bits) overflow = true;  // warp-uniform
-        if (nb && !overflow) {
-            LaneSink<Shared> sink;
-            sink.init(words, bitpos + (inc - nb));
-            if (Shared && !nzf && n == K3_RUN) {
-                // common case (full run, no ZRL): eight branch-free appends
-                if constexpr (Shared) {
-#pragma unroll
-                    for (int i = 0; i < K3_RUN; i++) sink.put_nobranch(val[i], (int)ln[i]);
-                }
-            } else if (!nzf) {
-#pragma unroll
-                for (int i = 0; i < K3_RUN; i++)
-                    if (ln[i]) sink.put(val[i], (int)ln[i]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < K3_RUN; i++) {
-                    if (ln[i]) {
-                        uint32_t nz = (t[i] >> 10) & 3u;
-                        if (nz) {  // ZRL codes first (categorize.rs:139-142)
-                            const uint32_t z = s_enc[(t[i] & 0x300u) | 0xF0u];
-                            for (; nz; --nz) sink.put(z & 0xFFFFu, (int)(z >> 16));
-                        }
-                        sink.put(val[i], (int)ln[i]);
-                    }
-                }
-            }
-            sink.flush();
-        }
-        bitpos += step_bits;
+        bitpos += emit_step<Shared>(t, n, s_enc2, zl_y, zl_c, words, bitpos, cap_bits, sym_ok, overflow);
     }
     return bitpos - start;
 }
 
+// K3's first pass (private shared-memory buffer).  The common step -- no ZRL prefix in the warp's 256 tokens and
+// every PAIR of neighbouring tokens at most 32 bits long -- needs no per-token bookkeeping at all: s_enc2 holds
+// {code << cat, len + cat} per (table, symbol), so a token is one 64-bit LUT read and one OR; a lane merges its
+// 8 tokens into 4 pairs (32-bit) and 2 quads (64-bit) with plain shifts and ORs each quad into the bit buffer
+// as up to three words.  Tokens beyond the range read as K3_PAD_TOKEN, whose LUT entry is {0, 0}; a symbol
+// without a code has bit 31 set in its entry (the output of such an image is discarded, encoder.rs:381-386).
+// Any other step (ZRLs, very long codes) goes through emit_step.
+// tokens [base, base + 8) into registers; tokens at or beyond `end` read as the pad token
+__device__ __forceinline__ void load_run_padded(const uint32_t* __restrict__ tok, uint32_t base, uint32_t end,
+                                                uint32_t (&t)[K3_RUN]) {
+    if (base + K3_RUN <= end) {
+        const uint4* p = reinterpret_cast<const uint4*>(tok + base);  // chunk bases and `base` are multiples of 8
+        const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
+        t[0] = v0.x, t[1] = v0.y, t[2] = v0.z, t[3] = v0.w, t[4] = v1.x, t[5] = v1.y, t[6] = v1.z, t[7] = v1.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < K3_RUN; i++) t[i] = (base + i < end) ? __ldg(tok + base + i) : K3_PAD_TOKEN;
+    }
+}
+__device__ __forceinline__ void or_quad(uint32_t* words, unsigned long long pos, unsigned long long v, uint32_t len) {
+    const unsigned long long left = v << ((64u - len) & 63u);  // len = 0 comes with v = 0
+    const uint32_t hi = (uint32_t)(left >> 32), lo = (uint32_t)left;
+    const uint32_t s = (uint32_t)pos & 31u;
+    uint32_t* w = words + (pos >> 5);
+    const uint32_t w0 = hi >> s, w1 = __funnelshift_r(lo, hi, s), w2 = __funnelshift_r(0u, lo, s);
+    if (w0) atomicOr(w, w0);
+    if (w1) atomicOr(w + 1, w1);
+    if (w2) atomicOr(w + 2, w2);
+}
+__device__ __forceinline__ unsigned long long emit_range_fast(const uint32_t* __restrict__ tok, uint32_t begin,
+                                                              uint32_t end, const uint2* s_enc2, uint32_t zl_y, uint32_t zl_c, uint32_t* words,
+                                                              unsigned long long cap_bits, bool& sym_ok, bool& overflow) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long bitpos = 0ull;
+    // the tokens of step k + 1 are requested before step k is processed (the chain of bit positions makes the
+    // steps sequential, so the load latency would otherwise be exposed once per step)
+    uint32_t tn[K3_RUN];
+    load_run_padded(tok, begin + lane * K3_RUN, end, tn);
+    for (uint32_t wbase = begin; wbase < end; wbase += K3_STEP) {
+        const uint32_t base = wbase + lane * K3_RUN;
+        uint32_t t[K3_RUN];
+#pragma unroll
+        for (int i = 0; i < K3_RUN; i++) t[i] = tn[i];
+        if (wbase + K3_STEP < end) load_run_padded(tok, base + K3_STEP, end, tn);
+        uint32_t val[K3_RUN], ln[K3_RUN], flags = 0, tor = 0;
+#pragma unroll
+        for (int i = 0; i < K3_RUN; i++) {
+            const uint2 e = s_enc2[t[i] & 0x3FFu];
+            val[i] = e.x | (t[i] >> 16);
+            ln[i] = e.y;
+            flags |= e.x;
+            tor |= t[i];
+        }
+        const uint32_t l01 = ln[0] + ln[1], l23 = ln[2] + ln[3], l45 = ln[4] + ln[5], l67 = ln[6] + ln[7];
+        const uint32_t q0 = l01 + l23, q1 = l45 + l67, nb = q0 + q1;
+        const bool simple = (tor & 0xC00u) == 0u && max(max(l01, l23), max(l45, l67)) <= 32u;
+        if (__all_sync(0xffffffffu, simple)) {
+            if (flags >> 31) sym_ok = false;  // Error::HuffmanSymbolNotPresentInTranslator
+            uint32_t inc = nb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += u;
+            }
+            const uint32_t step_bits = __shfl_sync(0xffffffffu, inc, 31);
+            if (bitpos + step_bits > cap_bits) overflow = true;  // warp-uniform
+            if (!overflow) {
+                const uint32_t p01 = (val[0] << ln[1]) | val[1], p23 = (val[2] << ln[3]) | val[3];
+                const uint32_t p45 = (val[4] << ln[5]) | val[5], p67 = (val[6] << ln[7]) | val[7];
+                const unsigned long long v0 = ((unsigned long long)p01 << l23) | p23;
+                const unsigned long long v1 = ((unsigned long long)p45 << l67) | p67;
+                const unsigned long long at = bitpos + (inc - nb);
+                or_quad(words, at, v0, q0);
+                or_quad(words, at + q0, v1, q1);
+            }
+            bitpos += step_bits;
+        } else {
+            const int n = base < end ? (int)min((uint32_t)K3_RUN, end - base) : 0;
+            bitpos += emit_step<true>(t, n, s_enc2, zl_y, zl_c, words, bitpos, cap_bits, sym_ok, overflow);
+        }
+    }
+    return bitpos;
+}
+
 constexpr int K3_WBUF_WORDS = 640;  // per-warp private bit buffer: 20480 bits (2.5 KB), 20 KB per CTA
 
-__global__ void __launch_bounds__(EB) k3_pack(const K3Args a) {
+__global__ void __launch_bounds__(EB, 4) k3_pack(const K3Args a) {
     __shared__ __align__(16) uint32_t s_wbuf[EB / 32][K3_WBUF_WORDS];
-    __shared__ uint32_t s_enc[4 * 256];
+    __shared__ __align__(8) uint2 s_enc2[4 * 256];
     __shared__ unsigned long long s_wsum[EB / 32];
     __shared__ unsigned long long s_prefix;
-    __shared__ unsigned int s_chunk;
-    __shared__ int s_err, s_ovf;
+    __shared__ unsigned int s_item;
+    __shared__ int s_err;
+    __shared__ unsigned int s_ovf_tag;  // = 1 + item in which some warp's range did not fit its buffer
 
-    const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    // Images flagged by K1/K2/K2b (range / capacity) are skipped; the flag is read once per CTA
-    // (K3 itself may set it concurrently, so it must not be re-read later).
-    if (tid == 0) s_err = *reinterpret_cast<volatile int32_t*>(&a.meta[img].error);
-    for (int i = tid; i < 1024; i += EB) s_enc[i] = a.enc[img].e[i >> 8][i & 255];
-    __syncthreads();
-    if (s_err != 0 && s_err != DMMT_E_SYMBOL) return;
-    const uint32_t zl_y = s_enc[T_YAC * 256 + 0xF0] >> 16, zl_c = s_enc[T_CAC * 256 + 0xF0] >> 16;
-    uint32_t* gscan = a.scan + (size_t)img * a.scan_img_stride_words;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint32_t* wbuf = s_wbuf[wid];
+    int cur_img = -1;
+    uint32_t zl_y = 0, zl_c = 0;
+    if (tid == 0) s_ovf_tag = 0u;
 
+    // Work items = the chunks of ALL images, image-major, taken by one ticket in START order (so a waiting
+    // chunk's predecessors are always running or done) by a grid sized to what the device holds at once:
+    // no second, partly empty wave however the image count divides the device.
     while (true) {
-        // chunks are taken in START order, so a waiting chunk's predecessors are always running or done
+        __syncthreads();  // everybody is done with s_item, s_enc2 and (overflow pass) the previous chunk
+        if (tid == 0) s_item = atomicAdd(a.ticket, 1u);
         __syncthreads();
-        if (tid == 0) s_chunk = atomicAdd(&a.ticket[img], 1u), s_ovf = 0;
-        __syncthreads();
-        const uint32_t chunk = s_chunk;
-        if (chunk >= a.n_chunks) return;
+        const uint32_t item = s_item;
+        if (item >= a.n_items) return;
+        const int img = (int)(item / a.n_chunks);
+        const uint32_t chunk = item % a.n_chunks;
+        if (img != cur_img) {  // CTA-uniform: (re)build the encoder LUT of this image
+            cur_img = img;
+            // images flagged by K1/K2/K2b (range / capacity) are skipped; K3 itself only ever adds DMMT_E_SYMBOL
+            if (tid == 0) s_err = *reinterpret_cast<volatile int32_t*>(&a.meta[img].error);
+            for (int i = tid; i < 1024; i += EB) {
+                const uint32_t e = a.enc[img].e[i >> 8][i & 255];
+                const uint32_t len = e >> 16, cat = (uint32_t)i & 15u;
+                s_enc2[i] = len ? make_uint2((e & 0xFFFFu) << cat, len + cat)
+                                : make_uint2((uint32_t)i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
+            }
+            __syncthreads();
+            zl_y = s_enc2[T_YAC * 256 + 0xF0].y, zl_c = s_enc2[T_CAC * 256 + 0xF0].y;
+        }
+        if (s_err != 0 && s_err != DMMT_E_SYMBOL) continue;
+        uint32_t* gscan = a.scan + (size_t)img * a.scan_img_stride_words;
+
         // token range of this warp: generic mode = a slice (multiple of 256 tokens, so the 128-bit loads
         // stay aligned) of the chunk's region; tile mode (fused K1) = the whole region of tile 8 * chunk + warp
         const uint32_t* __restrict__ tok;
@@ -684,12 +777,12 @@ __global__ void __launch_bounds__(EB) k3_pack(const K3Args a) {
             reinterpret_cast<uint4*>(wbuf)[i * 32 + lane] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         bool sym_ok = true, ovf = false;
-        const unsigned long long wbits =
-            emit_range<true>(tok, begin, end, s_enc, zl_y, zl_c, wbuf, 0ull, (unsigned long long)K3_WBUF_WORDS * 32 - 64, sym_ok, ovf);
+        const unsigned long long wbits = emit_range_fast(tok, begin, end, s_enc2, zl_y, zl_c, wbuf,
+                                                         (unsigned long long)K3_WBUF_WORDS * 32 - 64, sym_ok, ovf);
         if (!sym_ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_SYMBOL);
         if (lane == 0) {
             s_wsum[wid] = wbits;
-            if (ovf) s_ovf = 1;
+            if (ovf) s_ovf_tag = item + 1u;
         }
         __syncthreads();
         unsigned long long wbase = 0, chunk_bits = 0;
@@ -699,11 +792,14 @@ __global__ void __launch_bounds__(EB) k3_pack(const K3Args a) {
             if (w < wid) wbase += v;
             chunk_bits += v;
         }
-        if (tid == 0) s_prefix = lookback_exclusive(a.lb_state + (size_t)img * a.n_chunks, (int)chunk, chunk_bits);
+        if (wid == 0) {
+            const unsigned long long ex = lookback_exclusive_warp(a.lb_state + (size_t)img * a.n_chunks, (int)chunk, chunk_bits);
+            if (lane == 0) s_prefix = ex;
+        }
         __syncthreads();
         const unsigned long long g0 = (a.seed_src ? (*a.seed_src & 7ull) : a.seed_bits) + s_prefix;  // global bit position of the chunk
         const unsigned long long p0 = g0 + wbase;                    // ... and of this warp's range
-        if (!s_ovf) {
+        if (s_ovf_tag != item + 1u) {
             // shifted copy of the private buffer to its place: destination word k holds relative bits
             // [32k - s, 32k - s + 32); the first and last word are shared with the neighbours
             const uint32_t sft = (uint32_t)(p0 & 31);
@@ -722,7 +818,7 @@ __global__ void __launch_bounds__(EB) k3_pack(const K3Args a) {
         } else {
             // a range too dense for the private buffer (rare): second pass straight into the zeroed stream
             bool d0 = true, d1 = false;
-            (void)emit_range<false>(tok, begin, end, s_enc, zl_y, zl_c, gscan, p0, ~0ull, d0, d1);
+            (void)emit_range<false>(tok, begin, end, s_enc2, zl_y, zl_c, gscan, p0, ~0ull, d0, d1);
         }
         if (chunk == a.n_chunks - 1 && a.pad_ones && tid == 0) {
             const uint32_t pad = (uint32_t)((8 - ((g0 + chunk_bits) & 7)) & 7);  // binary_stream.rs:89-96
@@ -1079,12 +1175,21 @@ uint32_t k4_max_chunks(size_t scan_cap_bytes) { return (uint32_t)((scan_cap_byte
 cudaError_t launch_k3(uint32_t n_chunks, uint32_t n_segs, int n, const TokBuf& tb, const EncTables* enc, ImgMeta* meta,
                       unsigned long long* lb_state, unsigned int* ticket, uint32_t* scan, size_t scan_stride_words,
                       unsigned long long seed_bits, int pad_ones, cudaStream_t st, const unsigned long long* seed_src) {
-    K3Args a{n_chunks, n_segs, tb, enc, meta, lb_state, ticket, scan, scan_stride_words, seed_bits, pad_ones, seed_src};
-    // CTAs take chunks by ticket and keep their encoder LUT in shared memory: about 6 CTAs per SM
-    uint32_t per_image = (uint32_t)((148 * 6 + n - 1) / n);
-    if (per_image < 4) per_image = 4;
-    if (per_image > a.n_chunks) per_image = a.n_chunks;
-    k3_pack<<<dim3(per_image, n), EB, 0, st>>>(a);
+    K3Args a{n_chunks, n_segs, tb, enc, meta, lb_state, ticket, scan, scan_stride_words, seed_bits, pad_ones, seed_src,
+             n_chunks * (uint32_t)n};
+    // persistent CTAs, exactly as many as the device holds at once (a larger grid would run a second,
+    // partly empty wave)
+    static int resident = 0;
+    if (!resident) {
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_pack, EB, 0);
+        if (e == cudaSuccess) e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        resident = per_sm * sms > 0 ? per_sm * sms : 148;
+    }
+    const uint32_t grid = a.n_items < (uint32_t)resident ? a.n_items : (uint32_t)resident;
+    k3_pack<<<grid ? grid : 1u, EB, 0, st>>>(a);
     return cudaGetLastError();
 }
 
