@@ -105,18 +105,19 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long l
     return excl;
 }
 
-// The same, called by ALL 32 lanes of one warp: the lanes inspect 32 predecessors at once, so the walk costs one
-// memory round trip per 32 chunks instead of one per chunk (the chunks of an image are packed by CTAs that
-// run in lock step, so the nearest inclusive prefix is usually many chunks back).  Returns the exclusive
-// prefix in every lane.
-__device__ __forceinline__ unsigned long long lookback_exclusive_warp(unsigned long long* state, int chunk,
-                                                                      unsigned long long aggregate) {
+// The same in two halves, for a warp: lookback_publish_aggregate (ONE lane) makes the chunk's aggregate visible
+// without waiting for anybody; lookback_resolve_warp (ALL 32 lanes of one warp, any time later) walks the
+// predecessors 32 at a time -- one memory round trip per 32 chunks instead of one per chunk --, publishes the
+// inclusive prefix and returns the exclusive prefix in every lane.  A CTA that publishes chunk i, goes on with
+// other work and resolves chunk i later never waits for predecessors that started before it.
+__device__ __forceinline__ void lookback_publish_aggregate(unsigned long long* state, int chunk,
+                                                           unsigned long long aggregate) {
+    st_relaxed_u64(&state[chunk], (chunk == 0 ? LB_INC : LB_AGG) | aggregate);
+}
+__device__ __forceinline__ unsigned long long lookback_resolve_warp(unsigned long long* state, int chunk,
+                                                                    unsigned long long aggregate) {
     const int lane = threadIdx.x & 31;
-    if (chunk == 0) {
-        if (lane == 0) st_relaxed_u64(&state[0], LB_INC | aggregate);
-        return 0ull;
-    }
-    if (lane == 0) st_relaxed_u64(&state[chunk], LB_AGG | aggregate);
+    if (chunk == 0) return 0ull;  // published as inclusive already
     unsigned long long excl = 0ull;
     int base = chunk - 1;
     while (true) {

@@ -710,104 +710,135 @@ __device__ __forceinline__ unsigned long long emit_range_fast(const uint32_t* __
     return bitpos;
 }
 
-constexpr int K3_WBUF_WORDS = 640;  // per-warp private bit buffer: 20480 bits (2.5 KB), 20 KB per CTA
+constexpr int K3_WBUF_WORDS = 576;  // per-warp private bit buffer: 18432 bits; two of them per warp (pipelined chunks)
 
+__device__ __forceinline__ uint32_t k3_load_ntok(const K3Args& a, int img, uint32_t chunk, int wid) {
+    if (a.n_segs) {
+        const uint32_t seg = chunk * (EB / 32) + wid;
+        return seg < a.n_segs ? a.tb.ntok[(size_t)img * a.n_segs + seg] : 0u;
+    }
+    return a.tb.ntok[(size_t)img * a.n_chunks + chunk];
+}
+
+// K3.  Work items = the chunks of ALL images, image-major, taken by one ticket in START order by a grid sized
+// to what the device holds at once.  A CTA works on TWO chunks at a time: it packs chunk i into one set of
+// per-warp buffers and publishes its bit count, and only then resolves the look-back of its previous chunk
+// and copies that one out -- by then the predecessors of the previous chunk have long published, so nobody
+// waits for a neighbour that is still packing.  The next ticket, the next image's code table and the next
+// token counts are requested while the current chunk is being packed.
 __global__ void __launch_bounds__(EB, 4) k3_pack(const K3Args a) {
-    __shared__ __align__(16) uint32_t s_wbuf[EB / 32][K3_WBUF_WORDS];
+    __shared__ __align__(16) uint32_t s_wbuf[2][EB / 32][K3_WBUF_WORDS];
     __shared__ __align__(8) uint2 s_enc2[4 * 256];
-    __shared__ unsigned long long s_wsum[EB / 32];
+    __shared__ uint32_t s_wsum[EB / 32];
     __shared__ unsigned long long s_prefix;
-    __shared__ unsigned int s_item;
-    __shared__ int s_err;
+    __shared__ unsigned int s_next;
+    __shared__ int s_err_next;
     __shared__ unsigned int s_ovf_tag;  // = 1 + item in which some warp's range did not fit its buffer
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    uint32_t* wbuf = s_wbuf[wid];
-    int cur_img = -1;
-    uint32_t zl_y = 0, zl_c = 0;
-    if (tid == 0) s_ovf_tag = 0u;
+    if (tid == 0) {
+        s_next = atomicAdd(a.ticket, 1u);
+        s_ovf_tag = 0u;
+    }
+    __syncthreads();
+    uint32_t item = s_next;
+    if (item >= a.n_items) return;
+    int cur_img = (int)(item / a.n_chunks);
+    // images flagged by K1/K2/K2b (range / capacity) are skipped; K3 itself only ever adds DMMT_E_SYMBOL
+    if (tid == 0) s_err_next = *reinterpret_cast<volatile int32_t*>(&a.meta[cur_img].error);
+    for (int i = tid; i < 1024; i += EB) {
+        const uint32_t e = a.enc[cur_img].e[i >> 8][i & 255];
+        const uint32_t len = e >> 16, cat = (uint32_t)i & 15u;
+        s_enc2[i] = len ? make_uint2((e & 0xFFFFu) << cat, len + cat)
+                        : make_uint2((uint32_t)i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
+    }
+    uint32_t ntok_cur = k3_load_ntok(a, cur_img, item % a.n_chunks, wid);
+    __syncthreads();
+    int err = s_err_next;
+    uint32_t zl_y = s_enc2[T_YAC * 256 + 0xF0].y, zl_c = s_enc2[T_CAC * 256 + 0xF0].y;
+    const unsigned long long seed = a.seed_src ? (*a.seed_src & 7ull) : a.seed_bits;
 
-    // Work items = the chunks of ALL images, image-major, taken by one ticket in START order (so a waiting
-    // chunk's predecessors are always running or done) by a grid sized to what the device holds at once:
-    // no second, partly empty wave however the image count divides the device.
+    bool pend = false;  // the previous chunk is packed in s_wbuf[buf ^ 1] and waits for its position
+    int p_img = 0, buf = 0;
+    uint32_t p_chunk = 0, p_wbase = 0, p_wbits = 0, p_cbits = 0;
+
     while (true) {
-        __syncthreads();  // everybody is done with s_item, s_enc2 and (overflow pass) the previous chunk
-        if (tid == 0) s_item = atomicAdd(a.ticket, 1u);
-        __syncthreads();
-        const uint32_t item = s_item;
-        if (item >= a.n_items) return;
-        const int img = (int)(item / a.n_chunks);
-        const uint32_t chunk = item % a.n_chunks;
-        if (img != cur_img) {  // CTA-uniform: (re)build the encoder LUT of this image
-            cur_img = img;
-            // images flagged by K1/K2/K2b (range / capacity) are skipped; K3 itself only ever adds DMMT_E_SYMBOL
-            if (tid == 0) s_err = *reinterpret_cast<volatile int32_t*>(&a.meta[img].error);
-            for (int i = tid; i < 1024; i += EB) {
-                const uint32_t e = a.enc[img].e[i >> 8][i & 255];
-                const uint32_t len = e >> 16, cat = (uint32_t)i & 15u;
-                s_enc2[i] = len ? make_uint2((e & 0xFFFFu) << cat, len + cat)
-                                : make_uint2((uint32_t)i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
-            }
-            __syncthreads();
-            zl_y = s_enc2[T_YAC * 256 + 0xF0].y, zl_c = s_enc2[T_CAC * 256 + 0xF0].y;
-        }
-        if (s_err != 0 && s_err != DMMT_E_SYMBOL) continue;
-        uint32_t* gscan = a.scan + (size_t)img * a.scan_img_stride_words;
+        const bool have = item < a.n_items;  // false only in the last round, which drains the pending chunk
+        const int img = cur_img;
+        const uint32_t chunk = have ? item % a.n_chunks : 0u;
+        const bool active = have && (err == 0 || err == DMMT_E_SYMBOL);
+        unsigned int nxt = 0xFFFFFFFFu;
+        if (tid == 0 && have) nxt = atomicAdd(a.ticket, 1u);  // in flight while this chunk is packed
 
         // token range of this warp: generic mode = a slice (multiple of 256 tokens, so the 128-bit loads
         // stay aligned) of the chunk's region; tile mode (fused K1) = the whole region of tile 8 * chunk + warp
-        const uint32_t* __restrict__ tok;
-        uint32_t begin, end;
-        if (a.n_segs) {
-            const uint32_t seg = chunk * (EB / 32) + wid;
-            tok = a.tb.tok + (size_t)img * a.tb.img_stride_words + (size_t)seg * a.tb.chunk_cap;
-            begin = 0;
-            end = seg < a.n_segs ? a.tb.ntok[(size_t)img * a.n_segs + seg] : 0u;
-        } else {
-            const uint32_t ntok = a.tb.ntok[(size_t)img * a.n_chunks + chunk];
-            tok = a.tb.tok + (size_t)img * a.tb.img_stride_words + (size_t)chunk * a.tb.chunk_cap;
-            const uint32_t per_warp = ((ntok + EB / 32 * K3_STEP - 1) / (EB / 32 * K3_STEP)) * K3_STEP;
-            begin = min(ntok, wid * per_warp), end = min(ntok, begin + per_warp);
+        const uint32_t* __restrict__ tok = a.tb.tok + (size_t)img * a.tb.img_stride_words;
+        uint32_t begin = 0, end = 0;
+        if (active) {
+            if (a.n_segs) {
+                tok += (size_t)(chunk * (EB / 32) + wid) * a.tb.chunk_cap;
+                end = ntok_cur;
+            } else {
+                tok += (size_t)chunk * a.tb.chunk_cap;
+                const uint32_t per_warp = ((ntok_cur + EB / 32 * K3_STEP - 1) / (EB / 32 * K3_STEP)) * K3_STEP;
+                begin = min(ntok_cur, wid * per_warp), end = min(ntok_cur, begin + per_warp);
+            }
         }
-
-        // ONE pass over the tokens: the warp packs its range into its private buffer from bit 0;
-        // where the range starts in the scan is only known after the look-back below
-#pragma unroll
-        for (int i = 0; i < K3_WBUF_WORDS / 128; i++)
-            reinterpret_cast<uint4*>(wbuf)[i * 32 + lane] = make_uint4(0, 0, 0, 0);
-        __syncwarp();
-        bool sym_ok = true, ovf = false;
-        const unsigned long long wbits = emit_range_fast(tok, begin, end, s_enc2, zl_y, zl_c, wbuf,
-                                                         (unsigned long long)K3_WBUF_WORDS * 32 - 64, sym_ok, ovf);
-        if (!sym_ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_SYMBOL);
-        if (lane == 0) {
-            s_wsum[wid] = wbits;
-            if (ovf) s_ovf_tag = item + 1u;
+        // ONE pass over the tokens: the warp packs its range into its private buffer from bit 0
+        uint32_t* wbuf = s_wbuf[buf][wid];
+        uint32_t wbits = 0;
+        if (active) {
+            for (int i = lane; i < K3_WBUF_WORDS / 4; i += 32) reinterpret_cast<uint4*>(wbuf)[i] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+            bool sym_ok = true, ovf = false;
+            wbits = (uint32_t)emit_range_fast(tok, begin, end, s_enc2, zl_y, zl_c, wbuf,
+                                              (unsigned long long)K3_WBUF_WORDS * 32 - 64, sym_ok, ovf);
+            if (!sym_ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_SYMBOL);
+            if (ovf && lane == 0) s_ovf_tag = item + 1u;
         }
-        __syncthreads();
-        unsigned long long wbase = 0, chunk_bits = 0;
+        if (lane == 0) s_wsum[wid] = wbits;
+        if (tid == 0) s_next = nxt;
+        __syncthreads();  // (a) bit counts, overflow tag and the next ticket are visible
+        uint32_t wbase = 0, cbits = 0;
 #pragma unroll
         for (int w = 0; w < EB / 32; w++) {
-            const unsigned long long v = s_wsum[w];
+            const uint32_t v = s_wsum[w];
             if (w < wid) wbase += v;
-            chunk_bits += v;
+            cbits += v;
         }
+        const bool cur_ovf = active && s_ovf_tag == item + 1u;
+        const uint32_t nitem = s_next;
+        const bool nhave = nitem < a.n_items;
+        const int nimg = nhave ? (int)(nitem / a.n_chunks) : cur_img;
         if (wid == 0) {
-            const unsigned long long ex = lookback_exclusive_warp(a.lb_state + (size_t)img * a.n_chunks, (int)chunk, chunk_bits);
-            if (lane == 0) s_prefix = ex;
+            if (active && lane == 0) lookback_publish_aggregate(a.lb_state + (size_t)img * a.n_chunks, (int)chunk, cbits);
+            if (pend) {
+                const unsigned long long ex =
+                    lookback_resolve_warp(a.lb_state + (size_t)p_img * a.n_chunks, (int)p_chunk, p_cbits);
+                if (lane == 0) s_prefix = ex;
+            }
         }
-        __syncthreads();
-        const unsigned long long g0 = (a.seed_src ? (*a.seed_src & 7ull) : a.seed_bits) + s_prefix;  // global bit position of the chunk
-        const unsigned long long p0 = g0 + wbase;                    // ... and of this warp's range
-        if (s_ovf_tag != item + 1u) {
+        // requests for the next chunk: code table and error flag if the image changes, token count
+        uint32_t e_next[1024 / EB];
+        if (nimg != cur_img) {
+#pragma unroll
+            for (int k = 0; k < 1024 / EB; k++) e_next[k] = a.enc[nimg].e[(tid + k * EB) >> 8][(tid + k * EB) & 255];
+            if (tid == 0) s_err_next = *reinterpret_cast<volatile int32_t*>(&a.meta[nimg].error);
+        }
+        const uint32_t ntok_next = nhave ? k3_load_ntok(a, nimg, nitem % a.n_chunks, wid) : 0u;
+        __syncthreads();  // (b) the pending chunk's prefix is known
+        if (pend) {
             // shifted copy of the private buffer to its place: destination word k holds relative bits
             // [32k - s, 32k - s + 32); the first and last word are shared with the neighbours
+            uint32_t* gscan = a.scan + (size_t)p_img * a.scan_img_stride_words;
+            const uint32_t* src = s_wbuf[buf ^ 1][wid];
+            const unsigned long long g0 = seed + s_prefix, p0 = g0 + p_wbase;
             const uint32_t sft = (uint32_t)(p0 & 31);
-            const uint32_t n_dst = (uint32_t)((sft + wbits + 31) >> 5);
+            const uint32_t n_dst = (sft + p_wbits + 31) >> 5;
             uint32_t* dst = gscan + (p0 >> 5);
             for (uint32_t k = lane; k < n_dst; k += 32) {
-                const uint32_t cur = k < (uint32_t)K3_WBUF_WORDS ? wbuf[k] : 0u;
-                const uint32_t prv = k ? wbuf[k - 1] : 0u;
+                const uint32_t cur = k < (uint32_t)K3_WBUF_WORDS ? src[k] : 0u;
+                const uint32_t prv = k ? src[k - 1] : 0u;
                 const uint32_t v = bswap32(__funnelshift_r(cur, prv, sft));
                 if (k == 0 || k == n_dst - 1) {
                     if (v) atomicOr(dst + k, v);
@@ -815,15 +846,53 @@ __global__ void __launch_bounds__(EB, 4) k3_pack(const K3Args a) {
                     dst[k] = v;
                 }
             }
-        } else {
-            // a range too dense for the private buffer (rare): second pass straight into the zeroed stream
+            if (p_chunk == a.n_chunks - 1 && a.pad_ones && tid == 0) {
+                const uint32_t pad = (uint32_t)((8 - ((g0 + p_cbits) & 7)) & 7);  // binary_stream.rs:89-96
+                if (pad) or_bits<false>(gscan, g0 + p_cbits, (1u << pad) - 1u, pad);
+            }
+        }
+        if (cur_ovf) {
+            // a range too dense for the private buffer (rare): resolve this chunk right away and make a second
+            // pass straight into the zeroed stream while its code table is still loaded
+            __syncthreads();
+            if (wid == 0) {
+                const unsigned long long ex = lookback_resolve_warp(a.lb_state + (size_t)img * a.n_chunks, (int)chunk, cbits);
+                if (lane == 0) s_prefix = ex;
+            }
+            __syncthreads();
+            uint32_t* gscan = a.scan + (size_t)img * a.scan_img_stride_words;
+            const unsigned long long g0 = seed + s_prefix;
             bool d0 = true, d1 = false;
-            (void)emit_range<false>(tok, begin, end, s_enc2, zl_y, zl_c, gscan, p0, ~0ull, d0, d1);
+            (void)emit_range<false>(tok, begin, end, s_enc2, zl_y, zl_c, gscan, g0 + wbase, ~0ull, d0, d1);
+            if (chunk == a.n_chunks - 1 && a.pad_ones && tid == 0) {
+                const uint32_t pad = (uint32_t)((8 - ((g0 + cbits) & 7)) & 7);
+                if (pad) or_bits<false>(gscan, g0 + cbits, (1u << pad) - 1u, pad);
+            }
+            __syncthreads();  // the table may be replaced below
+            pend = false;
+        } else {
+            pend = active;
+            p_img = img, p_chunk = chunk, p_wbase = wbase, p_wbits = wbits, p_cbits = cbits;
         }
-        if (chunk == a.n_chunks - 1 && a.pad_ones && tid == 0) {
-            const uint32_t pad = (uint32_t)((8 - ((g0 + chunk_bits) & 7)) & 7);  // binary_stream.rs:89-96
-            if (pad) or_bits<false>(gscan, g0 + chunk_bits, (1u << pad) - 1u, pad);
+        if (!nhave && !pend) return;
+        if (nimg != cur_img) {  // every warp is past its emission: install the next image's table
+#pragma unroll
+            for (int k = 0; k < 1024 / EB; k++) {
+                const uint32_t i = (uint32_t)tid + k * EB, e = e_next[k];
+                const uint32_t len = e >> 16, cat = i & 15u;
+                s_enc2[i] = len ? make_uint2((e & 0xFFFFu) << cat, len + cat)
+                                : make_uint2(i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
+            }
         }
+        __syncthreads();  // (c) table, error flag ready; s_wsum / s_next / s_prefix may be rewritten
+        if (nimg != cur_img) {
+            cur_img = nimg;
+            err = s_err_next;
+            zl_y = s_enc2[T_YAC * 256 + 0xF0].y, zl_c = s_enc2[T_CAC * 256 + 0xF0].y;
+        }
+        item = nitem;
+        ntok_cur = ntok_next;
+        buf ^= 1;
     }
 }
 
