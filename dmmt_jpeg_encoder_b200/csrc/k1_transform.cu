@@ -204,6 +204,7 @@ struct K1Args {
     ImgMeta* meta;               // [n] error flags
     QuantF qf;                   // divisors
     QuantF rq_hi, rq_lo;         // 1/q split in two f32 (see quantize)
+    float neg_zero;              // -0.0f, opaque to ptxas: addend of the never-contracted packed multiply (mulx)
     int force_scalar;            // DMMT_K1_SCALAR=1: use the scalar kernel for P420 too (A/B measurements)
     TileTok fo;                  // fused path: token stream per tile (k1_transform_p420<FMT, true>)
     unsigned int* hist;          // fused path: [n][4][256]
@@ -431,8 +432,12 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform(const __grid_const
 // fewer issue slots, which moves it from issue-bound to FP32-lane-bound (tools/ubench_pipes.cu).
 //
 // CAUTION (verified on ptxas 12.9): ptxas contracts mul.rn.f32x2 feeding add/sub.rn.f32x2 into
-// FFMA2 even under --fmad=false.  Therefore every multiplication whose product feeds an addition
-// is issued as a SCALAR __fmul_rn (never contracted); packed multiplies are only used where the
+// FFMA2 even under --fmad=false (and folds fma(a, b, -0.0) with a literal -0.0 back into that
+// multiply first).  Therefore a multiplication whose product feeds an addition is issued as `mulx`:
+// fma.rn.f32x2(a, c, nz) with nz = -0.0 read from the kernel arguments, i.e. opaque to ptxas.
+// a * c + (-0.0) rounds once and equals fl(a * c) for every input including both zeros, and an
+// FFMA2 cannot be contracted any further (SASS: one FFMA2 with the constant as a broadcast
+// immediate, followed by separate FADD2s).  Plain packed multiplies (mul2) are only used where the
 // product feeds a multiply, an fma multiplicand/addend, a conversion or a store.
 // tests/test_cuda_parity.py compares every coefficient bit for bit, which would expose a contraction.
 typedef unsigned long long f2;  // two f32 in an aligned register pair: {lo, hi}
@@ -473,24 +478,24 @@ __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
-// product that feeds an addition: two scalar multiplies (see CAUTION above)
-__device__ __forceinline__ f2 mul2s(f2 a, float c) { return pk(__fmul_rn(lo_of(a), c), __fmul_rn(hi_of(a), c)); }
+// product that feeds an addition: fl(a * c) as one FFMA2 that ptxas cannot contract (see CAUTION above)
+__device__ __forceinline__ f2 mulx(f2 a, float c, f2 nz) { return fma2(a, bc(c), nz); }
 
 // arai.rs:29-92 on two independent 8-vectors at once.  -v24 never materialises: with u24 = v14 + v15,
 // v24 = (-v14) - v15 = -u24 exactly, (-v24) * A2 = u24 * A2 and v24 + v26 = v26 - u24 (same roundings).
 // The eight scaled outputs are produced by `out(k, v, S_k)`.
 template <class Out>
-__device__ __forceinline__ void fast_arai2(f2 x0, f2 x1, f2 x2, f2 x3, f2 x4, f2 x5, f2 x6, f2 x7, Out&& out) {
+__device__ __forceinline__ void fast_arai2(f2 x0, f2 x1, f2 x2, f2 x3, f2 x4, f2 x5, f2 x6, f2 x7, f2 nz, Out&& out) {
     const f2 v10 = add2(x0, x7), v11 = add2(x1, x6), v12 = add2(x2, x5), v13 = add2(x3, x4);
     const f2 v14 = sub2(x3, x4), v15 = sub2(x2, x5), v16 = sub2(x1, x6), v17 = sub2(x0, x7);
     const f2 v20 = add2(v10, v13), v21 = add2(v11, v12), v22 = sub2(v11, v12), v23 = sub2(v10, v13);
     const f2 u24 = add2(v14, v15), v25 = add2(v15, v16), v26 = add2(v16, v17);
     const f2 v30 = add2(v20, v21), v31 = sub2(v20, v21), v32 = add2(v22, v23);
-    const f2 v42 = mul2s(v32, kA1);
-    const f2 t5 = mul2s(sub2(v26, u24), kA5);
-    const f2 v44 = sub2(mul2s(u24, kA2), t5);
-    const f2 v45 = mul2s(v25, kA3);
-    const f2 v46 = sub2(mul2s(v26, kA4), t5);
+    const f2 v42 = mulx(v32, kA1, nz);
+    const f2 t5 = mulx(sub2(v26, u24), kA5, nz);
+    const f2 v44 = sub2(mulx(u24, kA2, nz), t5);
+    const f2 v45 = mulx(v25, kA3, nz);
+    const f2 v46 = sub2(mulx(v26, kA4, nz), t5);
     const f2 v52 = add2(v42, v23), v53 = sub2(v23, v42), v55 = add2(v45, v17), v57 = sub2(v17, v45);
     const f2 v64 = add2(v44, v57), v65 = add2(v55, v46), v66 = sub2(v55, v46), v67 = sub2(v57, v44);
     out(0, v30, kS0);
@@ -538,6 +543,7 @@ __device__ __forceinline__ bool p420_block_coefs(const K1Args& a, int u, int mcu
                                                  int& comp) {
     constexpr int NYU = 64, NCU = 16;
     f2 P[4][8];  // P[j][c] = {d[2j][c], d[2j+1][c]}
+    const f2 nz = bc(a.neg_zero);
     if (u < NYU) {
         const int q = u >> 4, sx = u & 15;
         const int byl = q >> 1, p = q & 1;
@@ -568,7 +574,7 @@ __device__ __forceinline__ bool p420_block_coefs(const K1Args& a, int u, int mcu
     float d[64];
 #pragma unroll
     for (int j = 0; j < 4; j++)
-        fast_arai2(P[j][0], P[j][1], P[j][2], P[j][3], P[j][4], P[j][5], P[j][6], P[j][7], [&](int kk, f2 v, float S) {
+        fast_arai2(P[j][0], P[j][1], P[j][2], P[j][3], P[j][4], P[j][5], P[j][6], P[j][7], nz, [&](int kk, f2 v, float S) {
             d[16 * j + kk] = __fmul_rn(lo_of(v), S);
             d[16 * j + 8 + kk] = __fmul_rn(hi_of(v), S);
         });
@@ -579,7 +585,7 @@ __device__ __forceinline__ bool p420_block_coefs(const K1Args& a, int u, int mcu
         fast_arai2(pk(d[2 * kp], d[2 * kp + 1]), pk(d[8 + 2 * kp], d[8 + 2 * kp + 1]), pk(d[16 + 2 * kp], d[16 + 2 * kp + 1]),
                    pk(d[24 + 2 * kp], d[24 + 2 * kp + 1]), pk(d[32 + 2 * kp], d[32 + 2 * kp + 1]),
                    pk(d[40 + 2 * kp], d[40 + 2 * kp + 1]), pk(d[48 + 2 * kp], d[48 + 2 * kp + 1]),
-                   pk(d[56 + 2 * kp], d[56 + 2 * kp + 1]), [&](int r, f2 v, float S) { D[r][kp] = mul2(v, bc(S)); });
+                   pk(d[56 + 2 * kp], d[56 + 2 * kp + 1]), nz, [&](int r, f2 v, float S) { D[r][kp] = mul2(v, bc(S)); });
 
     // quantise: x = fma(d, rq_hi, d * rq_lo), round half away from zero, saturate (see quantize<>).
     // `comp` is warp-uniform (warps 0-1 luma, warp 2 chroma), so the table is selected by a uniform
@@ -668,7 +674,10 @@ __device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, 
 }
 
 template <int FMT, bool FUSED>
-__global__ void __launch_bounds__(K1_THREADS, FUSED ? 6 : 5) k1_transform_p420(const __grid_constant__ K1Args a) {
+#ifndef K1_MINB
+#define K1_MINB 6
+#endif
+__global__ void __launch_bounds__(K1_THREADS, FUSED ? K1_MINB : 5) k1_transform_p420(const __grid_constant__ K1Args a) {
     // planes as ROW-PAIR interleaved float4 = {v(x,2j), v(x,2j+1), v(x+1,2j), v(x+1,2j+1)}:
     //   sY[row pair][16-byte chunk: 2 columns][strip], sC*[row pair][chunk][strip]
     __shared__ __align__(16) float4 s_planes[8 * 8 * 16 + 2 * 4 * 4 * 16];  // 24 KB: Y | Cb | Cr (reused for tokens)
@@ -710,7 +719,7 @@ __global__ void __launch_bounds__(K1_THREADS, FUSED ? 6 : 5) k1_transform_p420(c
                 }
             }
         }
-        const f2 rhi = bc(a.r_hi), rlo = bc(a.r_lo);
+        const f2 rhi = bc(a.r_hi), rlo = bc(a.r_lo), nz = bc(a.neg_zero);
         float* cbp = reinterpret_cast<float*>(&sCb[sy >> 1][0][sx]) + (sy & 1);
         float* crp = reinterpret_cast<float*>(&sCr[sy >> 1][0][sx]) + (sy & 1);
 #pragma unroll
@@ -734,16 +743,16 @@ __global__ void __launch_bounds__(K1_THREADS, FUSED ? 6 : 5) k1_transform_p420(c
                 }
                 // color.rs:75-100, products scalar (they feed additions), sums and final scale packed
                 constexpr float kShift = 128.0f / 255.0f;
-                yy[q] = mul2(add2(add2(add2(mul2s(n[0], 0.299f), mul2s(n[1], 0.587f)), mul2s(n[2], 0.114f)), bc(-kShift)),
+                yy[q] = mul2(add2(add2(add2(mulx(n[0], 0.299f, nz), mulx(n[1], 0.587f, nz)), mulx(n[2], 0.114f, nz)), bc(-kShift)),
                              bc(255.0f));
                 if constexpr (FMT == DMMT_RGB_F32_NORM) {
-                    cb[q] = mul2(add2(add2(mul2s(n[0], -0.1687f), mul2s(n[1], -0.3312f)), mul2s(n[2], 0.5f)), bc(255.0f));
-                    cr[q] = mul2(add2(add2(mul2s(n[0], 0.5f), mul2s(n[1], -0.4186f)), mul2s(n[2], -0.0813f)), bc(255.0f));
+                    cb[q] = mul2(add2(add2(mulx(n[0], -0.1687f, nz), mulx(n[1], -0.3312f, nz)), mulx(n[2], 0.5f, nz)), bc(255.0f));
+                    cr[q] = mul2(add2(add2(mulx(n[0], 0.5f, nz), mulx(n[1], -0.4186f, nz)), mulx(n[2], -0.0813f, nz)), bc(255.0f));
                 } else {
                     // x * 0.5 is exact for normalised integer samples, so s + x * 0.5 == fma(x, 0.5, s) bit for bit:
                     // the two halvings ride on the additions they feed (one packed FFMA2 instead of 2 FMUL + FADD2)
-                    cb[q] = mul2(fma2(n[2], bc(0.5f), add2(mul2s(n[0], -0.1687f), mul2s(n[1], -0.3312f))), bc(255.0f));
-                    cr[q] = mul2(add2(fma2(n[0], bc(0.5f), mul2s(n[1], -0.4186f)), mul2s(n[2], -0.0813f)), bc(255.0f));
+                    cb[q] = mul2(fma2(n[2], bc(0.5f), add2(mulx(n[0], -0.1687f, nz), mulx(n[1], -0.3312f, nz))), bc(255.0f));
+                    cr[q] = mul2(add2(fma2(n[0], bc(0.5f), mulx(n[1], -0.4186f, nz)), mulx(n[2], -0.0813f, nz)), bc(255.0f));
                 }
             }
             sY[sy][c][sx] = make_float4(lo_of(yy[0]), hi_of(yy[0]), lo_of(yy[1]), hi_of(yy[1]));
@@ -920,6 +929,9 @@ template <int HR, int VR, int FMT>
 cudaError_t launch_fmt(const K1Args& a, dim3 grid, bool dbg, bool exact, cudaStream_t st) {
     if constexpr (HR == 2 && VR == 2) {
         if (!dbg && !exact && !a.force_scalar) {
+            // shared memory is what bounds residency, L1 is barely used (streaming loads): take the largest carve-out
+            static const cudaError_t carve = cudaFuncSetAttribute(k1_transform_p420<FMT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            (void)carve;
             if (a.fo.tok) k1_transform_p420<FMT, true><<<grid, K1_THREADS, 0, st>>>(a);
             else k1_transform_p420<FMT, false><<<grid, K1_THREADS, 0, st>>>(a);
             return cudaGetLastError();
@@ -976,6 +988,7 @@ cudaError_t launch_k1(const Geom& g, int fmt, const K1Consts& c, int check_max, 
     a.maxf = c.maxf;
     a.r_hi = c.r_hi;
     a.r_lo = c.r_lo;
+    a.neg_zero = -0.0f;
     const size_t pb = (fmt == DMMT_RGB_U8) ? 3 : (fmt == DMMT_RGB_U16 ? 6 : 12);
     a.vec_ok = ((reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0) && (((size_t)g.W * pb) % 16 == 0) &&
                (img_stride_bytes % 16 == 0);
