@@ -171,6 +171,57 @@ __device__ __forceinline__ void load_strip_row(const uint8_t* __restrict__ row_b
     }
 }
 
+// Raw samples of one row of an 8-pixel strip (the P420 kernels): 24 / 48 / 96 bytes, same three
+// cases as load_strip_row.  The strip starts at a multiple of 8 pixels, so it is 8-byte (u8) or
+// 16-byte (u16, f32) aligned whenever the row is.
+template <int FMT>
+__device__ __forceinline__ void load_strip8_row(const uint8_t* __restrict__ row_base, int x0, int W, bool row_valid,
+                                                bool vec_ok, uint32_t (&w)[Px<FMT>::kWords / 2]) {
+    constexpr int NW = Px<FMT>::kWords / 2;
+    if (row_valid && vec_ok && x0 + 8 <= W) {
+        if constexpr (FMT == DMMT_RGB_U8) {
+            const uint2* p = reinterpret_cast<const uint2*>(row_base + (size_t)x0 * 3);
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const uint2 v = __ldg(p + i);
+                w[2 * i] = v.x, w[2 * i + 1] = v.y;
+            }
+        } else {
+            const uint4* p = reinterpret_cast<const uint4*>(row_base + (size_t)x0 * Px<FMT>::kBytes);
+#pragma unroll
+            for (int i = 0; i < NW / 4; i++) {
+                const uint4 v = __ldg(p + i);
+                w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i] = 0u;
+    if (!row_valid || x0 >= W) return;
+    // ragged edge / unaligned pitch: rare, so a rolled loop over a local array keeps the cold code
+    // small (the hot path stays contiguous in the instruction cache)
+    const int nval = min(8, W - x0) * 3;  // samples available
+    uint32_t tmp[NW];
+#pragma unroll 1
+    for (int i = 0; i < NW; i++) tmp[i] = 0u;
+    if constexpr (FMT == DMMT_RGB_U8) {
+        const uint8_t* q = row_base + (size_t)x0 * 3;
+#pragma unroll 1
+        for (int i = 0; i < nval; i++) tmp[i >> 2] |= (uint32_t)q[i] << (8 * (i & 3));
+    } else if constexpr (FMT == DMMT_RGB_U16) {
+        const uint16_t* q = reinterpret_cast<const uint16_t*>(row_base) + (size_t)x0 * 3;
+#pragma unroll 1
+        for (int i = 0; i < nval; i++) tmp[i >> 1] |= (uint32_t)q[i] << (16 * (i & 1));
+    } else {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(row_base) + (size_t)x0 * 3;
+#pragma unroll 1
+        for (int i = 0; i < nval; i++) tmp[i] = q[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i] = tmp[i];
+}
+
 // sample i (0..47) of the strip row as the reference's normalised f32 (color.rs:45-53).
 // v / max == fma(v, r_hi, v * r_lo) for every v <= max <= 65535 (exhaustively verified on the host
 // at plan creation, dmmt_api.cu; tools/exhaustive_div.cu checks all max); `exact` selects IEEE division.
@@ -509,8 +560,8 @@ __device__ __forceinline__ void fast_arai2(f2 x0, f2 x1, f2 x2, f2 x3, f2 x4, f2
 }
 
 // raw sample i (0..47) of a strip row as f32 (before normalisation)
-template <int FMT>
-__device__ __forceinline__ float sample_raw(const uint32_t (&w)[Px<FMT>::kWords], int i) {
+template <int FMT, int NW>
+__device__ __forceinline__ float sample_raw(const uint32_t (&w)[NW], int i) {
     if constexpr (FMT == DMMT_RGB_F32_NORM) return __uint_as_float(w[i]);
     else if constexpr (FMT == DMMT_RGB_U8) return (float)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
     else return (float)((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
@@ -537,7 +588,7 @@ __device__ __forceinline__ void quantize_block_packed(const K1Args& a, const f2 
 // Phase B of the P420 kernels: block `u` of the tile (stream slot m * 6 + k) -> 64 quantised
 // coefficients in NATURAL order.  Returns false for blocks of MCUs beyond the padded image.
 template <int FMT>
-__device__ __forceinline__ bool p420_block_coefs(const K1Args& a, int u, int mcus_here, const float4 (*sY)[8][16],
+__device__ __forceinline__ bool p420_block_coefs(const K1Args& a, int u, int mcus_here, const float4 (*sY)[4][32],
                                                  const float4 (*sCb)[4][16], const float4 (*sCr)[4][16],
                                                  const int* s_flag_p, unsigned short (&qv)[64], int& m, int& k,
                                                  int& comp) {
@@ -545,14 +596,14 @@ __device__ __forceinline__ bool p420_block_coefs(const K1Args& a, int u, int mcu
     f2 P[4][8];  // P[j][c] = {d[2j][c], d[2j+1][c]}
     const f2 nz = bc(a.neg_zero);
     if (u < NYU) {
-        const int q = u >> 4, sx = u & 15;
-        const int byl = q >> 1, p = q & 1;
-        comp = 0, m = sx, k = byl * 2 + p;
+        // warp 0: upper block row of the MCU row, warp 1: lower; lane = block column = 8-pixel strip
+        const int byl = u >> 5, bx = u & 31;
+        comp = 0, m = bx >> 1, k = byl * 2 + (bx & 1);
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
             for (int cc = 0; cc < 4; cc++) {
-                const float4 v = sY[4 * byl + j][4 * p + cc][sx];
+                const float4 v = sY[4 * byl + j][cc][bx];
                 P[j][2 * cc] = pk(v.x, v.y), P[j][2 * cc + 1] = pk(v.z, v.w);
             }
     } else {
@@ -607,9 +658,12 @@ __device__ __forceinline__ bool p420_block_coefs(const K1Args& a, int u, int mcu
 
 // categorize.rs:22-41 for a non-zero value: category and the cat low bits of the pattern
 __device__ __forceinline__ void k1_cat_bits(int v, int& cat, uint32_t& bits) {
-    const int av = abs(v);
-    cat = 32 - __clz(av);
-    bits = (uint32_t)(v > 0 ? v : v - 1) & ((1u << cat) - 1u);
+    const uint32_t av = (uint32_t)abs(v);
+    uint32_t msb;
+    asm("bfind.u32 %0, %1;" : "=r"(msb) : "r"(av));  // position of the leading one (v != 0)
+    cat = (int)msb + 1;
+    // v > 0: v; v < 0: v - 1 == ~|v|  -> one xor with the sign mask, then the low `cat` bits
+    bits = (av ^ (uint32_t)(v >> 31)) & ~(0xFFFFFFFFu << cat);
 }
 __device__ __forceinline__ uint32_t k1_token(int table, int sym, int nzrl, uint32_t extra) {
     return (uint32_t)sym | ((uint32_t)table << 8) | ((uint32_t)nzrl << 10) | (extra << 16);
@@ -623,6 +677,8 @@ __device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, 
                                                     const short* s_dc, const uint4* s_stage, unsigned int* s_hist,
                                                     uint32_t* dcpos) {
     const int tdc = comp ? T_CDC : T_YDC, tac = tdc + 1;
+    unsigned int* const h_dc = s_hist + (comp ? 16 : 0);     // tile histogram layout: SH_YDC / SH_CDC / SH_YAC / SH_CAC
+    unsigned int* const h_ac = s_hist + (comp ? 288 : 32);
     bool ok = true;
     {
         const int ps = k == 0 ? slot - 3 : (k < 4 ? slot - 1 : slot - 6);
@@ -632,7 +688,7 @@ __device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, 
             uint32_t bits = 0;
             if (diff != 0) k1_cat_bits(diff, cat, bits);
             ok &= cat <= 15;
-            atomicAdd(&s_hist[tdc * 256 + (cat & 15)], 1u);
+            atomicAdd(&h_dc[cat & 15], 1u);
             if (store) dst[off] = k1_token(tdc, cat & 15, 0, bits);
         } else {
             // predictor is in the previous tile (or is the seed): k2_fix_dc finishes this token
@@ -647,10 +703,11 @@ __device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, 
     uint32_t nzrl_total = 0;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-        uint32_t mk = half ? mhi : (mlo & ~1u);
+        uint32_t mk = __brev(half ? mhi : (mlo & ~1u));  // bit-reversed once: the walk needs one FLO per step
         while (mk) {
-            const int pos = 32 * half + __ffs((int)mk) - 1;
-            mk &= mk - 1;
+            const int lz = __clz((int)mk);
+            const int pos = 32 * half + lz;
+            mk &= ~(0x80000000u >> lz);
             const int run = pos - prev - 1;
             prev = pos;
             const int v = sb[pos ^ sw8];  // chunk (pos >> 3) lives at slot (pos >> 3) ^ (slot & 7)
@@ -660,39 +717,44 @@ __device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, 
             ok &= cat <= 15;
             const int sym = ((run & 15) << 4) | (cat & 15);
             nzrl_total += (uint32_t)(run >> 4);
-            atomicAdd(&s_hist[tac * 256 + sym], 1u);
+            atomicAdd(&h_ac[sym], 1u);
             if (store) dst[off] = k1_token(tac, sym, run >> 4, bits);
             ++off;
         }
     }
-    if (nzrl_total) atomicAdd(&s_hist[tac * 256 + 0xF0], nzrl_total);
+    if (nzrl_total) atomicAdd(&h_ac[0xF0], nzrl_total);
     if (prev != 63) {
-        atomicAdd(&s_hist[tac * 256], 1u);
+        atomicAdd(&h_ac[0], 1u);
         if (store) dst[off] = k1_token(tac, 0x00, 0, 0u);
     }
     return ok;
 }
 
-template <int FMT, bool FUSED>
+constexpr int P420_THREADS = 96;   // one thread per 8x8 block of the tile (16 MCUs x 6 blocks)
+// shared-memory histogram of a tile: only the bins that exist, [Y-DC 16 | C-DC 16 | Y-AC 256 | C-AC 256]
+constexpr int SH_YDC = 0, SH_CDC = 16, SH_YAC = 32, SH_CAC = 288, SH_BINS = 544;
+
 #ifndef K1_MINB
-#define K1_MINB 6
+#define K1_MINB 8
 #endif
-__global__ void __launch_bounds__(K1_THREADS, FUSED ? K1_MINB : 5) k1_transform_p420(const __grid_constant__ K1Args a) {
+// CTA = 96 threads = 3 warps, every one of them busy in every phase: 8 CTAs (24 warps) per SM at 80 registers.
+template <int FMT, bool FUSED>
+__global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transform_p420(const __grid_constant__ K1Args a) {
     // planes as ROW-PAIR interleaved float4 = {v(x,2j), v(x,2j+1), v(x+1,2j), v(x+1,2j+1)}:
-    //   sY[row pair][16-byte chunk: 2 columns][strip], sC*[row pair][chunk][strip]
-    __shared__ __align__(16) float4 s_planes[8 * 8 * 16 + 2 * 4 * 4 * 16];  // 24 KB: Y | Cb | Cr (reused for tokens)
-    float4(*sY)[8][16] = reinterpret_cast<float4(*)[8][16]>(s_planes);
+    //   sY[row pair][16-byte chunk of the strip: 2 columns][8-pixel strip], sC*[row pair][chunk][MCU]
+    __shared__ __align__(16) float4 s_planes[8 * 4 * 32 + 2 * 4 * 4 * 16];  // 24 KB: Y | Cb | Cr (reused for tokens)
+    float4(*sY)[4][32] = reinterpret_cast<float4(*)[4][32]>(s_planes);
     float4(*sCb)[4][16] = reinterpret_cast<float4(*)[4][16]>(s_planes + 1024);
     float4(*sCr)[4][16] = reinterpret_cast<float4(*)[4][16]>(s_planes + 1280);
     // quantised blocks of the tile in stream order (zig-zag, swizzled): own array on the coefficient path,
     // the first half of the (dead) plane storage on the fused path
     __shared__ uint4 s_stage_own[FUSED ? 1 : 96 * 8];
     uint4* s_stage = FUSED ? reinterpret_cast<uint4*>(s_planes) : s_stage_own;
-    __shared__ __align__(16) unsigned int s_hist[FUSED ? 1024 : 4];   // fused path: symbol counts of the tile
+    __shared__ __align__(16) unsigned int s_hist[FUSED ? SH_BINS : 4];   // fused path: symbol counts of the tile
     __shared__ uint32_t s_cnt[FUSED ? 100 : 1];         // tokens per block, then exclusive offsets (+ total)
     __shared__ short s_dc[FUSED ? 96 : 1];
     __shared__ int s_flag;
-    constexpr int BPM = 6, MPT = 16, NYU = 64, NCU = 16, NUNITS = 96;
+    constexpr int BPM = 6, MPT = 16, NUNITS = 96;
     if constexpr (FMT == DMMT_RGB_F32_NORM) {
         if (threadIdx.x == 0) s_flag = 0;
         __syncthreads();
@@ -701,67 +763,86 @@ __global__ void __launch_bounds__(K1_THREADS, FUSED ? K1_MINB : 5) k1_transform_
     const uint8_t* __restrict__ pix = a.pixels + (size_t)img * a.img_stride_bytes;
     const size_t pitch = (size_t)a.W * Px<FMT>::kBytes;
 
-    // ---------------- phase A: strip = 16 px x 2 rows, both rows packed in one register pair ----------------
+    // ---------------- phase A: strip = 8 px x 2 rows, both rows packed in one register pair ----------------
+    // 256 strips per tile = 8 row pairs x 32 strips; a warp takes one whole row pair per round (rounds 0-1: all
+    // three warps, round 2: warps 0 and 1), so the plane stores of a warp are contiguous.
     {
-        const int sx = threadIdx.x & 15, sy = threadIdx.x >> 4;  // sy = row pair of the MCU row
-        const int x0 = tile_x * TILE_W + sx * 16;
-        const int y = mrow * 16 + 2 * sy;
-        uint32_t w0[Px<FMT>::kWords], w1[Px<FMT>::kWords];
-        load_strip_row<FMT>(pix + (size_t)y * pitch, x0, a.W, y < a.H, a.vec_ok != 0, w0);
-        load_strip_row<FMT>(pix + (size_t)(y + 1) * pitch, x0, a.W, y + 1 < a.H, a.vec_ok != 0, w1);
-        bool bad = false;
-        if constexpr (FMT != DMMT_RGB_F32_NORM) {
-            if (a.check_max) {  // color.rs:62-65 (SIMD-in-word compare)
-#pragma unroll
-                for (int i = 0; i < Px<FMT>::kWords; i++) {
-                    bad |= (FMT == DMMT_RGB_U8 ? __vcmpgtu4(w0[i], a.max_rep) : __vcmpgtu2(w0[i], a.max_rep)) != 0u;
-                    bad |= (FMT == DMMT_RGB_U8 ? __vcmpgtu4(w1[i], a.max_rep) : __vcmpgtu2(w1[i], a.max_rep)) != 0u;
-                }
-            }
-        }
+        constexpr int NW = Px<FMT>::kWords / 2;
         const f2 rhi = bc(a.r_hi), rlo = bc(a.r_lo), nz = bc(a.neg_zero);
-        float* cbp = reinterpret_cast<float*>(&sCb[sy >> 1][0][sx]) + (sy & 1);
-        float* crp = reinterpret_cast<float*>(&sCr[sy >> 1][0][sx]) + (sy & 1);
+        bool bad = false;
+        // Rolled on purpose (strips, then the two 4-pixel halves of a strip): the loop body is what stays in
+        // the instruction cache; fully unrolled, the kernel's hot code exceeds the 32 KB L1.5 I-cache and a
+        // quarter of phase B's cycles were instruction-fetch stalls (profiles/).
+#pragma unroll 1
+        for (int s = (int)threadIdx.x; s < 256; s += P420_THREADS) {
+            const int sx = s & 31, sy = s >> 5;  // sy = row pair of the MCU row (warp-uniform)
+            const int x0 = tile_x * TILE_W + sx * 8;
+            const int y = mrow * 16 + 2 * sy;
+            uint32_t w0[NW], w1[NW];
+            load_strip8_row<FMT>(pix + (size_t)y * pitch, x0, a.W, y < a.H, a.vec_ok != 0, w0);
+            load_strip8_row<FMT>(pix + (size_t)(y + 1) * pitch, x0, a.W, y + 1 < a.H, a.vec_ok != 0, w1);
+            if constexpr (FMT != DMMT_RGB_F32_NORM) {
+                if (a.check_max) {  // color.rs:62-65 (SIMD-in-word compare)
 #pragma unroll
-        for (int c = 0; c < 8; c++) {  // chunk = 2 pixels x 2 rows
-            f2 yy[2], cb[2], cr[2];
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int p = 2 * c + q;
-                f2 n[3];
-#pragma unroll
-                for (int ch = 0; ch < 3; ch++) {
-                    // (u8 -> f32 stays on I2F: the PRMT 0x4B000000 + FADD2 trick was measured 7 % slower, the
-                    // quarter-rate conversion pipe is not what limits this kernel)
-                    const f2 v = pk(sample_raw<FMT>(w0, 3 * p + ch), sample_raw<FMT>(w1, 3 * p + ch));
-                    if constexpr (FMT == DMMT_RGB_F32_NORM) {
-                        n[ch] = v;
-                        bad |= !(fabsf(lo_of(v)) <= 1024.0f) | !(fabsf(hi_of(v)) <= 1024.0f);
-                    } else {
-                        n[ch] = fma2(v, rhi, mul2(v, rlo));  // v / max, proven per plan (make_k1_consts)
+                    for (int i = 0; i < NW; i++) {
+                        bad |= (FMT == DMMT_RGB_U8 ? __vcmpgtu4(w0[i], a.max_rep) : __vcmpgtu2(w0[i], a.max_rep)) != 0u;
+                        bad |= (FMT == DMMT_RGB_U8 ? __vcmpgtu4(w1[i], a.max_rep) : __vcmpgtu2(w1[i], a.max_rep)) != 0u;
                     }
                 }
-                // color.rs:75-100, products scalar (they feed additions), sums and final scale packed
-                constexpr float kShift = 128.0f / 255.0f;
-                yy[q] = mul2(add2(add2(add2(mulx(n[0], 0.299f, nz), mulx(n[1], 0.587f, nz)), mulx(n[2], 0.114f, nz)), bc(-kShift)),
-                             bc(255.0f));
-                if constexpr (FMT == DMMT_RGB_F32_NORM) {
-                    cb[q] = mul2(add2(add2(mulx(n[0], -0.1687f, nz), mulx(n[1], -0.3312f, nz)), mulx(n[2], 0.5f, nz)), bc(255.0f));
-                    cr[q] = mul2(add2(add2(mulx(n[0], 0.5f, nz), mulx(n[1], -0.4186f, nz)), mulx(n[2], -0.0813f, nz)), bc(255.0f));
-                } else {
-                    // x * 0.5 is exact for normalised integer samples, so s + x * 0.5 == fma(x, 0.5, s) bit for bit:
-                    // the two halvings ride on the additions they feed (one packed FFMA2 instead of 2 FMUL + FADD2)
-                    cb[q] = mul2(fma2(n[2], bc(0.5f), add2(mulx(n[0], -0.1687f, nz), mulx(n[1], -0.3312f, nz))), bc(255.0f));
-                    cr[q] = mul2(add2(fma2(n[0], bc(0.5f), mulx(n[1], -0.4186f, nz)), mulx(n[2], -0.0813f, nz)), bc(255.0f));
-                }
             }
-            sY[sy][c][sx] = make_float4(lo_of(yy[0]), hi_of(yy[0]), lo_of(yy[1]), hi_of(yy[1]));
-            // window (x,y),(x,y+1),(x+1,y),(x+1,y+1), f32 sum from 0, / 4 (subsampling.rs:108-122,231-236)
-            const float sb = __fadd_rn(__fadd_rn(__fadd_rn(lo_of(cb[0]), hi_of(cb[0])), lo_of(cb[1])), hi_of(cb[1]));
-            const float sr = __fadd_rn(__fadd_rn(__fadd_rn(lo_of(cr[0]), hi_of(cr[0])), lo_of(cr[1])), hi_of(cr[1]));
-            // chroma column c of the strip: chunk c >> 1, column c & 1; this thread owns half `sy & 1` of each pair
-            cbp[(c >> 1) * 64 + (c & 1) * 2] = __fmul_rn(sb, 0.25f);
-            crp[(c >> 1) * 64 + (c & 1) * 2] = __fmul_rn(sr, 0.25f);
+            // chroma sample c of the strip is column 4 * (sx & 1) + c of chroma block sx >> 1: chunk
+            // 2 * (sx & 1) + (c >> 1), column c & 1 of it; this thread owns half `sy & 1` of each row pair
+            float* cbp = reinterpret_cast<float*>(&sCb[sy >> 1][2 * (sx & 1)][sx >> 1]) + (sy & 1);
+            float* crp = reinterpret_cast<float*>(&sCr[sy >> 1][2 * (sx & 1)][sx >> 1]) + (sy & 1);
+            float4* yp = &sY[sy][0][sx];
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {  // pixels 4h .. 4h+3 of the strip = the first NW / 2 words
+#pragma unroll
+                for (int cl = 0; cl < 2; cl++) {  // chunk 2h + cl = 2 pixels x 2 rows
+                    f2 yy[2], cb[2], cr[2];
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int p = 2 * cl + q;
+                        f2 n[3];
+#pragma unroll
+                        for (int ch = 0; ch < 3; ch++) {
+                            // (u8 -> f32 stays on I2F: the PRMT 0x4B000000 + FADD2 trick was measured 7 % slower)
+                            const f2 v = pk(sample_raw<FMT>(w0, 3 * p + ch), sample_raw<FMT>(w1, 3 * p + ch));
+                            if constexpr (FMT == DMMT_RGB_F32_NORM) {
+                                n[ch] = v;
+                                bad |= !(fabsf(lo_of(v)) <= 1024.0f) | !(fabsf(hi_of(v)) <= 1024.0f);
+                            } else {
+                                n[ch] = fma2(v, rhi, mul2(v, rlo));  // v / max, proven per plan (make_k1_consts)
+                            }
+                        }
+                        // color.rs:75-100, products that feed additions as mulx, sums and final scale packed
+                        constexpr float kShift = 128.0f / 255.0f;
+                        yy[q] = mul2(add2(add2(add2(mulx(n[0], 0.299f, nz), mulx(n[1], 0.587f, nz)), mulx(n[2], 0.114f, nz)),
+                                          bc(-kShift)),
+                                     bc(255.0f));
+                        if constexpr (FMT == DMMT_RGB_F32_NORM) {
+                            cb[q] = mul2(add2(add2(mulx(n[0], -0.1687f, nz), mulx(n[1], -0.3312f, nz)), mulx(n[2], 0.5f, nz)),
+                                         bc(255.0f));
+                            cr[q] = mul2(add2(add2(mulx(n[0], 0.5f, nz), mulx(n[1], -0.4186f, nz)), mulx(n[2], -0.0813f, nz)),
+                                         bc(255.0f));
+                        } else {
+                            // x * 0.5 is exact for normalised integer samples, so s + x * 0.5 == fma(x, 0.5, s) bit for bit:
+                            // the two halvings ride on the additions they feed
+                            cb[q] = mul2(fma2(n[2], bc(0.5f), add2(mulx(n[0], -0.1687f, nz), mulx(n[1], -0.3312f, nz))), bc(255.0f));
+                            cr[q] = mul2(add2(fma2(n[0], bc(0.5f), mulx(n[1], -0.4186f, nz)), mulx(n[2], -0.0813f, nz)), bc(255.0f));
+                        }
+                    }
+                    yp[cl * 32] = make_float4(lo_of(yy[0]), hi_of(yy[0]), lo_of(yy[1]), hi_of(yy[1]));
+                    // window (x,y),(x,y+1),(x+1,y),(x+1,y+1), f32 sum from 0, / 4 (subsampling.rs:108-122,231-236)
+                    const float sb = __fadd_rn(__fadd_rn(__fadd_rn(lo_of(cb[0]), hi_of(cb[0])), lo_of(cb[1])), hi_of(cb[1]));
+                    const float sr = __fadd_rn(__fadd_rn(__fadd_rn(lo_of(cr[0]), hi_of(cr[0])), lo_of(cr[1])), hi_of(cr[1]));
+                    cbp[cl * 2] = __fmul_rn(sb, 0.25f);
+                    crp[cl * 2] = __fmul_rn(sr, 0.25f);
+                }
+                yp += 2 * 32, cbp += 64, crp += 64;
+#pragma unroll
+                for (int i = 0; i < NW / 2; i++) w0[i] = w0[i + NW / 2], w1[i] = w1[i + NW / 2];
+            }
         }
         if (bad) {
             if constexpr (FMT == DMMT_RGB_F32_NORM) s_flag = 1;
@@ -813,7 +894,7 @@ __global__ void __launch_bounds__(K1_THREADS, FUSED ? K1_MINB : 5) k1_transform_
         const size_t sblk0 = ((size_t)mrow * a.mcus_x + (size_t)tile_x * MPT) * BPM;
         uint4* out = reinterpret_cast<uint4*>(a.coef + (size_t)img * a.coef_img_stride + sblk0 * 64);
         const int n16 = mcus_here * BPM * 8;
-        for (int i = threadIdx.x; i < n16; i += K1_THREADS) {
+        for (int i = threadIdx.x; i < n16; i += P420_THREADS) {
             const int sl = i >> 3;
             out[i] = s_stage[sl * 8 + ((i & 7) ^ (sl & 7))];
         }
@@ -826,8 +907,7 @@ __global__ void __launch_bounds__(K1_THREADS, FUSED ? K1_MINB : 5) k1_transform_
         // DC for k2_fix_dc.
         uint32_t* s_ctok = reinterpret_cast<uint32_t*>(s_planes) + 96 * 8 * 4;  // second half of the plane storage
         constexpr uint32_t S_CTOK_CAP = sizeof(s_planes) / 4 - 96 * 8 * 4;
-#pragma unroll
-        for (int i = 0; i < 2; i++) reinterpret_cast<uint4*>(s_hist)[i * K1_THREADS + threadIdx.x] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < SH_BINS / 4; i += P420_THREADS) reinterpret_cast<uint4*>(s_hist)[i] = make_uint4(0, 0, 0, 0);
         uint32_t cnt = 0;
         if (active) {
             // DC + one token per non-zero AC (ZRLs ride on it) + EOB unless coefficient 63 is non-zero
@@ -876,7 +956,7 @@ __global__ void __launch_bounds__(K1_THREADS, FUSED ? K1_MINB : 5) k1_transform_
         if (in_smem && fits) {  // compact tile -> one coalesced run (tile_cap is a multiple of 8 words)
             uint4* dst = reinterpret_cast<uint4*>(g_tok);
             const uint4* src = reinterpret_cast<const uint4*>(s_ctok);
-            for (uint32_t i = threadIdx.x; i < (total + 3) / 4; i += K1_THREADS) dst[i] = src[i];
+            for (uint32_t i = threadIdx.x; i < (total + 3) / 4; i += P420_THREADS) dst[i] = src[i];
         }
         if (threadIdx.x == 0) {
             a.fo.ntok[(size_t)img * a.fo.tiles + tile] = fits ? total : 0u;
@@ -886,15 +966,17 @@ __global__ void __launch_bounds__(K1_THREADS, FUSED ? K1_MINB : 5) k1_transform_
             ld[0] = s_dc[lm + 3], ld[1] = s_dc[lm + 4], ld[2] = s_dc[lm + 5], ld[3] = 0;
         }
         unsigned int* gh = a.hist + (size_t)img * 1024;
-#pragma unroll
-        for (int i = 0; i < 2; i++) {  // 4 bins per 128-bit load; most bins of a tile are empty
-            const int q4 = i * K1_THREADS + threadIdx.x;
+        for (int q4 = threadIdx.x; q4 < SH_BINS / 4; q4 += P420_THREADS) {  // 4 bins per 128-bit load; most bins of a tile are empty
             const uint4 v = reinterpret_cast<const uint4*>(s_hist)[q4];
             if (v.x | v.y | v.z | v.w) {
-                if (v.x) atomicAdd(&gh[4 * q4], v.x);
-                if (v.y) atomicAdd(&gh[4 * q4 + 1], v.y);
-                if (v.z) atomicAdd(&gh[4 * q4 + 2], v.z);
-                if (v.w) atomicAdd(&gh[4 * q4 + 3], v.w);
+                // tile layout -> [4][256] of the image: Y-DC 0.., C-DC 512.., Y-AC 256.., C-AC 768..
+                const int b = 4 * q4;
+                unsigned int* g = gh + (b < SH_CDC ? b : b < SH_YAC ? T_CDC * 256 + (b - SH_CDC)
+                                                   : b < SH_CAC ? T_YAC * 256 + (b - SH_YAC) : T_CAC * 256 + (b - SH_CAC));
+                if (v.x) atomicAdd(g, v.x);
+                if (v.y) atomicAdd(g + 1, v.y);
+                if (v.z) atomicAdd(g + 2, v.z);
+                if (v.w) atomicAdd(g + 3, v.w);
             }
         }
     }
@@ -932,8 +1014,8 @@ cudaError_t launch_fmt(const K1Args& a, dim3 grid, bool dbg, bool exact, cudaStr
             // shared memory is what bounds residency, L1 is barely used (streaming loads): take the largest carve-out
             static const cudaError_t carve = cudaFuncSetAttribute(k1_transform_p420<FMT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
             (void)carve;
-            if (a.fo.tok) k1_transform_p420<FMT, true><<<grid, K1_THREADS, 0, st>>>(a);
-            else k1_transform_p420<FMT, false><<<grid, K1_THREADS, 0, st>>>(a);
+            if (a.fo.tok) k1_transform_p420<FMT, true><<<grid, P420_THREADS, 0, st>>>(a);
+            else k1_transform_p420<FMT, false><<<grid, P420_THREADS, 0, st>>>(a);
             return cudaGetLastError();
         }
     }
