@@ -174,20 +174,22 @@ __device__ __forceinline__ void load_strip_row(const uint8_t* __restrict__ row_b
 // Raw samples of one row of an 8-pixel strip (the P420 kernels): 24 / 48 / 96 bytes, same three
 // cases as load_strip_row.  The strip starts at a multiple of 8 pixels, so it is 8-byte (u8) or
 // 16-byte (u16, f32) aligned whenever the row is.
+// `strip`: first sample of the strip in this row; `navail`: pixels of the row from there on (<= 0: outside);
+// `fast`: the strip is complete and aligned for vector loads (hoisted by the caller).
 template <int FMT>
-__device__ __forceinline__ void load_strip8_row(const uint8_t* __restrict__ row_base, int x0, int W, bool row_valid,
-                                                bool vec_ok, uint32_t (&w)[Px<FMT>::kWords / 2]) {
+__device__ __forceinline__ void load_strip8_row(const uint8_t* __restrict__ strip, int navail, bool row_valid,
+                                                bool fast, uint32_t (&w)[Px<FMT>::kWords / 2]) {
     constexpr int NW = Px<FMT>::kWords / 2;
-    if (row_valid && vec_ok && x0 + 8 <= W) {
+    if (row_valid && fast) {
         if constexpr (FMT == DMMT_RGB_U8) {
-            const uint2* p = reinterpret_cast<const uint2*>(row_base + (size_t)x0 * 3);
+            const uint2* p = reinterpret_cast<const uint2*>(strip);
 #pragma unroll
             for (int i = 0; i < 3; i++) {
                 const uint2 v = __ldg(p + i);
                 w[2 * i] = v.x, w[2 * i + 1] = v.y;
             }
         } else {
-            const uint4* p = reinterpret_cast<const uint4*>(row_base + (size_t)x0 * Px<FMT>::kBytes);
+            const uint4* p = reinterpret_cast<const uint4*>(strip);
 #pragma unroll
             for (int i = 0; i < NW / 4; i++) {
                 const uint4 v = __ldg(p + i);
@@ -198,23 +200,23 @@ __device__ __forceinline__ void load_strip8_row(const uint8_t* __restrict__ row_
     }
 #pragma unroll
     for (int i = 0; i < NW; i++) w[i] = 0u;
-    if (!row_valid || x0 >= W) return;
+    if (!row_valid || navail <= 0) return;
     // ragged edge / unaligned pitch: rare, so a rolled loop over a local array keeps the cold code
     // small (the hot path stays contiguous in the instruction cache)
-    const int nval = min(8, W - x0) * 3;  // samples available
+    const int nval = min(8, navail) * 3;  // samples available
     uint32_t tmp[NW];
 #pragma unroll 1
     for (int i = 0; i < NW; i++) tmp[i] = 0u;
     if constexpr (FMT == DMMT_RGB_U8) {
-        const uint8_t* q = row_base + (size_t)x0 * 3;
+        const uint8_t* q = strip;
 #pragma unroll 1
         for (int i = 0; i < nval; i++) tmp[i >> 2] |= (uint32_t)q[i] << (8 * (i & 3));
     } else if constexpr (FMT == DMMT_RGB_U16) {
-        const uint16_t* q = reinterpret_cast<const uint16_t*>(row_base) + (size_t)x0 * 3;
+        const uint16_t* q = reinterpret_cast<const uint16_t*>(strip);
 #pragma unroll 1
         for (int i = 0; i < nval; i++) tmp[i >> 1] |= (uint32_t)q[i] << (16 * (i & 1));
     } else {
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(row_base) + (size_t)x0 * 3;
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(strip);
 #pragma unroll 1
         for (int i = 0; i < nval; i++) tmp[i] = q[i];
     }
@@ -704,22 +706,30 @@ __device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, 
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         uint32_t mk = __brev(half ? mhi : (mlo & ~1u));  // bit-reversed once: the walk needs one FLO per step
-        while (mk) {
-            const int lz = __clz((int)mk);
-            const int pos = 32 * half + lz;
-            mk &= ~(0x80000000u >> lz);
-            const int run = pos - prev - 1;
-            prev = pos;
-            const int v = sb[pos ^ sw8];  // chunk (pos >> 3) lives at slot (pos >> 3) ^ (slot & 7)
-            int cat;
-            uint32_t bits;
-            k1_cat_bits(v, cat, bits);
-            ok &= cat <= 15;
-            const int sym = ((run & 15) << 4) | (cat & 15);
-            nzrl_total += (uint32_t)(run >> 4);
-            atomicAdd(&h_ac[sym], 1u);
-            if (store) dst[off] = k1_token(tac, sym, run >> 4, bits);
-            ++off;
+        if (mk) {
+            // software-pipelined: the coefficient of the NEXT non-zero position is requested before the current
+            // one is categorised (an exhausted mask gives position 32 -- a harmless read inside the plane storage)
+            int lz = __clz((int)mk);
+            int v = sb[(32 * half + lz) ^ sw8];  // chunk (pos >> 3) lives at slot (pos >> 3) ^ (slot & 7)
+            while (true) {
+                const int pos = 32 * half + lz;
+                mk &= ~(0x80000000u >> lz);
+                const int nlz = __clz((int)mk);
+                const int nv = sb[(32 * half + nlz) ^ sw8];
+                const int run = pos - prev - 1;
+                prev = pos;
+                int cat;
+                uint32_t bits;
+                k1_cat_bits(v, cat, bits);
+                ok &= cat <= 15;
+                const int sym = ((run & 15) << 4) | (cat & 15);
+                nzrl_total += (uint32_t)(run >> 4);
+                atomicAdd(&h_ac[sym], 1u);
+                if (store) dst[off] = k1_token(tac, sym, run >> 4, bits);
+                ++off;
+                if (!mk) break;
+                lz = nlz, v = nv;
+            }
         }
     }
     if (nzrl_total) atomicAdd(&h_ac[0xF0], nzrl_total);
@@ -736,6 +746,15 @@ constexpr int SH_YDC = 0, SH_CDC = 16, SH_YAC = 32, SH_CAC = 288, SH_BINS = 544;
 
 #ifndef K1_MINB
 #define K1_MINB 8
+#endif
+#ifndef K1_PREFETCH
+#define K1_PREFETCH 1
+#endif
+#ifndef K1_MAGIC
+#define K1_MAGIC 0   // bit ch set: channel ch of u8 input is converted with the 2^23 trick instead of I2F
+#endif
+#ifndef K1_HUNROLL
+#define K1_HUNROLL 0
 #endif
 // CTA = 96 threads = 3 warps, every one of them busy in every phase: 8 CTAs (24 warps) per SM at 80 registers.
 template <int FMT, bool FUSED>
@@ -773,14 +792,32 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
         // Rolled on purpose (strips, then the two 4-pixel halves of a strip): the loop body is what stays in
         // the instruction cache; fully unrolled, the kernel's hot code exceeds the 32 KB L1.5 I-cache and a
         // quarter of phase B's cycles were instruction-fetch stalls (profiles/).
+        // A thread keeps its strip column (sx) and walks down the row pairs sy, sy + 3, sy + 6: everything that
+        // depends on the column only is hoisted, the row pointer advances by six rows per strip.
+        const int sx = threadIdx.x & 31;
+        const int navail = a.W - (tile_x * TILE_W + sx * 8);
+        const bool fast = a.vec_ok != 0 && navail >= 8;
+        int y = mrow * 16 + 2 * (int)(threadIdx.x >> 5);
+        const uint8_t* rowp = pix + (size_t)y * pitch + (size_t)(tile_x * TILE_W + sx * 8) * Px<FMT>::kBytes;
+        auto load_rows = [&](const uint8_t* p, int yy, uint32_t (&r0)[NW], uint32_t (&r1)[NW]) {
+            load_strip8_row<FMT>(p, navail, yy < a.H, fast, r0);
+            load_strip8_row<FMT>(p + pitch, navail, yy + 1 < a.H, fast, r1);
+        };
+        // the rows of the next strip are requested before the current strip is converted (integer formats: the
+        // second buffer costs 2 * NW registers, too many for the 96-byte f32 rows)
+        constexpr bool PREFETCH = K1_PREFETCH && FMT != DMMT_RGB_F32_NORM;
+        uint32_t n0[PREFETCH ? NW : 1], n1[PREFETCH ? NW : 1];
+        if constexpr (PREFETCH) load_rows(rowp, y, n0, n1);
 #pragma unroll 1
-        for (int s = (int)threadIdx.x; s < 256; s += P420_THREADS) {
-            const int sx = s & 31, sy = s >> 5;  // sy = row pair of the MCU row (warp-uniform)
-            const int x0 = tile_x * TILE_W + sx * 8;
-            const int y = mrow * 16 + 2 * sy;
+        for (int sy = threadIdx.x >> 5; sy < 8; sy += 3, y += 6, rowp += 6 * pitch) {  // sy = row pair of the MCU row (warp-uniform)
             uint32_t w0[NW], w1[NW];
-            load_strip8_row<FMT>(pix + (size_t)y * pitch, x0, a.W, y < a.H, a.vec_ok != 0, w0);
-            load_strip8_row<FMT>(pix + (size_t)(y + 1) * pitch, x0, a.W, y + 1 < a.H, a.vec_ok != 0, w1);
+            if constexpr (PREFETCH) {
+#pragma unroll
+                for (int i = 0; i < NW; i++) w0[i] = n0[i], w1[i] = n1[i];
+                if (sy + 3 < 8) load_rows(rowp + 6 * pitch, y + 6, n0, n1);
+            } else {
+                load_rows(rowp, y, w0, w1);
+            }
             if constexpr (FMT != DMMT_RGB_F32_NORM) {
                 if (a.check_max) {  // color.rs:62-65 (SIMD-in-word compare)
 #pragma unroll
@@ -795,7 +832,11 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
             float* cbp = reinterpret_cast<float*>(&sCb[sy >> 1][2 * (sx & 1)][sx >> 1]) + (sy & 1);
             float* crp = reinterpret_cast<float*>(&sCr[sy >> 1][2 * (sx & 1)][sx >> 1]) + (sy & 1);
             float4* yp = &sY[sy][0][sx];
+#if K1_HUNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
             for (int h = 0; h < 2; h++) {  // pixels 4h .. 4h+3 of the strip = the first NW / 2 words
 #pragma unroll
                 for (int cl = 0; cl < 2; cl++) {  // chunk 2h + cl = 2 pixels x 2 rows
@@ -807,7 +848,17 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
 #pragma unroll
                         for (int ch = 0; ch < 3; ch++) {
                             // (u8 -> f32 stays on I2F: the PRMT 0x4B000000 + FADD2 trick was measured 7 % slower)
-                            const f2 v = pk(sample_raw<FMT>(w0, 3 * p + ch), sample_raw<FMT>(w1, 3 * p + ch));
+                            f2 v;
+                            if (FMT == DMMT_RGB_U8 && ((K1_MAGIC >> ch) & 1)) {
+                                // 0x4B0000vv is 2^23 + v: one PRMT per sample, one packed subtraction per pair -- takes
+                                // these conversions off the quarter-rate I2F pipe
+                                const int i = 3 * p + ch;
+                                v = add2(pk(__uint_as_float(__byte_perm(w0[i >> 2], 0x4B000000u, 0x7440 | (i & 3))),
+                                            __uint_as_float(__byte_perm(w1[i >> 2], 0x4B000000u, 0x7440 | (i & 3)))),
+                                         bc(-8388608.0f));
+                            } else {
+                                v = pk(sample_raw<FMT>(w0, 3 * p + ch), sample_raw<FMT>(w1, 3 * p + ch));
+                            }
                             if constexpr (FMT == DMMT_RGB_F32_NORM) {
                                 n[ch] = v;
                                 bad |= !(fabsf(lo_of(v)) <= 1024.0f) | !(fabsf(hi_of(v)) <= 1024.0f);
