@@ -176,11 +176,29 @@ __device__ __forceinline__ void load_strip_row(const uint8_t* __restrict__ row_b
 // 16-byte (u16, f32) aligned whenever the row is.
 // `strip`: first sample of the strip in this row; `navail`: pixels of the row from there on (<= 0: outside);
 // `fast`: the strip is complete and aligned for vector loads (hoisted by the caller).
-template <int FMT>
+// VEC selects the kernel variant: true = rows 16-byte aligned (vector loads), false = any alignment (word loads +
+// funnel shift).  Two kernels rather than two paths in one: the aligned kernel is sensitive to its instruction
+// footprint (+180 instructions of word path cost it 3 %).
+template <int FMT, bool VEC>
 __device__ __forceinline__ void load_strip8_row(const uint8_t* __restrict__ strip, int navail, bool row_valid,
-                                                bool fast, uint32_t (&w)[Px<FMT>::kWords / 2]) {
+                                                bool fast, bool words_ok, uint32_t (&w)[Px<FMT>::kWords / 2]) {
     constexpr int NW = Px<FMT>::kWords / 2;
-    if (row_valid && fast) {
+    if (!VEC && row_valid && words_ok) {
+        // complete strip at any byte alignment (row pitch not a multiple of 16 bytes: 500, 1366, 1000 ... pixel wide
+        // images): aligned 32-bit loads and one funnel shift per word.  The caller guarantees that the up to three
+        // bytes before and after the strip belong to the image buffer (`words_ok`).
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(strip);
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(addr & ~static_cast<uintptr_t>(3));
+        const uint32_t sh = ((uint32_t)addr & 3u) * 8u;
+        uint32_t d[NW + 1];
+#pragma unroll
+        for (int i = 0; i < NW; i++) d[i] = __ldg(p + i);
+        d[NW] = sh ? __ldg(p + NW) : 0u;
+#pragma unroll
+        for (int i = 0; i < NW; i++) w[i] = __funnelshift_r(d[i], d[i + 1], sh);
+        return;
+    }
+    if (VEC && row_valid && fast) {
         if constexpr (FMT == DMMT_RGB_U8) {
             const uint2* p = reinterpret_cast<const uint2*>(strip);
 #pragma unroll
@@ -757,7 +775,7 @@ constexpr int SH_YDC = 0, SH_CDC = 16, SH_YAC = 32, SH_CAC = 288, SH_BINS = 544;
 #define K1_HUNROLL 0
 #endif
 // CTA = 96 threads = 3 warps, every one of them busy in every phase: 8 CTAs (24 warps) per SM at 80 registers.
-template <int FMT, bool FUSED>
+template <int FMT, bool FUSED, bool VEC>
 __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transform_p420(const __grid_constant__ K1Args a) {
     // planes as ROW-PAIR interleaved float4 = {v(x,2j), v(x,2j+1), v(x+1,2j), v(x+1,2j+1)}:
     //   sY[row pair][16-byte chunk of the strip: 2 columns][8-pixel strip], sC*[row pair][chunk][MCU]
@@ -799,9 +817,15 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
         const bool fast = a.vec_ok != 0 && navail >= 8;
         int y = mrow * 16 + 2 * (int)(threadIdx.x >> 5);
         const uint8_t* rowp = pix + (size_t)y * pitch + (size_t)(tile_x * TILE_W + sx * 8) * Px<FMT>::kBytes;
+        // unaligned rows: word loads may touch up to 3 bytes before / after the strip -- fine when a pixel of the
+        // same image precedes (x0 > 0 or an earlier row; the very first strip only if the image base is aligned)
+        // and follows (another pixel of the row or another row)
+        const bool head0 = sx > 0 || tile_x > 0 || (reinterpret_cast<uintptr_t>(pix) & 3) == 0;
         auto load_rows = [&](const uint8_t* p, int yy, uint32_t (&r0)[NW], uint32_t (&r1)[NW]) {
-            load_strip8_row<FMT>(p, navail, yy < a.H, fast, r0);
-            load_strip8_row<FMT>(p + pitch, navail, yy + 1 < a.H, fast, r1);
+            const bool w0ok = !VEC && navail >= 8 && (head0 || yy > 0) && (navail >= 9 || yy + 1 < a.H);
+            const bool w1ok = !VEC && navail >= 8 && (navail >= 9 || yy + 2 < a.H);
+            load_strip8_row<FMT, VEC>(p, navail, yy < a.H, fast, w0ok, r0);
+            load_strip8_row<FMT, VEC>(p + pitch, navail, yy + 1 < a.H, fast, w1ok, r1);
         };
         // the rows of the next strip are requested before the current strip is converted (integer formats: the
         // second buffer costs 2 * NW registers, too many for the 96-byte f32 rows)
@@ -1063,10 +1087,17 @@ cudaError_t launch_fmt(const K1Args& a, dim3 grid, bool dbg, bool exact, cudaStr
     if constexpr (HR == 2 && VR == 2) {
         if (!dbg && !exact && !a.force_scalar) {
             // shared memory is what bounds residency, L1 is barely used (streaming loads): take the largest carve-out
-            static const cudaError_t carve = cudaFuncSetAttribute(k1_transform_p420<FMT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            static const cudaError_t carve[2] = {
+                cudaFuncSetAttribute(k1_transform_p420<FMT, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
+                cudaFuncSetAttribute(k1_transform_p420<FMT, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)};
             (void)carve;
-            if (a.fo.tok) k1_transform_p420<FMT, true><<<grid, P420_THREADS, 0, st>>>(a);
-            else k1_transform_p420<FMT, false><<<grid, P420_THREADS, 0, st>>>(a);
+            if (a.fo.tok) {
+                if (a.vec_ok) k1_transform_p420<FMT, true, true><<<grid, P420_THREADS, 0, st>>>(a);
+                else k1_transform_p420<FMT, true, false><<<grid, P420_THREADS, 0, st>>>(a);
+            } else {
+                if (a.vec_ok) k1_transform_p420<FMT, false, true><<<grid, P420_THREADS, 0, st>>>(a);
+                else k1_transform_p420<FMT, false, false><<<grid, P420_THREADS, 0, st>>>(a);
+            }
             return cudaGetLastError();
         }
     }
