@@ -36,6 +36,16 @@ static_assert(sizeof(ImgMeta) == sizeof(dmmt_image_meta), "meta layout is part o
 // Table indices
 enum { T_YDC = 0, T_YAC = 1, T_CDC = 2, T_CAC = 3 };
 
+// Symbol field of a TOKEN (and index of K3's shared-memory code LUT).  DC symbols are stored as they are.  An AC
+// symbol (run << 4 | cat) is stored with its low nibble XOR-ed with the run nibble (and with 8 for the chroma
+// table): the LUT entries are 8 bytes, so the bank pair of an entry is its index mod 16, and the frequent symbols
+// of one category (0x01, 0x11, 0x21 ... and their chroma twins) would all sit in the SAME bank pair -- 44 % of K3's
+// shared-memory wavefronts were bank-conflict replays.  The map is an involution per table; histograms, code
+// tables and everything outside the token stream use the plain symbol.
+__host__ __device__ constexpr uint32_t tok_swz(uint32_t table, uint32_t sym) {
+    return (table & 1u) ? sym ^ (((sym >> 4) ^ ((table & 2u) << 2)) & 15u) : sym;
+}
+
 // Encoder LUT entry: (len << 16) | right-aligned code.  len == 0 => symbol absent.
 struct EncTables {
     uint32_t e[4][256];

@@ -698,7 +698,11 @@ __device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, 
                                                     uint32_t* dcpos) {
     const int tdc = comp ? T_CDC : T_YDC, tac = tdc + 1;
     unsigned int* const h_dc = s_hist + (comp ? 16 : 0);     // tile histogram layout: SH_YDC / SH_CDC / SH_YAC / SH_CAC
+    // AC symbols in the bank-swizzled form of tok_swz (dmmt_common.cuh): symp = sym ^ (run & 15) for both tables;
+    // the chroma table's extra "^ 8" lives in tbase, so the walk needs no operation more than the plain symbol did.
+    // The tile histogram is indexed by symp (un-swizzled at the flush).
     unsigned int* const h_ac = s_hist + (comp ? 288 : 32);
+    const uint32_t tbase = ((uint32_t)tac << 8) | (comp ? 8u : 0u);
     bool ok = true;
     {
         const int ps = k == 0 ? slot - 3 : (k < 4 ? slot - 1 : slot - 6);
@@ -740,20 +744,20 @@ __device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, 
                 uint32_t bits;
                 k1_cat_bits(v, cat, bits);
                 ok &= cat <= 15;
-                const int sym = ((run & 15) << 4) | (cat & 15);
+                const int symp = ((run & 15) << 4) | ((cat ^ run) & 15);
                 nzrl_total += (uint32_t)(run >> 4);
-                atomicAdd(&h_ac[sym], 1u);
-                if (store) dst[off] = k1_token(tac, sym, run >> 4, bits);
+                atomicAdd(&h_ac[symp], 1u);
+                if (store) dst[off] = ((uint32_t)symp ^ (tbase + ((uint32_t)(run >> 4) << 10))) | (bits << 16);
                 ++off;
                 if (!mk) break;
                 lz = nlz, v = nv;
             }
         }
     }
-    if (nzrl_total) atomicAdd(&h_ac[0xF0], nzrl_total);
+    if (nzrl_total) atomicAdd(&h_ac[0xFF], nzrl_total);  // ZRL 0xF0
     if (prev != 63) {
         atomicAdd(&h_ac[0], 1u);
-        if (store) dst[off] = k1_token(tac, 0x00, 0, 0u);
+        if (store) dst[off] = tbase;  // EOB 0x00
     }
     return ok;
 }
@@ -1044,14 +1048,20 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
         for (int q4 = threadIdx.x; q4 < SH_BINS / 4; q4 += P420_THREADS) {  // 4 bins per 128-bit load; most bins of a tile are empty
             const uint4 v = reinterpret_cast<const uint4*>(s_hist)[q4];
             if (v.x | v.y | v.z | v.w) {
-                // tile layout -> [4][256] of the image: Y-DC 0.., C-DC 512.., Y-AC 256.., C-AC 768..
+                // tile layout -> [4][256] of the image: Y-DC 0.., C-DC 512.., Y-AC 256.., C-AC 768..  The AC bins are
+                // indexed by symp = sym ^ (run nibble): within four neighbouring bins only the low two bits move, so
+                // the plain symbols are the same aligned group of four, permuted by k & 3 (k = the run nibble)
                 const int b = 4 * q4;
-                unsigned int* g = gh + (b < SH_CDC ? b : b < SH_YAC ? T_CDC * 256 + (b - SH_CDC)
-                                                   : b < SH_CAC ? T_YAC * 256 + (b - SH_YAC) : T_CAC * 256 + (b - SH_CAC));
-                if (v.x) atomicAdd(g, v.x);
-                if (v.y) atomicAdd(g + 1, v.y);
-                if (v.z) atomicAdd(g + 2, v.z);
-                if (v.w) atomicAdd(g + 3, v.w);
+                int g0 = b, k = 0;
+                if (b >= SH_CAC) g0 = T_CAC * 256 + (b - SH_CAC), k = (b - SH_CAC) >> 4;
+                else if (b >= SH_YAC) g0 = T_YAC * 256 + (b - SH_YAC), k = (b - SH_YAC) >> 4;
+                else if (b >= SH_CDC) g0 = T_CDC * 256 + (b - SH_CDC);
+                unsigned int* g = gh + (g0 ^ (k & 12));
+                k &= 3;
+                if (v.x) atomicAdd(g + k, v.x);
+                if (v.y) atomicAdd(g + (1 ^ k), v.y);
+                if (v.z) atomicAdd(g + (2 ^ k), v.z);
+                if (v.w) atomicAdd(g + (3 ^ k), v.w);
             }
         }
     }

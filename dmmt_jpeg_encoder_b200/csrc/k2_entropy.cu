@@ -20,7 +20,8 @@
 // divergent walk happens once per image and the bit packing is balanced.
 //
 // Token word: bits 0-7 symbol, 8-9 table (T_*), 10-11 number of ZRL (0xF0) codes that precede the
-// symbol (categorize.rs:139-142), 16-31 the category's extra bits.  bits 0-9 index the encoder LUT.
+// symbol (categorize.rs:139-142), 16-31 the category's extra bits.  bits 0-9 index the encoder LUT; the symbol
+// field of AC tokens is bank-swizzled (tok_swz, dmmt_common.cuh).
 #include "dmmt_kernels.h"
 
 namespace dmmt {
@@ -168,14 +169,14 @@ __global__ void __launch_bounds__(EB) k2_tokenize(const K2Args a) {
                 const int sym = ((run & 15) << 4) | (cat & 15);
                 nzrl_total += (uint32_t)(run >> 4);
                 atomicAdd(&s_hist[tac * 256 + sym], 1u);
-                if (fits) tok[off] = make_token(tac, sym, run >> 4, bits);
+                if (fits) tok[off] = make_token(tac, (int)tok_swz((uint32_t)tac, (uint32_t)sym), run >> 4, bits);
                 ++off;
             }
         }
         if (nzrl_total) atomicAdd(&s_hist[tac * 256 + 0xF0], nzrl_total);
         if (prev != 63) {
             atomicAdd(&s_hist[tac * 256], 1u);
-            if (fits) tok[off] = make_token(tac, 0x00, 0, 0u);
+            if (fits) tok[off] = make_token(tac, (int)tok_swz((uint32_t)tac, 0x00u), 0, 0u);
         }
         if (!ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_RANGE);
     }
@@ -597,7 +598,7 @@ __device__ __forceinline__ uint32_t emit_step(const uint32_t (&t)[K3_RUN], int n
                 if (ln[i]) {
                     uint32_t nz = (t[i] >> 10) & 3u;
                     if (nz) {  // ZRL codes first (categorize.rs:139-142); symbol 0xF0 has category 0
-                        const uint2 z = s_enc2[(t[i] & 0x300u) | 0xF0u];
+                        const uint2 z = s_enc2[(t[i] & 0x300u) | tok_swz(t[i] >> 8 & 3u, 0xF0u)];
                         for (; nz; --nz) sink.put(z.x & 0xFFFFu, (int)z.y);
                     }
                     sink.put(val[i], (int)ln[i]);
@@ -749,13 +750,14 @@ __global__ void __launch_bounds__(EB, 4) k3_pack(const K3Args a) {
     for (int i = tid; i < 1024; i += EB) {
         const uint32_t e = a.enc[cur_img].e[i >> 8][i & 255];
         const uint32_t len = e >> 16, cat = (uint32_t)i & 15u;
-        s_enc2[i] = len ? make_uint2((e & 0xFFFFu) << cat, len + cat)
-                        : make_uint2((uint32_t)i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
+        s_enc2[(i & 0x300) | tok_swz((uint32_t)i >> 8, (uint32_t)i & 255u)] =
+            len ? make_uint2((e & 0xFFFFu) << cat, len + cat)
+                : make_uint2((uint32_t)i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
     }
     uint32_t ntok_cur = k3_load_ntok(a, cur_img, item % a.n_chunks, wid);
     __syncthreads();
     int err = s_err_next;
-    uint32_t zl_y = s_enc2[T_YAC * 256 + 0xF0].y, zl_c = s_enc2[T_CAC * 256 + 0xF0].y;
+    uint32_t zl_y = s_enc2[T_YAC * 256 + tok_swz(T_YAC, 0xF0u)].y, zl_c = s_enc2[T_CAC * 256 + tok_swz(T_CAC, 0xF0u)].y;
     const unsigned long long seed = a.seed_src ? (*a.seed_src & 7ull) : a.seed_bits;
 
     bool pend = false;  // the previous chunk is packed in s_wbuf[buf ^ 1] and waits for its position
@@ -880,15 +882,16 @@ __global__ void __launch_bounds__(EB, 4) k3_pack(const K3Args a) {
             for (int k = 0; k < 1024 / EB; k++) {
                 const uint32_t i = (uint32_t)tid + k * EB, e = e_next[k];
                 const uint32_t len = e >> 16, cat = i & 15u;
-                s_enc2[i] = len ? make_uint2((e & 0xFFFFu) << cat, len + cat)
-                                : make_uint2(i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
+                s_enc2[(i & 0x300u) | tok_swz(i >> 8, i & 255u)] =
+                    len ? make_uint2((e & 0xFFFFu) << cat, len + cat)
+                        : make_uint2(i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
             }
         }
         __syncthreads();  // (c) table, error flag ready; s_wsum / s_next / s_prefix may be rewritten
         if (nimg != cur_img) {
             cur_img = nimg;
             err = s_err_next;
-            zl_y = s_enc2[T_YAC * 256 + 0xF0].y, zl_c = s_enc2[T_CAC * 256 + 0xF0].y;
+            zl_y = s_enc2[T_YAC * 256 + tok_swz(T_YAC, 0xF0u)].y, zl_c = s_enc2[T_CAC * 256 + tok_swz(T_CAC, 0xF0u)].y;
         }
         item = nitem;
         ntok_cur = ntok_next;
