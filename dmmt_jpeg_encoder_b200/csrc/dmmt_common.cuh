@@ -46,6 +46,15 @@ __host__ __device__ constexpr uint32_t tok_swz(uint32_t table, uint32_t sym) {
     return (table & 1u) ? sym ^ (((sym >> 4) ^ ((table & 2u) << 2)) & 15u) : sym;
 }
 
+constexpr bool tok_swz_is_an_involution() {
+    for (uint32_t t = 0; t < 4; t++)
+        for (uint32_t s = 0; s < 256; s++)
+            if (tok_swz(t, tok_swz(t, s)) != s || (tok_swz(t, s) >> 4) != (s >> 4) || tok_swz(t, s) > 255u) return false;
+    return tok_swz(T_YDC, 0x0B) == 0x0B && tok_swz(T_YAC, 0xF0) == 0xFF && tok_swz(T_CAC, 0xF0) == 0xF7 &&
+           tok_swz(T_CAC, 0x00) == 0x08 && tok_swz(T_YAC, 0x21) == 0x23;
+}
+static_assert(tok_swz_is_an_involution(), "tok_swz must be a bijection per table that keeps the run nibble");
+
 // Encoder LUT entry: (len << 16) | right-aligned code.  len == 0 => symbol absent.
 struct EncTables {
     uint32_t e[4][256];

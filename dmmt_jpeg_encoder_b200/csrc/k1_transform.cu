@@ -12,6 +12,10 @@
 // __fsub_rn/__fdiv_rn) in the reference's operation order, so nothing contracts to FMA and the
 // coefficients are bit-identical to the CPU path (the file is also compiled with -fmad=false).
 //
+// Two kernel families.  k1_transform_p420<FMT, FUSED, VEC> (4:2:0 with the proven fast divisions; the path
+// bench.py measures) is described at its definition below: 96-thread CTAs, 8-pixel strips, packed FP32, fused
+// tokeniser.  The generic kernel k1_transform<HR, VR, FMT, DBG, EXACT> (4:4:4, 4:2:2, debug fetches, exact
+// divisions) maps like this:
 // Mapping (B200): one CTA = 128 threads = one tile of 256 x (8*VR) pixels of one MCU row.
 //   phase A: thread = one 16 x VR pixel strip.  128-bit loads of the interleaved samples (scalar,
 //            bounds-checked loads at ragged edges / unaligned pitches), colour conversion and the
@@ -659,7 +663,7 @@ __device__ __forceinline__ bool p420_block_coefs(const K1Args& a, int u, int mcu
                    pk(d[56 + 2 * kp], d[56 + 2 * kp + 1]), nz, [&](int r, f2 v, float S) { D[r][kp] = mul2(v, bc(S)); });
 
     // quantise: x = fma(d, rq_hi, d * rq_lo), round half away from zero, saturate (see quantize<>).
-    // `comp` is warp-uniform (warps 0-1 luma, warp 2 chroma), so the table is selected by a uniform
+    // `comp` is warp-uniform (warps 0 and 1 luma, warp 2 chroma), so the table is selected by a uniform
     // branch and its entries become uniform-register operands.
     bool exact = false;
     if constexpr (FMT == DMMT_RGB_F32_NORM) exact = *s_flag_p != 0;
