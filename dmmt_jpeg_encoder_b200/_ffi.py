@@ -66,6 +66,10 @@ SIGNATURES = {
     "dmmt_free": (None, [_VP]),
     "dmmt_strerror": (C.c_char_p, [C.c_int]),
     "dmmt_last_cuda_error": (C.c_char_p, []),
+    "dmmt_ppm_parse": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16),
+                                 C.POINTER(C.c_uint16), C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(C.c_size_t),
+                                 C.POINTER(C.c_int)]),
+    "dmmt_ppm_strerror": (C.c_char_p, [C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
     "dmmt_plan_create": (C.c_int, [_VP, C.c_uint16, C.c_uint16, C.c_int, C.c_uint16, C.POINTER(Options), C.c_int, _PVP]),
     "dmmt_plan_destroy": (None, [_VP]),
     "dmmt_plan_pixel_bytes": (C.c_size_t, [_VP]),

@@ -13,6 +13,7 @@
 
 #include "dmmt_internal.h"
 #include "dmmt_qtables.h"
+#include "ppm_parse.hpp"
 
 using namespace dmmt;
 
@@ -46,6 +47,43 @@ extern "C" const char* dmmt_strerror(int code) {
 }
 
 extern "C" void dmmt_free(void* p) { free(p); }
+
+// ---- host ingest (ppm_parse.hpp): no device involved
+extern "C" int dmmt_ppm_parse(const char* text, size_t len, int threads, uint16_t* width, uint16_t* height,
+                              uint16_t* max_value, uint16_t** samples, size_t* n_samples, int* detail) {
+    if (!text || !width || !height || !max_value || !samples || !n_samples) return DMMT_E_INVALID;
+    *samples = nullptr, *n_samples = 0;
+    dmmt_ppm::Result r;
+    try {
+        r = dmmt_ppm::parse(text, len, threads > 1 ? (unsigned)threads : 1u);
+    } catch (const std::bad_alloc&) {
+        return DMMT_E_NOMEM;
+    } catch (...) {
+        return DMMT_E_INVALID;
+    }
+    if (detail) *detail = r.detail;
+    *width = r.width, *height = r.height, *max_value = r.max_value;
+    if (r.status != dmmt_ppm::OK) return (int)r.status;
+    *n_samples = r.samples.size();
+    *samples = r.samples.release();  // malloc'd by the tokenizer: dmmt_free releases it
+    return DMMT_OK;
+}
+
+extern "C" const char* dmmt_ppm_strerror(int status, int detail, char* buf, size_t cap) {
+    if (!buf || !cap) return buf;
+    static const char* const kTok[5] = {"P3 Header", "Width Header", "Height Header", "Max Value Header", "Color Component Value"};
+    const char* tok = kTok[detail >= 0 && detail < 5 ? detail : 4];
+    switch (status) {
+        case DMMT_OK: snprintf(buf, cap, "ok"); break;
+        case DMMT_PPM_MISSING_TOKEN: snprintf(buf, cap, "Expected token '%s' not found in PPM file", tok); break;
+        case DMMT_PPM_BAD_TOKEN: snprintf(buf, cap, "Parsing of token '%s' failed", tok); break;
+        case DMMT_PPM_INCOMPLETE_PIXEL: snprintf(buf, cap, "Incomplete pixel parsed. Expected 3 components, but got %d.", detail); break;
+        case DMMT_PPM_SIZE_MISMATCH: snprintf(buf, cap, "Nubmer of pixels do not match the size, provided in header"); break;
+        case DMMT_PPM_SAMPLE_ABOVE_MAX: snprintf(buf, cap, "color component exceeds the max value (color.rs:62-65)"); break;
+        default: snprintf(buf, cap, "%s", dmmt_strerror(status)); break;
+    }
+    return buf;
+}
 
 extern "C" int dmmt_host_alloc(size_t bytes, void** out) {
     if (!out) return DMMT_E_INVALID;

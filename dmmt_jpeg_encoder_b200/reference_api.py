@@ -200,6 +200,38 @@ class PPMImageReader:
         return Image(width, height, samples=vals.astype(dt).reshape(height, width, 3), max_value=max_value)
 
 
+def parse_ppm_native(data, threads: int = 1):
+    """The library's host-side P3 tokenizer (dmmt_ppm_parse, csrc/ppm_parse.hpp: needs no GPU) ->
+    (status, detail, width, height, max_value, samples as a uint16 array).  status 0 = OK, 1..5 = DMMT_PPM_*."""
+    import ctypes as C
+
+    from . import _ffi as F
+
+    if isinstance(data, str):
+        data = data.encode()
+    L = F.lib()
+    w, h, m = C.c_uint16(), C.c_uint16(), C.c_uint16()
+    ptr, n, detail = C.POINTER(C.c_uint16)(), C.c_size_t(), C.c_int()
+    st = L.dmmt_ppm_parse(data, len(data), threads, C.byref(w), C.byref(h), C.byref(m), C.byref(ptr), C.byref(n),
+                          C.byref(detail))
+    if st < 0:
+        raise F.DmmtError(st, "dmmt_ppm_parse")
+    samples = np.empty(0, np.uint16)
+    if st == 0:
+        samples = np.ctypeslib.as_array(ptr, shape=(n.value,)).copy() if n.value else samples
+        L.dmmt_free(ptr)
+    return st, detail.value, w.value, h.value, m.value, samples
+
+
+def ppm_error_text(status: int, detail: int) -> str:
+    import ctypes as C
+
+    from . import _ffi as F
+
+    buf = C.create_string_buffer(256)
+    return F.lib().dmmt_ppm_strerror(status, detail, buf, 256).decode()
+
+
 # ----------------------------------------------------------------------------------- the writer
 @dataclass
 class JpegTransformationOptions:

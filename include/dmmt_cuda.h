@@ -262,6 +262,24 @@ int dmmt_shard_launch_count_bytes(dmmt_shard *, const int32_t *d_all_tail2, cons
 int dmmt_shard_launch_stuff_into(dmmt_shard *, const int64_t *d_all_bit_offsets, int rank, int world, uint8_t *d_file,
                                  size_t file_capacity, const int64_t *d_byte_offset, int64_t *d_result2);
 
+/* ---- host ingest: ASCII P3 reader (replaces PPMImageReader::read_image, src/image/reader/ppm.rs:9-251) ----
+ * Pure host code (no device needed): tokenises `len` bytes of a P3 file with the reference's rules (`#` comments
+ * anywhere, Rust's ASCII whitespace set, every number a u16) and returns the raw samples (interleaved R,G,B u16,
+ * malloc'd, release with dmmt_free) -- feed them to dmmt_encode as DMMT_RGB_U16 with *max_value; the device performs
+ * the reader's `v as f32 / max as f32` (ppm.rs:153-157, color.rs:45-53).  `threads` > 1 parses a comment-free sample
+ * section in parallel (the CLI's -t/--threads, src/cli.rs:104-109).  Returns DMMT_OK or one of DMMT_PPM_* (> 0) with
+ * *detail = the header token index 0..3 (P3, width, height, max value; 4 = "Color Component Value") for
+ * MISSING_TOKEN / BAD_TOKEN and `n % 3` for INCOMPLETE_PIXEL; the texts of src/error.rs are dmmt_ppm_strerror's. */
+#define DMMT_PPM_MISSING_TOKEN 1    /* Error::PPMFileDoesNotContainRequiredToken (error.rs:6) */
+#define DMMT_PPM_BAD_TOKEN 2        /* Error::ParsingOfTokenFailed (error.rs:8) */
+#define DMMT_PPM_INCOMPLETE_PIXEL 3 /* Error::IncompletePixelParsed (error.rs:10) */
+#define DMMT_PPM_SIZE_MISMATCH 4    /* Error::MismatchOfSizeBetweenHeaderAndValues (error.rs:12) */
+#define DMMT_PPM_SAMPLE_ABOVE_MAX 5 /* the reference panics (color.rs:62-65) */
+int dmmt_ppm_parse(const char *text, size_t len, int threads, uint16_t *width, uint16_t *height, uint16_t *max_value,
+                   uint16_t **samples, size_t *n_samples, int *detail);
+/* Display text of the reader error (status, detail) into buf (NUL-terminated, truncated to cap); returns buf. */
+const char *dmmt_ppm_strerror(int status, int detail, char *buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,6 +108,116 @@ def test_ppm_reader_agrees_with_oracle_parser_on_fixtures():
         np.testing.assert_array_equal(im.samples, s)
 
 
+# ------------------------------------------ native P3 tokenizer (csrc/ppm_parse.hpp, dmmt_ppm_parse)
+def _native(text, threads=1):
+    import dmmt_jpeg_encoder_b200.reference_api as R
+
+    return R.parse_ppm_native(text, threads)
+
+
+def _expect_from_python_reader(text):
+    """(status, detail, samples) the native tokenizer must produce, derived from the Python mirror of ppm.rs."""
+    import dmmt_jpeg_encoder_b200.reference_api as R
+
+    names = [R.P3_HEADER_TOKEN_NAME, R.WIDTH_HEADER_TOKEN_NAME, R.HEIGHT_HEADER_TOKEN_NAME,
+             R.MAX_VALUE_HEADER_TOKEN_NAME, R.COLOR_COMPONENT_VALUE_TOKEN_NAME]
+    try:
+        im = _read(text)
+    except R.PPMFileDoesNotContainRequiredToken as e:
+        return 1, [n in str(e) for n in names].index(True), None
+    except R.ParsingOfTokenFailed as e:
+        return 2, [n in str(e) for n in names].index(True), None
+    except R.IncompletePixelParsed as e:
+        return 3, int(str(e).split("got ")[1].rstrip(".")), None
+    except R.MismatchOfSizeBetweenHeaderAndValues:
+        return 4, 0, None
+    except R.ReferencePanic:
+        return 5, 0, None
+    return 0, 0, np.asarray(im.samples).reshape(-1).astype(np.uint16)
+
+
+def test_native_ppm_tokenizer_known_cases_and_error_texts():
+    import dmmt_jpeg_encoder_b200.reference_api as R
+
+    st, det, w, h, m, s = _native("P3\n# a comment\n2 2\n255\n255 0 0  0 255 0\n0 0 255 # trailing\n 10 20 30\n")
+    assert (st, w, h, m) == (0, 2, 2, 255) and s.tolist() == [255, 0, 0, 0, 255, 0, 0, 0, 255, 10, 20, 30]
+    assert _native("P3 1 1 255 1#x\n2 3 4")[5].tolist() == [12, 3, 4]          # comment inside a token
+    assert _native("P3 1 1 65535 +5 007 65535")[5].tolist() == [5, 7, 65535]   # '+', leading zeros
+    assert _native("P3 1 1 65535 0000000012 3 4")[5].tolist() == [12, 3, 4]    # more than five digits
+    cases = {"P6 1 1 255 0 0 0": "Expected token 'P3 Header' not found in PPM file",
+             "": "Expected token 'P3 Header' not found in PPM file",
+             "P3 4": "Expected token 'Height Header' not found in PPM file",
+             "P3 x 1 255 0 0 0": "Parsing of token 'Width Header' failed",
+             "P3 1 1 255 0 0 70000": "Parsing of token 'Color Component Value' failed",
+             "P3 1 1 255 0 -1 0": "Parsing of token 'Color Component Value' failed",
+             "P3 1 1 255 0 1\x0b2 0": "Parsing of token 'Color Component Value' failed",   # \x0B is no whitespace
+             "P3 1 1 255 0 + 0": "Parsing of token 'Color Component Value' failed",
+             "P3 1 1 255 0 0 0 9 9": "Incomplete pixel parsed. Expected 3 components, but got 2.",
+             "P3 2 1 255 0 0 0": "Nubmer of pixels do not match the size, provided in header"}
+    for text, msg in cases.items():
+        st, det = _native(text)[:2]
+        assert st > 0 and R.ppm_error_text(st, det) == msg, (text, st, det)
+    assert _native("P3 1 1 15 0 16 0")[0] == 5   # the reference panics (color.rs:62-65)
+
+
+def test_native_ppm_tokenizer_fuzz_against_the_python_reader():
+    """Random token soups (all separators, comments inside and between tokens, '+', long and overflowing numbers,
+    stray bytes) of lengths that cross the 64-byte blocks of the fast path: same samples / same error."""
+    rng = np.random.default_rng(20261018)
+    seps = [" ", "\n", "\t", "\r", "\x0c", "  ", " \n", "\r\n"]
+    for case in range(400):
+        n = int(rng.integers(0, 80)) * 3
+        w = max(1, n // 3)
+        mx = int(rng.choice([255, 65535, 1023]))
+        toks = [str(int(v)) for v in rng.integers(0, mx + 1, n)]
+        flavour = case % 8
+        for i in range(len(toks)):
+            r = rng.random()
+            if flavour >= 2 and r < 0.03:
+                toks[i] = "+" + toks[i]
+            elif flavour >= 2 and r < 0.06:
+                toks[i] = "0" * int(rng.integers(1, 7)) + toks[i]
+            elif flavour >= 4 and r < 0.09 and len(toks[i]) > 1:
+                toks[i] = toks[i][0] + "#c " + str(i) + "\n" + toks[i][1:]      # comment inside the token
+            elif flavour >= 6 and r < 0.10:
+                toks[i] = rng.choice(["70000", "65536", "1x", "-1", "1\x0b", "+", "99999999999"])
+        text = f"P3 {w} 1 {mx}" + rng.choice(seps)
+        for t in toks:
+            text += t + (rng.choice(seps) if rng.random() < 0.9 else " # note\n")
+        if flavour == 1 and n:
+            text = text.rstrip()                                                   # number ends the buffer
+        if flavour == 3:
+            text += " 7"                                                           # incomplete pixel / mismatch
+        est, edet, esam = _expect_from_python_reader(text)
+        for threads in (1, 3):
+            st, det, gw, gh, gm, s = _native(text, threads)
+            assert (st, det) == (est, edet), (case, text[:200], st, det, est, edet)
+            if st == 0:
+                np.testing.assert_array_equal(s, esam)
+
+
+def test_native_ppm_tokenizer_large_file_threads_agree():
+    """A 2.4 MB comment-free file takes the multi-threaded path: every thread count gives the same samples; one bad
+    token anywhere fails the parse; a '#' anywhere falls back to one thread and still agrees."""
+    rng = np.random.default_rng(7)
+    w, h = 640, 320
+    px = rng.integers(0, 65536, w * h * 3)
+    body = "".join(f"{v}{' ' if (i + 1) % 17 else chr(10)}" for i, v in enumerate(px.tolist()))
+    text = f"P3\n{w} {h}\n65535\n" + body
+    assert len(text) > (1 << 20)
+    ref = None
+    for threads in (1, 2, 5, 8, 64, 1000):
+        st, det, gw, gh, gm, s = _native(text, threads)
+        assert (st, gw, gh, gm) == (0, w, h, 65535)
+        np.testing.assert_array_equal(s, px.astype(np.uint16))
+    cut = len(text) * 3 // 4
+    cut = text.index(" ", cut)
+    bad = text[:cut] + " 65536" + text[cut:]
+    assert _native(bad, 8)[:2] == (2, 4) and _native(bad, 1)[:2] == (2, 4)
+    commented = text[:cut] + " # a comment 1 2 3\n" + text[cut:]
+    np.testing.assert_array_equal(_native(commented, 8)[5], px.astype(np.uint16))
+
+
 # ------------------------------------------------------------------------------------------ CLI
 def test_cli_defaults_and_aliases():
     from dmmt_jpeg_encoder_b200 import ChromaSubsamplingPreset, CLIParser, QuantizationTablePreset
