@@ -338,6 +338,33 @@ def test_plan_batch_of_images(D, ctx, O, pname):
     plan.close()
 
 
+@pytest.mark.parametrize("fmt_name,w,h", [("u8", 151, 33), ("u8", 1366, 20), ("u16", 151, 33), ("u16", 257, 17),
+                                          ("f32", 151, 33), ("f32", 34, 40)])
+def test_plan_batch_unaligned_rows_all_formats(D, ctx, O, fmt_name, w, h):
+    """Rows that are not 16-byte aligned (and image bases that are not either) take K1's word-load kernel
+    (k1_transform_p420<FMT, FUSED, VEC = false>: aligned 32-bit loads + funnel shift): every byte alignment of a
+    strip, the first strip of an unaligned image base, the last rows / last strip of the last image."""
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    n = 5
+    rng = np.random.default_rng(w * 1000 + h)
+    if fmt_name == "u8":
+        px, mx, fmt = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8), 255, F.FMT_U8
+        want = [O.encode(px[i], 255, O.P420).jpeg for i in range(n)]
+    elif fmt_name == "u16":
+        px, mx, fmt = rng.integers(0, 1024, (n, h, w, 3)).astype(np.uint16), 1023, F.FMT_U16
+        want = [O.encode(px[i], 1023, O.P420).jpeg for i in range(n)]
+    else:
+        raw = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+        px, mx, fmt = raw.astype(np.float32) / np.float32(255), 1, F.FMT_F32_NORM
+        want = [O.encode(raw[i], 255, O.P420).jpeg for i in range(n)]
+    plan = D.Plan(ctx, w, h, fmt, mx, D.Options(PRESETS["P420"], 8, 0), n)
+    got = plan.encode_host(px)
+    plan.close()
+    for i in range(n):
+        assert got[i] == want[i], (fmt_name, i)
+
+
 @pytest.mark.parametrize("sub,depth", [(4, 3), (5, 2), (16, 1), (1, 4)])
 def test_pipelined_batch_host_and_device(D, ctx, O, sub, depth):
     from dmmt_jpeg_encoder_b200 import _ffi as F
