@@ -196,6 +196,31 @@ def test_native_ppm_tokenizer_fuzz_against_the_python_reader():
                 np.testing.assert_array_equal(s, esam)
 
 
+def test_python_reader_native_mode_equals_pure_python_mode():
+    """PPMImageReader(native=True) (what convert_ppm_to_jpeg uses) raises the same errors with the same texts and
+    returns the same Image as the pure-Python mirror."""
+    from conftest import FIXTURES, load_fixture
+    from dmmt_jpeg_encoder_b200 import PPMImageReader
+    import dmmt_jpeg_encoder_b200.reference_api as R
+
+    def both(text):
+        out = []
+        for native in (False, True):
+            try:
+                im = PPMImageReader(io.BytesIO(text.encode()), native=native, threads=2).read_image()
+                out.append(("ok", im.width, im.height, im.max_value, im.samples.dtype, im.samples.tolist()))
+            except (R.Error, R.ReferencePanic) as e:
+                out.append((type(e).__name__, str(e)))
+        return out
+
+    texts = ["P6 1 1 255 0 0 0", "P3 4", "P3 x 1 255 0 0 0", "P3 1 1 255 0 0 70000", "P3 1 1 255 0 0 0 9 9",
+             "P3 2 1 255 0 0 0", "P3 1 1 15 0 16 0", "P3 1 1 65535 +5 007 65535", "P3 1 1 255 1#x\n2 3 4", ""]
+    texts += [load_fixture(name)[0] for name in FIXTURES]
+    for text in texts:
+        a, b = both(text if isinstance(text, str) else text.decode())
+        assert a == b, (text[:60], a[:2], b[:2])
+
+
 def test_native_ppm_tokenizer_large_file_threads_agree():
     """A 2.4 MB comment-free file takes the multi-threaded path: every thread count gives the same samples; one bad
     token anywhere fails the parse; a '#' anywhere falls back to one thread and still agrees."""
