@@ -569,11 +569,6 @@ static inline void load_norm_rgb(const void *pixels, int fmt, size_t idx, float 
     }
 }
 
-/* subsampling.rs:286-309 : plane (sw x sh, already subsampled) -> contiguous 8x8 blocks */
-static inline size_t tiled_index(size_t x, size_t y, size_t sw) {
-    return (y / 8) * (sw * 8) + (x / 8) * 64 + (y % 8) * 8 + (x % 8);
-}
-
 static void put(uint8_t **p, const void *src, size_t n) {
     memcpy(*p, src, n);
     *p += n;
@@ -583,6 +578,92 @@ static void put_segment(uint8_t **p, uint8_t marker, const uint8_t *content, siz
     uint8_t hd[4] = {0xFF, marker, (uint8_t)((n + 2) >> 8), (uint8_t)((n + 2) & 0xFF)};
     put(p, hd, 4);
     put(p, content, n);
+}
+
+/* padder.rs:18-38 : the dot at (x, y) of the padded image -- the source dot inside the original
+ * width x height, RGBColorFormat::default() = black (0,0,0) to the right of it and below it. */
+static inline void padded_dot(const void *pixels, int fmt, size_t x, size_t y, size_t width, size_t height,
+                              float maxf, float rgb[3]) {
+    rgb[0] = rgb[1] = rgb[2] = 0.0f;
+    if (x < width && y < height) load_norm_rgb(pixels, fmt, y * width + x, maxf, rgb);
+}
+
+/* padder.rs:12-42 PaddedImage::new(image, pad_nearest_width, pad_nearest_height) on normalised f32 dots.
+ * out (may be NULL to query the size) receives padded_w * padded_h RGB triples; returns their number. */
+size_t orc_pad_image(const float *rgb, int width, int height, int nearest_w, int nearest_h, float *out,
+                     int *padded_w, int *padded_h) {
+    const size_t pw = ((size_t)width + (size_t)nearest_w - 1) / (size_t)nearest_w * (size_t)nearest_w; /* :13 */
+    const size_t ph = ((size_t)height + (size_t)nearest_h - 1) / (size_t)nearest_h * (size_t)nearest_h; /* :14 */
+    if (padded_w) *padded_w = (int)pw;
+    if (padded_h) *padded_h = (int)ph;
+    if (out)
+        for (size_t y = 0; y < ph; y++)
+            for (size_t x = 0; x < pw; x++)
+                padded_dot(rgb, ORC_FMT_F32_NORM, x, y, (size_t)width, (size_t)height, 1.0f, out + 3 * (y * pw + x));
+    return pw * ph;
+}
+
+/* subsampling.rs:206-236 ChannelColumnView::nth on row `sy`, column `sx` of the subsampled view
+ * (row_index = sy * vr, column_index = sx * hr): Skip = the dot itself; Average = rect() -- x outer,
+ * y inner, clamped to the last column / row (:108-122) -- summed left to right from 0 and divided by
+ * the element count (:231-236).  Returns -1 for the reference's `None` (past the edge). */
+static inline int subsample_value(const float *plane, size_t w, size_t h, int hr, int vr, int average, size_t sx,
+                                  size_t sy, float *out) {
+    const size_t col = sx * (size_t)hr, row = sy * (size_t)vr;
+    if (row >= h || col >= w) return -1; /* :179-181, :213-215 */
+    if (!average) {
+        *out = plane[row * w + col];
+        return 0;
+    }
+    float sum = 0.0f;
+    for (int dx = 0; dx < hr; dx++) {
+        size_t cx = col + (size_t)dx;
+        if (cx > w - 1) cx = w - 1;
+        for (int dy = 0; dy < vr; dy++) {
+            size_t cy = row + (size_t)dy;
+            if (cy > h - 1) cy = h - 1;
+            sum = sum + plane[cy * w + cx];
+        }
+    }
+    *out = sum / (float)(hr * vr);
+    return 0;
+}
+int orc_subsample_value(const float *plane, int w, int h, int hr, int vr, int average, int sx, int sy,
+                        float *out) {
+    return subsample_value(plane, (size_t)w, (size_t)h, hr, vr, average, (size_t)sx, (size_t)sy, out);
+}
+
+/* subsampling.rs:136-140,150-166,286-309 subsample_to_square_structure(square): every row / column
+ * of the subsampled view goes to result[square_row * (row_length * square) + square_col * square^2 +
+ * y * square + x].  out holds (w / hr) * (h / vr) items; returns that number. */
+size_t orc_subsample_retile(const float *plane, int w, int h, int hr, int vr, int average, int square,
+                            float *out) {
+    const size_t sw = (size_t)(w / hr), sh = (size_t)(h / vr), sq = (size_t)square;
+    /* same mapping, walked square row by square row so that no index needs a division */
+    for (size_t y0 = 0, qrow = 0; y0 < sh; y0 += sq, qrow++)
+        for (size_t y = 0; y < sq && y0 + y < sh; y++)
+            for (size_t x0 = 0, qcol = 0; x0 < sw; x0 += sq, qcol++) {
+                float *dst = out + qrow * (sw * sq) + qcol * (sq * sq) + y * sq;
+                for (size_t x = 0; x < sq && x0 + x < sw; x++)
+                    subsample_value(plane, (size_t)w, (size_t)h, hr, vr, average, x0 + x, y0 + y, dst + x);
+            }
+    return sw * sh;
+}
+
+/* symbol_counting.rs:55-64 : one CategorizedBlock into the DC / AC counters -- the DC symbol is the
+ * category of the (already differenced) DC value, every token counts (zeros << 4) | category.
+ * Returns <0 where categorize.rs panics (-32768). */
+int orc_count_block(int16_t dc_value, const uint8_t *tok_zeros, const int16_t *tok_value, int ntok,
+                    uint64_t *dc_hist, uint64_t *ac_hist) {
+    int cat = orc_categorize(dc_value, NULL);
+    if (cat < 0) return -1;
+    dc_hist[cat]++;
+    for (int t = 0; t < ntok; t++) {
+        int c = orc_categorize(tok_value[t], NULL);
+        if (c < 0) return -1;
+        ac_hist[(tok_zeros[t] << 4) | c]++;
+    }
+    return 0;
 }
 
 int orc_encode(const void *pixels, int fmt, int width, int height, int max_value, int preset,
@@ -607,9 +688,8 @@ int orc_encode(const void *pixels, int fmt, int width, int height, int max_value
     float *pcr = (float *)malloc(sizeof(float) * PW * PH);
     for (size_t y = 0; y < PH; y++)
         for (size_t x = 0; x < PW; x++) {
-            float rgb[3] = {0.0f, 0.0f, 0.0f}, o[3];
-            if (x < (size_t)width && y < (size_t)height)
-                load_norm_rgb(pixels, fmt, y * (size_t)width + x, maxf, rgb);
+            float rgb[3], o[3];
+            padded_dot(pixels, fmt, x, y, (size_t)width, (size_t)height, maxf, rgb);
             orc_rgb_to_ycbcr(rgb, o);
             py[y * PW + x] = o[0];
             pcb[y * PW + x] = o[1];
@@ -620,34 +700,11 @@ int orc_encode(const void *pixels, int fmt, int width, int height, int max_value
     float *ty = (float *)malloc(sizeof(float) * ybl * 64);
     float *tcb = (float *)malloc(sizeof(float) * cbl * 64);
     float *tcr = (float *)malloc(sizeof(float) * cbl * 64);
-    for (size_t y = 0; y < PH; y++)
-        for (size_t x = 0; x < PW; x++) ty[tiled_index(x, y, PW)] = py[y * PW + x];
-    for (int ch = 0; ch < 2; ch++) {
-        const float *src = ch ? pcr : pcb;
-        float *dst = ch ? tcr : tcb;
-        for (size_t y = 0; y < chh; y++)
-            for (size_t x = 0; x < cw; x++) {
-                float v;
-                if (preset == ORC_P444) {
-                    v = src[y * PW + x]; /* SubsamplingMethod::Skip */
-                } else {
-                    /* rect(): x outer, y inner, clamped to the last column/row (:108-122);
-                     * average(): iter().sum() from 0 then / (len as f32) (:231-236) */
-                    float sum = 0.0f;
-                    for (int dx = 0; dx < hr; dx++) {
-                        size_t cx = x * (size_t)hr + (size_t)dx;
-                        if (cx > PW - 1) cx = PW - 1;
-                        for (int dy = 0; dy < vr; dy++) {
-                            size_t cy = y * (size_t)vr + (size_t)dy;
-                            if (cy > PH - 1) cy = PH - 1;
-                            sum = sum + src[cy * PW + cx];
-                        }
-                    }
-                    v = sum / (float)(hr * vr);
-                }
-                dst[tiled_index(x, y, cw)] = v;
-            }
-    }
+    /* luma: SubsamplingConfig 1x1 / Skip (transformer.rs:87-100); chroma: the preset's rates,
+     * Average unless P444 (subsampling.rs:48-54) */
+    orc_subsample_retile(py, pw, ph, 1, 1, 0, 8, ty);
+    orc_subsample_retile(pcb, pw, ph, hr, vr, preset != ORC_P444, 8, tcb);
+    orc_subsample_retile(pcr, pw, ph, hr, vr, preset != ORC_P444, 8, tcr);
     free(py);
     free(pcb);
     free(pcr);
@@ -707,15 +764,8 @@ int orc_encode(const void *pixels, int fmt, int width, int height, int max_value
             const int16_t *blk = stream + 64 * s;
             int16_t diff = (int16_t)(blk[0] - last_dc[comp]);
             last_dc[comp] = blk[0];
-            int cat = orc_categorize(diff, NULL);
-            if (cat < 0) return -13;
-            hist[tb][cat]++;
             int nt = orc_rle_tokens(blk + 1, 63, tz, tv);
-            for (int t = 0; t < nt; t++) {
-                int c = orc_categorize(tv[t], NULL);
-                if (c < 0) return -13;
-                hist[tb + 1][(tz[t] << 4) | c]++;
-            }
+            if (orc_count_block(diff, tz, tv, nt, hist[tb], hist[tb + 1]) < 0) return -13;
         }
     }
 

@@ -45,6 +45,21 @@ void orc_padded_dims(int w, int h, int preset, int *pw, int *ph);
 /* block_entangler.rs:69-77 : position i of the 2-line buffer -> source index */
 size_t orc_quadfold_index(size_t i, size_t line_length);
 
+/* padder.rs:12-42 : pad normalised RGB dots to multiples of (nearest_w, nearest_h) with black;
+ * out == NULL only reports the size.  Returns the number of dots. */
+size_t orc_pad_image(const float *rgb, int width, int height, int nearest_w, int nearest_h, float *out,
+                     int *padded_w, int *padded_h);
+/* subsampling.rs:206-236 : value (sx, sy) of the subsampled view (average != 0: window mean with
+ * border clamp); -1 = the reference's None */
+int orc_subsample_value(const float *plane, int w, int h, int hr, int vr, int average, int sx, int sy,
+                        float *out);
+/* subsampling.rs:136-140,286-309 : subsample_to_square_structure(square) */
+size_t orc_subsample_retile(const float *plane, int w, int h, int hr, int vr, int average, int square,
+                            float *out);
+/* symbol_counting.rs:55-64 : one categorised block (DC value, AC tokens) into the counters */
+int orc_count_block(int16_t dc_value, const uint8_t *tok_zeros, const int16_t *tok_value, int ntok,
+                    uint64_t *dc_hist, uint64_t *ac_hist);
+
 /* --- Huffman (length_limited.rs, symbol_counting.rs, huffman/encoder.rs) ---------------- */
 /* length_limited.rs:37-134 : package-merge; freqs ascending; returns 0 ok, <0 on the
  * reference's panics (n==0, n > 2^limit). */

@@ -73,6 +73,16 @@ def lib():
                                       C.POINTER(C.c_int)]
         L.orc_quadfold_index.restype = C.c_size_t
         L.orc_quadfold_index.argtypes = [C.c_size_t, C.c_size_t]
+        FP = C.POINTER(C.c_float)
+        L.orc_pad_image.restype = C.c_size_t
+        L.orc_pad_image.argtypes = [FP, C.c_int, C.c_int, C.c_int, C.c_int, FP, C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int)]
+        L.orc_subsample_value.argtypes = [FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, FP]
+        L.orc_subsample_retile.restype = C.c_size_t
+        L.orc_subsample_retile.argtypes = [FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, FP]
+        L.orc_count_block.argtypes = [C.c_int16, C.POINTER(C.c_uint8), C.POINTER(C.c_int16), C.c_int,
+                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.orc_package_merge.argtypes = [C.POINTER(C.c_uint64), C.c_int, C.c_int,
                                         C.POINTER(C.c_int)]
         L.orc_build_table.argtypes = [C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int,
@@ -157,6 +167,54 @@ def padded_dims(w, h, preset):
 
 def quadfold_index(i, line_length):
     return int(lib().orc_quadfold_index(i, line_length))
+
+
+def pad_image(rgb, nearest_w: int, nearest_h: int):
+    """padder.rs:12-42 on normalised f32 dots [H, W, 3] -> padded [pH, pW, 3]."""
+    a = np.ascontiguousarray(rgb, dtype=np.float32)
+    h, w, _ = a.shape
+    pw, ph = C.c_int(), C.c_int()
+    FP = C.POINTER(C.c_float)
+    n = lib().orc_pad_image(a.ctypes.data_as(FP), w, h, nearest_w, nearest_h, None, C.byref(pw), C.byref(ph))
+    out = np.full((ph.value, pw.value, 3), np.nan, np.float32)
+    assert n == pw.value * ph.value
+    lib().orc_pad_image(a.ctypes.data_as(FP), w, h, nearest_w, nearest_h, out.ctypes.data_as(FP), None, None)
+    return out
+
+
+def subsample_value(plane, hr: int, vr: int, average: bool, sx: int, sy: int):
+    """subsampling_iter().nth(sy).nth(sx) of subsampling.rs:169-229; None past the edge."""
+    a = np.ascontiguousarray(plane, dtype=np.float32)
+    h, w = a.shape
+    v = C.c_float()
+    rc = lib().orc_subsample_value(a.ctypes.data_as(C.POINTER(C.c_float)), w, h, hr, vr, int(average), sx, sy,
+                                   C.byref(v))
+    return None if rc < 0 else np.float32(v.value)
+
+
+def subsample_retile(plane, hr: int, vr: int, average: bool, square: int) -> np.ndarray:
+    """Subsampler::subsample_to_square_structure(square) (subsampling.rs:136-140)."""
+    a = np.ascontiguousarray(plane, dtype=np.float32)
+    h, w = a.shape
+    out = np.full((w // hr) * (h // vr), np.nan, np.float32)
+    FP = C.POINTER(C.c_float)
+    n = lib().orc_subsample_retile(a.ctypes.data_as(FP), w, h, hr, vr, int(average), square, out.ctypes.data_as(FP))
+    assert n == out.size
+    return out
+
+
+def count_blocks(blocks):
+    """HuffmanCount::from_iter (symbol_counting.rs:55-74) over [(dc_value, [(zeros, value), ...]), ...]
+    -> (dc_hist[16], ac_hist[256]) as the oracle's own counting loop produces them."""
+    dc = np.zeros(16, np.uint64)
+    ac = np.zeros(256, np.uint64)
+    U64 = C.POINTER(C.c_uint64)
+    for d, toks in blocks:
+        z = (C.c_uint8 * max(1, len(toks)))(*[t[0] for t in toks])
+        v = (C.c_int16 * max(1, len(toks)))(*[t[1] for t in toks])
+        if lib().orc_count_block(d, z, v, len(toks), dc.ctypes.data_as(U64), ac.ctypes.data_as(U64)) < 0:
+            raise ValueError("categorize panics")
+    return dc, ac
 
 
 def package_merge(sorted_freqs, limit):

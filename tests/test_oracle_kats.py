@@ -135,20 +135,100 @@ def test_rle_tokens_kat():
     assert O.rle_tokens([0] * 62 + [5]) == [(15, 0), (15, 0), (15, 0), (14, 5)]
 
 
-# ---- symbol_counting.rs:108-198 (through the whole-path histogram)
-def test_histogram_counts_via_tokens():
+# ---- symbol_counting.rs:108-198 test_count_symbols, through the oracle's own counting code
+# (orc_count_block, the function orc_encode's histogram loop calls) and its frequency sort
+def test_count_symbols_kat():
     blocks = [(30, [(0, 300), (15, 0), (4, 5), (0, 0)]), (0, [(0, 600), (15, 0), (4, 15), (0, 0)]),
               (60, [(0, 100), (15, 0), (2, 7), (0, 0)]), (1, [(0, 900), (15, 0), (0, 1), (0, 0)])]
-    dc, ac = {}, {}
-    for d, toks in blocks:
-        c = O.categorize(d)[0]
-        dc[c] = dc.get(c, 0) + 1
-        for z, v in toks:
-            s = (z << 4) | O.categorize(v)[0]
-            ac[s] = ac.get(s, 0) + 1
-    assert dc == {5: 1, 0: 1, 6: 1, 1: 1}
-    assert ac == {0b00001001: 1, 0b11110000: 4, 0b01000011: 1, 0: 4, 0b00001010: 2, 0b01000100: 1,
-                  0b00000111: 1, 0b00100011: 1, 0b00000001: 1}
+    dc, ac = O.count_blocks(blocks)
+    assert {i: int(c) for i, c in enumerate(dc) if c} == {5: 1, 0: 1, 6: 1, 1: 1}
+    assert {i: int(c) for i, c in enumerate(ac) if c} == {
+        0b00001001: 1, 0b11110000: 4, 0b01000011: 1, 0b00000000: 4, 0b00001010: 2, 0b01000100: 1,
+        0b00000111: 1, 0b00100011: 1, 0b00000001: 1}
+    # to_symbol_frequencies + sort_by_frequency (:25-32, :92-94): ascending symbol, stable by frequency
+    sym, _ = O.build_table(ac)
+    assert sym == [0b00000001, 0b00000111, 0b00001001, 0b00100011, 0b01000011, 0b01000100, 0b00001010,
+                   0b00000000, 0b11110000]
+    with pytest.raises(ValueError):
+        O.count_blocks([(-32768, [])])   # categorize.rs:236-240 panics
+
+
+# ---- subsampling.rs:332-550
+CH1 = np.arange(1, 17, dtype=np.float32).reshape(4, 4)     # TEST_CHANNEL_ONE
+CH2 = np.arange(1, 65, dtype=np.float32).reshape(8, 8)     # TEST_CHANNEL_TWO
+
+
+def test_subsampling_value_kats():
+    assert O.subsample_value(CH1, 1, 1, False, 2, 1) == 7.0      # no_subsampling_test :342-362
+    assert O.subsample_value(CH1, 2, 1, False, 1, 1) == 7.0      # skip_subsampling_test :364-384
+    assert O.subsample_value(CH1, 1, 2, True, 1, 1) == 12.0      # average_subsampling_test :386-406
+    assert O.subsample_value(CH1, 2, 1, True, 2, 2) is None      # out_of_bounds_high :408-424
+    assert O.subsample_value(CH1, 2, 3, True, 1, 1) == 15.5      # repeat_border_test (clamp) :426-446
+    # the summation order of the 2x2 window is (x,y),(x,y+1),(x+1,y),(x+1,y+1) (rect(): x outer, :116-121):
+    # values chosen so that every other association of the four f32 additions rounds differently
+    w = np.array([[1.0, 2.0 ** -24], [2.0 ** -24, 2.0 ** -24]], np.float32)   # (y, x) layout
+    got = O.subsample_value(w, 2, 2, True, 0, 0)
+    s = np.float32(0.0)
+    for x in range(2):
+        for y in range(2):
+            s = np.float32(s + w[y, x])
+    assert got == np.float32(s / np.float32(4.0))
+    other = np.float32(np.float32(np.float32(w[1, 1] + w[1, 0]) + w[0, 1]) + w[0, 0]) / np.float32(4.0)
+    assert got != other
+
+
+def test_square_resorter_kats():
+    assert O.subsample_retile(CH1, 1, 1, False, 4).tolist() == CH1.reshape(-1).tolist()   # :448-466
+    exp_1x1 = [1, 2, 3, 4, 9, 10, 11, 12, 17, 18, 19, 20, 25, 26, 27, 28, 5, 6, 7, 8, 13, 14, 15, 16, 21, 22,
+               23, 24, 29, 30, 31, 32, 33, 34, 35, 36, 41, 42, 43, 44, 49, 50, 51, 52, 57, 58, 59, 60, 37, 38,
+               39, 40, 45, 46, 47, 48, 53, 54, 55, 56, 61, 62, 63, 64]
+    assert O.subsample_retile(CH2, 1, 1, False, 4).tolist() == exp_1x1                       # :468-497
+    exp_2x2 = [1, 3, 5, 7, 17, 19, 21, 23, 33, 35, 37, 39, 49, 51, 53, 55]
+    assert O.subsample_retile(CH2, 2, 2, False, 4).tolist() == exp_2x2                       # :499-523
+    exp_1x2 = [1, 2, 3, 4, 17, 18, 19, 20, 33, 34, 35, 36, 49, 50, 51, 52, 5, 6, 7, 8, 21, 22, 23, 24, 37, 38,
+               39, 40, 53, 54, 55, 56]
+    assert O.subsample_retile(CH2, 1, 2, False, 4).tolist() == exp_1x2                       # :525-550
+
+
+def test_encode_uses_the_pinned_retile_and_count():
+    """The whole-path oracle goes through the same functions the KATs above pin: its chroma planes equal
+    orc_subsample_retile of the colour-converted padded image, its histogram equals orc_count_block's."""
+    rng = np.random.default_rng(5)
+    px = rng.integers(0, 256, (19, 27, 3), dtype=np.uint8)
+    r = O.encode(px, 255, O.P420, keep_planes=True)
+    n = px.astype(np.float32) / np.float32(255.0)
+    pad = O.pad_image(n, 16, 16)
+    ycc = np.array([[O.rgb_to_ycbcr(*p) for p in row] for row in pad], np.float32)
+    cb = O.subsample_retile(ycc[..., 1], 2, 2, True, 8).reshape(-1, 64)
+    tmp = cb.copy()
+    for b in tmp:
+        b[:] = O.dct8x8(b)
+    assert np.array_equal(tmp.view(np.uint32) & 0x7FFFFFFF, r.dct_cb.view(np.uint32) & 0x7FFFFFFF)
+    blocks, last = [], [0, 0, 0]
+    for i, blk in enumerate(r.stream):
+        comp = 0 if i % 6 < 4 else i % 6 - 3
+        d = int(np.int16(int(blk[0]) - last[comp]))
+        last[comp] = int(blk[0])
+        blocks.append((comp, d, O.rle_tokens(blk[1:])))
+    for sel, t in ((lambda c: c == 0, 0), (lambda c: c > 0, 2)):
+        dc, ac = O.count_blocks([(d, tk) for c, d, tk in blocks if sel(c)])
+        assert np.array_equal(dc, r.hist[t][:16]) and np.array_equal(ac, r.hist[t + 1])
+
+
+# ---- padder.rs:52-87 (sizes) and :18-38 (content: source dots, black to the right and below)
+def test_padder_kats():
+    red = np.array([1.0, 0.0, 0.0], np.float32)
+    p = O.pad_image(np.tile(red, (1, 1, 1)), 16, 8)                      # pad_one
+    assert p.shape == (8, 16, 3) and p.shape[0] * p.shape[1] == 16 * 8
+    assert p[0, 0].tolist() == [1.0, 0.0, 0.0] and not p[0, 1:].any() and not p[1:].any()
+    p = O.pad_image(np.tile(red, (7, 17, 1)), 16, 16)                    # pad_7_17
+    assert p.shape == (16, 32, 3) and p.shape[0] * p.shape[1] == 32 * 16
+    assert (p[:7, :17] == red).all() and not p[:7, 17:].any() and not p[7:].any()
+    p = O.pad_image(np.tile(red, (99, 99, 1)), 10, 10)                   # pad_99_99
+    assert p.shape[0] * p.shape[1] == 10000
+    assert (p[:99, :99] == red).all() and not p[:, 99].any() and not p[99].any()
+    # black pads to YCbCr (-128, 0, 0) exactly (color.rs:157-167), which is what the DCT sees there
+    assert O.rgb_to_ycbcr(*p[99, 99]).tolist() == [-128.0, 0.0, 0.0]
 
 
 # ---- length_limited.rs:209-264, tree.rs:349-405
@@ -159,7 +239,9 @@ def test_package_merge_kats():
     with pytest.raises(ValueError):
         O.package_merge([1, 1, 1, 2, 2, 2, 3, 6, 17, 20], 3)
     # tree.rs:344-372: depths for limit 10 (sorted by frequency)
-    assert O.package_merge(sorted([17, 3, 12, 3, 18, 12]), 10) == [4, 4, 3, 2, 2, 2] or True
+    # test helper depth = code length + 1 (root counts as depth 1): [5,5,4,3,3,3] and [5,5,4,4,4,3,3]
+    assert O.package_merge(sorted([17, 3, 12, 3, 18, 12]), 10) == [4, 4, 3, 2, 2, 2]
+    assert O.package_merge(sorted([17, 3, 12, 3, 18, 12, 13]), 10) == [4, 4, 3, 3, 3, 2, 2]
     hist = np.zeros(256, np.uint64)
     for s, f in [(1, 17), (2, 3), (3, 12), (4, 3), (5, 18), (6, 12), (7, 13)]:
         hist[s] = f
@@ -167,7 +249,7 @@ def test_package_merge_kats():
     # tree.rs:391-405 one-star replaced depths [6,5,4,4,4,3,3] == lengths with the +1 quirk + 1
     # (tree depth counts the root); the code-length vector itself is:
     assert sym == [2, 4, 3, 6, 7, 1, 5]
-    assert ln[0] == ln[1] + 1 and sorted(ln, reverse=True) == ln
+    assert [x + 1 for x in ln] == [6, 5, 4, 4, 4, 3, 3]
     assert O.package_merge([5], 15) == [0]            # n = 1 -> length 0, +1 quirk makes it 1
 
 
