@@ -583,12 +583,19 @@ __device__ __forceinline__ void fast_arai2(f2 x0, f2 x1, f2 x2, f2 x3, f2 x4, f2
     out(3, v67, kS3);
 }
 
+#ifndef K1_I2FP
+#define K1_I2FP 0   // bit ch set: channel ch of u8 input is converted by PRMT + I2FP.F32.U32 (integer pipe) instead of I2F.U8
+#endif
 // raw sample i (0..47) of a strip row as f32 (before normalisation)
 template <int FMT, int NW>
 __device__ __forceinline__ float sample_raw(const uint32_t (&w)[NW], int i) {
     if constexpr (FMT == DMMT_RGB_F32_NORM) return __uint_as_float(w[i]);
-    else if constexpr (FMT == DMMT_RGB_U8) return (float)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
-    else return (float)((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+    else if constexpr (FMT == DMMT_RGB_U8) {
+        if ((K1_I2FP >> (i % 3)) & 1) {
+            return __uint2float_rn(__byte_perm(w[i >> 2], 0u, 0x4440u | (uint32_t)(i & 3)));
+        }
+        return (float)((w[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+    } else return (float)((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
 }
 
 template <int COMP>
@@ -766,6 +773,114 @@ __device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, 
     return ok;
 }
 
+#ifndef K1_WALK2
+#define K1_WALK2 1   // 1: reversed masks from VIMNMX + IMAD, run LUT, 28-instruction walk step; 0: round-1 walk
+#endif
+// Per-run part of an AC token, one 64-entry table per component class (luma | chroma), in shared memory:
+//   F[run] = table << 8 | (run >> 4) << 10 | (run & 15) << 4 | ((run & 15) ^ (chroma ? 8 : 0))
+// so that the token of a coefficient of category cat is (bits << 16) | (F[run] ^ cat) -- tok_swz(table, run << 4 | cat)
+// plus the ZRL count -- and F[0] itself is the EOB token.
+__device__ __forceinline__ uint32_t k1_run_lut_entry(int chroma, int run) {
+    const uint32_t tac = chroma ? T_CAC : T_YAC, r = (uint32_t)run & 15u;
+    return (tac << 8) | (((uint32_t)run >> 4) << 10) | (r << 4) | (r ^ (chroma ? 8u : 0u));
+}
+
+// The walk of one block over REVERSED occupancy masks: bit 31 - p of mrl = coefficient p (0..31) is non-zero, bit
+// 63 - p of mrh for p in 32..63.  The staged block holds the coefficient of zig-zag position p at int16 index
+// (p ^ 1) (the halves of a word are swapped, see the mask construction) of chunk (p >> 3) ^ (slot & 7).
+// CHECK: categories above 15 are possible (f32 input only: integer samples bound every coefficient by 8 * 128).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// HOT: the token destination is the tile's shared-memory buffer (32-bit shared addresses, always stored).  The cold
+// variant (a tile too dense for that buffer: tokens straight to global memory, or nowhere when the tile does not fit its
+// region either) is the same code behind a generic pointer, kept out of line so that it costs no instruction-cache space.
+template <bool CHECK, bool HOT>
+__device__ __forceinline__ bool p420_walk(uint32_t* __restrict__ dst, bool store, uint32_t off, unsigned short dcq, int slot,
+                                          int m, int k, int comp, uint32_t mrl, uint32_t mrh, const short* s_dc,
+                                          const uint4* s_stage, unsigned int* s_hist, const unsigned short* s_flut,
+                                          uint32_t* dcpos, uint32_t nz_bits) {
+    const int tdc = comp ? T_CDC : T_YDC;
+    unsigned int* const h_dc = s_hist + (comp ? 16 : 0);
+    const uint32_t hac_a = smem_u32(s_hist + (comp ? 288 : 32));   // AC bins, indexed by the low byte of the token
+    const uint32_t lut_a = smem_u32(s_flut + (comp ? 64 : 0));
+    bool ok = true;
+    {
+        const int ps = k == 0 ? slot - 3 : (k < 4 ? slot - 1 : slot - 6);
+        if ((k != 0 && k < 4) || m > 0) {
+            const int diff = (int)(short)((short)dcq - s_dc[ps]);
+            int cat = 0;
+            uint32_t bits = 0;
+            if (diff != 0) k1_cat_bits(diff, cat, bits);
+            if (CHECK) ok &= cat <= 15;
+            atomicAdd(&h_dc[cat & 15], 1u);
+            if (store) dst[off] = k1_token(tdc, cat & 15, 0, bits);
+        } else {
+            // predictor is in the previous tile (or is the seed): k2_fix_dc finishes this token
+            if (k >= 4) dcpos[k - 4] = off;
+            if (store) dst[off] = (uint32_t)dcq << 16;
+        }
+        ++off;
+    }
+    const uint32_t sbase = smem_u32(s_stage + slot * 8);
+    const uint32_t swz = (((uint32_t)slot & 7u) << 3) | 1u;
+    uint32_t dpa = HOT ? smem_u32(dst + off) : 0u;   // HOT: running shared address of the next token
+    int hp = 31;   // 31 - (position of the previous non-zero coefficient), in the coordinates of the current half
+    uint32_t nzrl_total = 0;
+    // 1 and ~1 derived from the opaque -0.0 argument: as literals ptxas re-materialises them in every step of the walk
+    const uint32_t c_one = nz_bits >> 31, c_m2 = ~c_one;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        uint32_t mk = half ? mrh : (mrl & 0x7FFFFFFFu);
+        uint32_t cs = (half ? 63u : 31u) ^ swz;   // position p = (31 | 63) - h sits at int16 index (p ^ swz) == h ^ cs
+        asm volatile("" : "+r"(cs));              // keep it ONE loop-invariant register
+        bool more = mk != 0u;
+#pragma unroll 1
+        while (more) {
+            uint32_t h, f, F;
+            int v;
+            asm("bfind.u32 %0, %1;" : "=r"(h) : "r"(mk));
+            asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(sbase + ((h ^ cs) << 1)));
+            const int run = hp - (int)h - 1;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(F) : "r"(lut_a + ((uint32_t)run << 1)));
+            const uint32_t bit = c_one << h;
+            more = bit != mk;
+            mk ^= bit;
+            hp = (int)h;
+            nzrl_total += (uint32_t)run >> 4;
+            asm("bfind.u32 %0, %1;" : "=r"(f) : "r"((uint32_t)abs(v)));   // category - 1
+            if (CHECK) ok &= f < 15u;
+            const uint32_t sym = F ^ (f + 1u);
+            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hac_a + ((sym & 0xFFu) << 2)) : "memory");
+            // v > 0: v; v < 0: v - 1; the low `cat` bits of it (categorize.rs:22-41)
+            const uint32_t bits = (uint32_t)(v + (v >> 31)) & ~(c_m2 << f);
+            const uint32_t tok = bits * 65536u + sym;
+            if (HOT) {
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(dpa), "r"(tok) : "memory");
+                dpa += 4;
+            } else {
+                if (store) dst[off] = tok;
+                ++off;
+            }
+        }
+        hp += 32;
+    }
+    if (nzrl_total) atomicAdd(&s_hist[(comp ? 288 : 32) + (comp ? 0xF7 : 0xFF)], nzrl_total);  // ZRL 0xF0, swizzled
+    if (hp != 32) {                                                                             // coefficient 63 is zero: EOB 0x00
+        atomicAdd(&s_hist[(comp ? 288 : 32) + (comp ? 8 : 0)], 1u);
+        const uint32_t eob = k1_run_lut_entry(comp, 0);
+        if (HOT) asm volatile("st.shared.u32 [%0], %1;" ::"r"(dpa), "r"(eob) : "memory");
+        else if (store) dst[off] = eob;
+    }
+    return ok;
+}
+template <bool CHECK>
+__device__ __noinline__ bool p420_walk_cold(uint32_t* __restrict__ dst, bool store, uint32_t off, unsigned short dcq, int slot,
+                                            int m, int k, int comp, uint32_t mrl, uint32_t mrh, const short* s_dc,
+                                            const uint4* s_stage, unsigned int* s_hist, const unsigned short* s_flut,
+                                            uint32_t* dcpos, uint32_t nz_bits) {
+    return p420_walk<CHECK, false>(dst, store, off, dcq, slot, m, k, comp, mrl, mrh, s_dc, s_stage, s_hist, s_flut, dcpos, nz_bits);
+}
+
 constexpr int P420_THREADS = 96;   // one thread per 8x8 block of the tile (16 MCUs x 6 blocks)
 // shared-memory histogram of a tile: only the bins that exist, [Y-DC 16 | C-DC 16 | Y-AC 256 | C-AC 256]
 constexpr int SH_YDC = 0, SH_CDC = 16, SH_YAC = 32, SH_CAC = 288, SH_BINS = 544;
@@ -781,6 +896,9 @@ constexpr int SH_YDC = 0, SH_CDC = 16, SH_YAC = 32, SH_CAC = 288, SH_BINS = 544;
 #endif
 #ifndef K1_HUNROLL
 #define K1_HUNROLL 0
+#endif
+#ifndef K1_PF
+#define K1_PF 0      // > 0: L2 prefetch of the tile K1_PF images ahead
 #endif
 // CTA = 96 threads = 3 warps, every one of them busy in every phase: 8 CTAs (24 warps) per SM at 80 registers.
 template <int FMT, bool FUSED, bool VEC>
@@ -798,6 +916,7 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
     __shared__ __align__(16) unsigned int s_hist[FUSED ? SH_BINS : 4];   // fused path: symbol counts of the tile
     __shared__ uint32_t s_cnt[FUSED ? 100 : 1];         // tokens per block, then exclusive offsets (+ total)
     __shared__ short s_dc[FUSED ? 96 : 1];
+    __shared__ unsigned short s_flut[FUSED && K1_WALK2 ? 128 : 1];   // k1_run_lut_entry: luma | chroma
     __shared__ int s_flag;
     constexpr int BPM = 6, MPT = 16, NUNITS = 96;
     if constexpr (FMT == DMMT_RGB_F32_NORM) {
@@ -807,6 +926,22 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
     const int tile_x = blockIdx.x, mrow = blockIdx.y, img = blockIdx.z;
     const uint8_t* __restrict__ pix = a.pixels + (size_t)img * a.img_stride_bytes;
     const size_t pitch = (size_t)a.W * Px<FMT>::kBytes;
+#if K1_PF > 0
+    // The pixel rows of the tile at the same place K1_PF images further on -- the CTA that takes them starts about one
+    // CTA lifetime from now (CTAs are issued x, then y, then image; an SM set holds ~2 frames of 1080p tiles) -- are
+    // requested into L2 now: one 128-byte line per thread covers the 16 rows x 768 B of a u8 tile, so the first
+    // strips of that CTA wait for L2, not for DRAM.
+    if (img + K1_PF < (int)gridDim.z) {
+        constexpr int LPR = (TILE_W * Px<FMT>::kBytes + 127) / 128;   // lines per tile row
+        for (int t = threadIdx.x; t < 16 * LPR; t += P420_THREADS) {
+            const int r = t / LPR, l = t - r * LPR;
+            const int y = mrow * 16 + r;
+            const size_t xoff = (size_t)tile_x * TILE_W * Px<FMT>::kBytes + (size_t)l * 128;
+            if (y < a.H && xoff < pitch)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pix + (size_t)K1_PF * a.img_stride_bytes + (size_t)y * pitch + xoff));
+        }
+    }
+#endif
 
     // ---------------- phase A: strip = 8 px x 2 rows, both rows packed in one register pair ----------------
     // 256 strips per tile = 8 row pairs x 32 strips; a warp takes one whole row pair per round (rounds 0-1: all
@@ -946,13 +1081,29 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
     // zig-zag by register renaming, two i16 per word.  Coefficient path: straight into the tile's staging
     // area (slot = stream order).  Fused path: the words stay in registers until the plane storage, which
     // the staging area and the token buffer reuse, is dead (after the barrier on the block counts).
-    uint32_t mlo = 0, mhi = 0;  // occupancy mask of the block (fused path)
+    uint32_t mlo = 0, mhi = 0;  // occupancy mask of the block (fused path; K1_WALK2: bit-reversed)
     uint32_t wq[FUSED ? 32 : 1];
     if (active) {
         uint32_t mm[2] = {0u, 0u};
+        uint32_t G[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             uint32_t w[4];
+            if constexpr (FUSED && K1_WALK2) {
+                // halves swapped (even position in the high half): min(w, 0x00010001) has the flag of the odd
+                // position in bit 0 and of the even one in bit 16, and ONE multiply-add per word drops both at their
+                // place of a bit-reversed mask: word wi of a group of 8 times 2^(15 - 2 wi) + 2^(30 - 2 wi) puts
+                // the even flag at bit 31 - 2 wi and the odd one at 30 - 2 wi (the even flag's second image falls off
+                // the top, the odd flag's second image lands in the low half, which is discarded).
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    asm("mov.b32 %0, {%1, %2};" : "=r"(w[j]) : "h"(qv[zz_at(8 * i + 2 * j + 1)]), "h"(qv[zz_at(8 * i + 2 * j)]));
+                    wq[4 * i + j] = w[j];
+                    const int wi = 4 * (i & 1) + j;
+                    G[i >> 1] += __vminu2(w[j], 0x00010001u) * ((1u << (15 - 2 * wi)) + (1u << (30 - 2 * wi)));
+                }
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 asm("mov.b32 %0, {%1, %2};" : "=r"(w[j]) : "h"(qv[zz_at(8 * i + 2 * j)]), "h"(qv[zz_at(8 * i + 2 * j + 1)]));
@@ -970,6 +1121,10 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
             }
         }
         mlo = mm[0], mhi = mm[1];
+        if constexpr (FUSED && K1_WALK2) {
+            mlo = __byte_perm(G[1], G[0], 0x7632);   // positions 0..31 in bits 31..0
+            mhi = __byte_perm(G[3], G[2], 0x7632);   // positions 32..63
+        }
     }
     if constexpr (!FUSED) {
         // the tile leaves as ONE contiguous, coalesced 12 KB run (16 MCUs x 6 blocks x 128 B in stream order)
@@ -991,10 +1146,13 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
         uint32_t* s_ctok = reinterpret_cast<uint32_t*>(s_planes) + 96 * 8 * 4;  // second half of the plane storage
         constexpr uint32_t S_CTOK_CAP = sizeof(s_planes) / 4 - 96 * 8 * 4;
         for (int i = threadIdx.x; i < SH_BINS / 4; i += P420_THREADS) reinterpret_cast<uint4*>(s_hist)[i] = make_uint4(0, 0, 0, 0);
+        if constexpr (K1_WALK2)
+            for (int i = threadIdx.x; i < 128; i += P420_THREADS) s_flut[i] = (unsigned short)k1_run_lut_entry(i >> 6, i & 63);
         uint32_t cnt = 0;
         if (active) {
             // DC + one token per non-zero AC (ZRLs ride on it) + EOB unless coefficient 63 is non-zero
-            cnt = 1u + __popc(mlo & ~1u) + __popc(mhi) + ((mhi >> 31) ? 0u : 1u);
+            if constexpr (K1_WALK2) cnt = 1u + __popc(mlo & 0x7FFFFFFFu) + __popc(mhi) + ((mhi & 1u) ? 0u : 1u);
+            else cnt = 1u + __popc(mlo & ~1u) + __popc(mhi) + ((mhi >> 31) ? 0u : 1u);
             s_dc[slot] = (short)qv[0];
         }
         if (u < NUNITS) s_cnt[slot] = cnt;  // every slot is written: blocks beyond the padded image count 0
@@ -1032,7 +1190,13 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
             bool ok;
             // ONE copy of the walk: the token destination (shared-memory tile buffer, or global memory for a very
             // dense tile) is a CTA-uniform generic pointer -- two specialised copies cost 1.6 % (instruction footprint)
-            ok = p420_tokenize_block(in_smem ? s_ctok : g_tok, in_smem || fits, my_off, qv[0], slot, m, k, comp, mlo, mhi, s_dc, s_stage, s_hist, a.fo.dcpos + dcp);
+            constexpr bool CHK = FMT == DMMT_RGB_F32_NORM;
+            if constexpr (K1_WALK2) {
+                if (in_smem) ok = p420_walk<CHK, true>(s_ctok, true, my_off, qv[0], slot, m, k, comp, mlo, mhi, s_dc, s_stage, s_hist, s_flut, a.fo.dcpos + dcp, __float_as_uint(a.neg_zero));
+                else ok = p420_walk_cold<CHK>(g_tok, fits, my_off, qv[0], slot, m, k, comp, mlo, mhi, s_dc, s_stage, s_hist, s_flut, a.fo.dcpos + dcp, __float_as_uint(a.neg_zero));
+            } else {
+                ok = p420_tokenize_block(in_smem ? s_ctok : g_tok, in_smem || fits, my_off, qv[0], slot, m, k, comp, mlo, mhi, s_dc, s_stage, s_hist, a.fo.dcpos + dcp);
+            }
             if (!ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_RANGE);
         }
         __syncthreads();
@@ -1057,7 +1221,7 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
                 // the plain symbols are the same aligned group of four, permuted by k & 3 (k = the run nibble)
                 const int b = 4 * q4;
                 int g0 = b, k = 0;
-                if (b >= SH_CAC) g0 = T_CAC * 256 + (b - SH_CAC), k = (b - SH_CAC) >> 4;
+                if (b >= SH_CAC) g0 = T_CAC * 256 + ((b - SH_CAC) ^ (K1_WALK2 ? 8 : 0)), k = (b - SH_CAC) >> 4;
                 else if (b >= SH_YAC) g0 = T_YAC * 256 + (b - SH_YAC), k = (b - SH_YAC) >> 4;
                 else if (b >= SH_CDC) g0 = T_CDC * 256 + (b - SH_CDC);
                 unsigned int* g = gh + (g0 ^ (k & 12));

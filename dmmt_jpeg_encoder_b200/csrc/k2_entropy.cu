@@ -1244,6 +1244,19 @@ cudaError_t launch_zero_scan(uint32_t* scan, size_t stride_words, const ImgMeta*
 
 uint32_t k4_max_chunks(size_t scan_cap_bytes) { return (uint32_t)((scan_cap_bytes + K4_CHUNK - 1) / K4_CHUNK); }
 
+// SMs of the current device (queried once per device; every context of this library sets its device first)
+static int sm_count() {
+    static int cached[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
+    if (!cached[dev]) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 1;
+        cached[dev] = sms;
+    }
+    return cached[dev];
+}
+
 cudaError_t launch_k3(uint32_t n_chunks, uint32_t n_segs, int n, const TokBuf& tb, const EncTables* enc, ImgMeta* meta,
                       unsigned long long* lb_state, unsigned int* ticket, uint32_t* scan, size_t scan_stride_words,
                       unsigned long long seed_bits, int pad_ones, cudaStream_t st, const unsigned long long* seed_src) {
@@ -1253,12 +1266,10 @@ cudaError_t launch_k3(uint32_t n_chunks, uint32_t n_segs, int n, const TokBuf& t
     // partly empty wave)
     static int resident = 0;
     if (!resident) {
-        int per_sm = 0, dev = 0, sms = 0;
+        int per_sm = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_pack, EB, 0);
-        if (e == cudaSuccess) e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
-        resident = per_sm * sms > 0 ? per_sm * sms : 148;
+        resident = (per_sm > 0 ? per_sm : 1) * sm_count();
     }
     const uint32_t grid = a.n_items < (uint32_t)resident ? a.n_items : (uint32_t)resident;
     k3_pack<<<grid ? grid : 1u, EB, 0, st>>>(a);
@@ -1271,7 +1282,7 @@ cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStre
              h.or_first_byte, h.seed_src, h.owned_mode, h.or_first_src, h.base_src};
     // CTAs take chunks by ticket, so the grid only has to keep the device busy: about 8 CTAs per SM
     // over all images, never more than the chunks an image can have
-    uint32_t per_image = (uint32_t)((148 * 8 + n - 1) / n);
+    uint32_t per_image = (uint32_t)((sm_count() * 8 + n - 1) / n);
     if (per_image < 8) per_image = 8;
     if (grid_chunks == 0) grid_chunks = 1;
     if (per_image > grid_chunks) per_image = grid_chunks;
@@ -1369,7 +1380,7 @@ __global__ void k_shard_result(const ImgMeta* meta, long long* out2) {
 cudaError_t launch_shard_count_bytes(const uint8_t* scan, const ImgMeta* meta, const unsigned long long* seed_src,
                                      int owned_mode, const int* or_first_src, int is_first, int is_last,
                                      unsigned long long* ctr2, long long* n_bytes, cudaStream_t st) {
-    k_shard_count_bytes<<<148 * 2, 256, 0, st>>>(scan, meta, seed_src, owned_mode, or_first_src, is_first, is_last, ctr2,
+    k_shard_count_bytes<<<sm_count() * 2, 256, 0, st>>>(scan, meta, seed_src, owned_mode, or_first_src, is_first, is_last, ctr2,
                                                  n_bytes);
     return cudaGetLastError();
 }
