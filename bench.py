@@ -17,6 +17,11 @@ packed files) over the rank's share of the batch.
           algorithmic bytes per launch / time vs MEASURED_PEAKS.json's HBM copy bandwidth.
   cpu_baseline : the C oracle (restatement of the reference; the Rust crate cannot be built in
           this image) on the host cores, on a bounded sample of the same images.
+  extra.config3 (N = 1): BASELINE config 3, ONE 3840x2160 frame: device microseconds per encode (events, chain
+          replayed from a CUDA graph) and host-buffer microseconds per encode (dmmt_plan_encode_host_into).
+  extra.config5 (N > 1): BASELINE config 5, ONE 32768x32768 image sharded by MCU rows over the N ranks, NCCL
+          exchanges, every rank's K4 writing into rank 0's file over NVLink; verified against the ORACLE's
+          SHA-256 of the same image (tests/golden/config5_sha256.json).
 
 `--impl reference` times only that CPU arm (rank 0), with the same JSON shape.
 """
@@ -55,6 +60,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=64, help="images of the batch timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra.config3 / extra.config5")
+    ap.add_argument("--config5-size", type=int, default=32768)
     return ap.parse_args()
 
 
@@ -195,23 +202,183 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------ GPU arm
 def bind_to_gpu_cpus(index: int):
-    """Restricts this process to the CPUs NVML reports as local to GPU `index`, so that first-touch
-    places the pinned host buffers of the e2e path on that GPU's NUMA node (one process per GPU)."""
+    """Restricts this process to the CPUs NVML reports as local to CUDA device `index` (looked up by PCI bus id: NVML and
+    CUDA may enumerate differently), so that first-touch places the pinned host buffers of the e2e path on that GPU's
+    NUMA node (one process per GPU).  Returns a description for the JSON line."""
     try:
         import pynvml as N
+        import torch
 
         N.nvmlInit()
-        h = N.nvmlDeviceGetHandleByIndex(index)
+        pr = torch.cuda.get_device_properties(index)
+        try:
+            bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            h = N.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            bus, h = f"nvml index {index}", N.nvmlDeviceGetHandleByIndex(index)
         ncpu = os.cpu_count() or 64
         words = N.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
         cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
         cpus &= set(os.sched_getaffinity(0))
         if cpus:
             os.sched_setaffinity(0, cpus)
-            return f"{len(cpus)} cpus local to gpu {index}"
+            lo, hi = min(cpus), max(cpus)
+            return f"gpu {index} ({bus}): {len(cpus)} cpus {lo}-{hi}"
     except Exception as e:  # no NVML / not permitted: keep the inherited affinity
-        return f"unbound ({type(e).__name__})"
-    return "unbound"
+        return f"gpu {index}: unbound ({type(e).__name__})"
+    return f"gpu {index}: unbound"
+
+
+def copy_ceiling(torch, dev, h_in, n_bytes_in, h_out, n_bytes_out, steps):
+    """Raw pinned-memory copy ceiling of this rank for the e2e traffic pattern: the step's H2D bytes and D2H bytes as
+    plain cudaMemcpyAsync in 32 MB pieces on two streams (both directions in flight), nothing else.  Returns seconds
+    per step; the caller turns the max over ranks into the job's copy-bound MPixel/s."""
+    d_in = torch.empty(n_bytes_in, dtype=torch.uint8, device=dev)
+    d_out = torch.zeros(max(n_bytes_out, 1), dtype=torch.uint8, device=dev)
+    t_in = torch.from_numpy(h_in.array)[:n_bytes_in]
+    t_out = torch.from_numpy(h_out.array)[:max(n_bytes_out, 1)]
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    piece = 32 << 20
+
+    def one():
+        with torch.cuda.stream(s1):
+            for o in range(0, n_bytes_in, piece):
+                d_in[o:o + piece].copy_(t_in[o:o + piece], non_blocking=True)
+        with torch.cuda.stream(s2):
+            for o in range(0, n_bytes_out, piece):
+                t_out[o:o + piece].copy_(d_out[o:o + piece], non_blocking=True)
+    one()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / steps
+
+
+def run_config3(D, F, synth, torch, ctx, stream, dev):
+    """BASELINE config 3: ONE 3840x2160 frame on one GPU.  device_us: CUDA events around 50 encodes of the
+    device-resident chain (dmmt_plan_encode_device, replayed from a CUDA graph after the first two calls);
+    host_us: wall clock per dmmt_plan_encode_host_into (pinned host pixels -> pinned host file, H2D + D2H inside)."""
+    import numpy as np
+
+    from oracle import oracle as O
+
+    W, H = 3840, 2160
+    plan = D.Plan(ctx, W, H, F.FMT_U8, 255, D.Options(), 1)
+    d_px = synth.make("photo", 0, H, W, dev).contiguous()
+    d_out = torch.empty(plan.out_stride, dtype=torch.uint8, device=dev)
+    d_len = torch.zeros(1, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    for _ in range(5):
+        plan.encode_device(d_px.data_ptr(), 1, d_out.data_ptr(), d_len.data_ptr())
+    plan.status()
+    n_bytes = int(d_len.item())
+    want = O.encode(d_px.cpu().numpy(), 255, O.P420).jpeg
+    ok = d_out[:n_bytes].cpu().numpy().tobytes() == want
+    K = 50
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(K):
+            plan.encode_device(d_px.data_ptr(), 1, d_out.data_ptr(), d_len.data_ptr())
+        e1.record(stream)
+    torch.cuda.synchronize()
+    plan.status()
+    device_us = e0.elapsed_time(e1) / K * 1e3
+    launches = plan.last_launch_count()
+    plan.set_profiling(True)
+    plan.encode_device(d_px.data_ptr(), 1, d_out.data_ptr(), d_len.data_ptr())
+    plan.status()
+    tm = {k: round(v * 1e3, 2) for k, v in plan.last_timings().items()}
+    plan.set_profiling(False)
+    # host buffers
+    h_in, h_out = D.PinnedBuffer(W * H * 3), D.PinnedBuffer(plan.out_stride)
+    torch.from_numpy(h_in.array).view(H, W, 3).copy_(d_px)
+    torch.cuda.synchronize()
+    offs, lens = np.zeros(1, np.uint64), np.zeros(1, np.uint64)
+    for _ in range(3):
+        plan.encode_host_into(h_in.ptr, 1, h_out.ptr, plan.out_stride, offs, lens)
+    ok = ok and h_out.array[: int(lens[0])].tobytes() == want
+    t0 = time.perf_counter()
+    for _ in range(20):
+        plan.encode_host_into(h_in.ptr, 1, h_out.ptr, plan.out_stride, offs, lens)
+    host_us = (time.perf_counter() - t0) / 20 * 1e6
+    plan.close()
+    h_in.close(), h_out.close()
+    return {"workload": "one synthetic 3840x2160 RGB u8 frame ('photo') -> baseline JPEG 4:2:0, device-resident chain",
+            "device_us": device_us, "mpixel_per_s": W * H / device_us, "host_us": host_us,
+            "host_mpixel_per_s": W * H / host_us, "h2d_bytes": W * H * 3, "d2h_bytes": n_bytes + 16,
+            "kernel_us": tm, "launches_per_encode": launches, "file_bytes": n_bytes,
+            "verified": "byte-identical to the oracle (device-resident and host-buffer paths)" if ok else "MISMATCH"}
+
+
+def run_config5(D, F, synth, torch, dist, local, dev, size, steps=5, warmup=2):
+    """BASELINE config 5: ONE size x size image, MCU-row shards over the ranks (one process per GPU), the small
+    exchanges over NCCL on the context's stream, every rank's K4 storing into rank 0's file over NVLink (CUDA IPC).
+    Timed with CUDA events on every rank between barriers, max over ranks.  Rank 0 compares the SHA-256 of the file
+    with the oracle's committed digest."""
+    import hashlib
+
+    from dmmt_jpeg_encoder_b200 import sharded as S
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = size
+    opts = D.Options()
+    rows = S.mcu_rows_total(n, opts)
+    b, e = S.shard_rows(rows, world, rank)
+    y0, y1 = S.pixel_row_range(n, opts, b, e)
+    d_px = torch.empty((y1 - y0, n, 3), dtype=torch.uint8, device=dev)
+    for s0 in range(y0, y1, 2048):
+        s1 = min(y1, s0 + 2048)
+        d_px[s0 - y0:s1 - y0] = synth.make("smooth", 5, s1 - s0, n, dev, y0=s0)
+    torch.cuda.synchronize()
+    ctx = D.Context(local, torch.cuda.current_stream().cuda_stream)   # launches and NCCL share torch's stream
+    be = S.CudaShardBackend(ctx, d_px.data_ptr(), n, n, F.FMT_U8, 255, opts, b, e)
+    pf = S.PeerFile(be)
+    out, ms, phases = None, [], {}
+    for it in range(warmup + steps):
+        marks = []
+
+        def mark(name):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+        dist.barrier()
+        torch.cuda.synchronize()
+        mark("start")
+        out = S.encode_sharded_peer(be, pf, to_host=False, mark=mark)
+        mark("end")
+        torch.cuda.synchronize()
+        t = torch.tensor([marks[0][1].elapsed_time(marks[-1][1])], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if it >= warmup:
+            ms.append(float(t.item()))
+            for (_, a0), (name, a1) in zip(marks, marks[1:]):
+                phases[name] = phases.get(name, 0.0) + a0.elapsed_time(a1) / steps
+    res = None
+    if rank == 0:
+        digest = hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest()
+        verified = "unchecked (no committed oracle digest for this size)"
+        try:
+            gold = json.load(open(os.path.join(ROOT, "tests", "golden", "config5_sha256.json")))[str(n)]
+            verified = ("sha256 and length equal the oracle's file (tests/golden/config5_sha256.json)"
+                        if (gold["sha256"], gold["bytes"]) == (digest, out.numel()) else "MISMATCH with the oracle's digest")
+        except Exception:
+            pass
+        t = sum(ms) / len(ms)
+        res = {"workload": f"one synthetic {n}x{n} RGB u8 image ('smooth') -> baseline JPEG 4:2:0, MCU-row shards over {world} "
+                           f"ranks, NCCL exchanges of last DCs / histograms / bit counts / tails / byte counts, K4 of every "
+                           f"rank writes into rank 0's file over NVLink", "ms": t, "mpixel_per_s": n * n / t / 1e3,
+               "n_gpus": world, "steps": steps, "warmup": warmup, "file_bytes": out.numel(),
+               "phases_ms_rank0": {k: round(v, 3) for k, v in phases.items()},
+               "timing": "CUDA events on each rank's stream between barriers, max over ranks", "verified": verified}
+    pf.close()
+    be.close()
+    ctx.close()
+    del d_px
+    torch.cuda.empty_cache()
+    return res
 
 
 def free_port():

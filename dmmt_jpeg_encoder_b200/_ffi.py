@@ -15,7 +15,7 @@ OK, E_INVALID, E_NODEVICE, E_CUDA, E_NCCL, E_NOMEM, E_OVERFLOW, E_SYMBOL, E_RANG
     0, -1, -2, -3, -4, -5, -6, -7, -8, -9, -10)
 P444, P422, P420 = 0, 1, 2
 FMT_F32_NORM, FMT_U8, FMT_U16 = 0, 1, 2
-FETCH_COEF, FETCH_HIST, FETCH_TABLES, FETCH_SCAN, FETCH_META = 0, 1, 2, 3, 4
+FETCH_COEF, FETCH_HIST, FETCH_TABLES, FETCH_SCAN, FETCH_META, FETCH_TOKEN_COUNT = 0, 1, 2, 3, 4, 5
 T_NAMES = ("k1_transform", "k2_histogram", "k2b_tables", "k3_pack", "k4_stuff", "k5_compact", "total")
 T_COUNT = 7
 
@@ -120,6 +120,9 @@ SIGNATURES = {
     "dmmt_shard_launch_pack": (C.c_int, [_VP, _VP, C.c_int, _VP]),
     "dmmt_shard_launch_stuff": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.POINTER(_VP), _VP]),
     "dmmt_shard_status": (C.c_int, [_VP]),
+    "dmmt_shard_launch_error": (C.c_int, [_VP, _VP]),
+    "dmmt_shard_set_scan_capacity": (C.c_int, [_VP, C.c_size_t]),
+    "dmmt_shard_worst_case_scan_bytes": (C.c_size_t, [_VP]),
     "dmmt_shard_out_stride": (C.c_size_t, [_VP]),
     "dmmt_device_alloc": (C.c_int, [_VP, C.c_size_t, C.POINTER(_VP)]),
     "dmmt_device_free": (C.c_int, [_VP, _VP]),

@@ -177,55 +177,69 @@ static void plan_free_scratch(dmmt_plan* p) {
     if (p->h_offsets) (void)cudaFreeHost(p->h_offsets), p->h_offsets = nullptr;
 }
 
-// (re)allocates everything whose size depends on the scan capacity
+// (re)allocates everything whose size depends on the scan capacity.  All-or-nothing: the new buffers are allocated
+// first and swapped in, sizes and pointers together, only when every allocation has succeeded; on failure the plan
+// keeps its old buffers and capacity (a plan with new sizes and null buffers would fault on the next encode).
 static int plan_alloc_scan(dmmt_plan* p, size_t scan_cap_bytes) {
-    (void)cudaFree(p->scan), p->scan = nullptr;
-    (void)cudaFree(p->tb.tok), p->tb.tok = nullptr;
-    (void)cudaFree(p->tb.ntok), p->tb.ntok = nullptr;
-    (void)cudaFree(p->zero_region), p->zero_region = nullptr;
-    (void)cudaFree(p->d_out_own), p->d_out_own = nullptr;
-    (void)cudaFree(p->d_dense), p->d_dense = nullptr;
-    p->dense_cap = 0;
-    p->scan_cap_bytes = align_up(std::max<size_t>(scan_cap_bytes, 64), 64);
-    p->scan_stride_words = p->scan_cap_bytes / 4 + 32;  // + slack: look-ahead loads of K4, seed byte
-    p->out_stride = align_up(1024 + p->scan_cap_bytes + p->scan_cap_bytes / 8 + 64, 16);
-    p->max_chunks4 = k4_max_chunks(p->scan_cap_bytes + 8);
-    DMMT_CUDA(cudaMalloc(&p->scan, (size_t)p->n * p->scan_stride_words * 4));
+    dmmt_plan n = *p;  // the sizes of the new layout are computed on a copy
+    n.scan_cap_bytes = align_up(std::max<size_t>(scan_cap_bytes, 64), 64);
+    n.scan_stride_words = n.scan_cap_bytes / 4 + 32;  // + slack: look-ahead loads of K4, seed byte
     // token stream: 32 tokens per block by default (the bytes of the coefficient stream); the worst
     // case is 65 per block (68 allocated) once the scan capacity has been grown to the worst case.
     // The same buffer serves the generic path (regions = K2's 256-block chunks) and the fused 4:2:0
     // path (regions = K1's 96-block tiles).
-    const bool worst = p->scan_cap_bytes >= (size_t)p->g.n_blocks * 209;
+    const bool worst = n.scan_cap_bytes >= (size_t)n.g.n_blocks * 209;
+    // output slot: header + stuffed scan + EOI.  By default the stuffing is given 1/8 of the scan; once the scan
+    // capacity is the true maximum the slot must hold a scan of nothing but 0xFF bytes too (every byte doubled)
+    n.out_stride = align_up(1024 + n.scan_cap_bytes + (worst ? n.scan_cap_bytes : n.scan_cap_bytes / 8) + 64, 16);
+    n.max_chunks4 = k4_max_chunks(n.scan_cap_bytes + 8);
     const uint32_t per_block = worst ? 68u : 32u;
-    p->tb.chunk_cap = tok_blocks_per_chunk() * per_block;
-    p->fused = k1_fused_supported(p->g, p->k1c) && !p->force_generic;
-    p->fo.tiles_x = k1_tiles_x(p->g);
-    p->fo.tiles = p->fo.tiles_x * (uint32_t)p->g.mcus_y;
-    p->fo.tile_cap = 96u * per_block;
-    p->n_chunks3f = (p->fo.tiles + 7) / 8;
-    const size_t words_generic = (size_t)p->n_chunks3 * p->tb.chunk_cap;
-    const size_t words_fused = (size_t)p->fo.tiles * p->fo.tile_cap;
+    n.tb.chunk_cap = tok_blocks_per_chunk() * per_block;
+    n.fused = k1_fused_supported(n.g, n.k1c) && !n.force_generic;
+    n.fo.tiles_x = k1_tiles_x(n.g);
+    n.fo.tiles = n.fo.tiles_x * (uint32_t)n.g.mcus_y;
+    n.fo.tile_cap = 96u * per_block;
+    n.n_chunks3f = (n.fo.tiles + 7) / 8;
+    const size_t words_generic = (size_t)n.n_chunks3 * n.tb.chunk_cap;
+    const size_t words_fused = (size_t)n.fo.tiles * n.fo.tile_cap;
     const size_t img_words = std::max(words_generic, words_fused);
-    p->tb.img_stride_words = img_words;
-    p->fo.img_stride_words = img_words;
-    DMMT_CUDA(cudaMalloc(&p->tb.tok, (size_t)p->n * img_words * 4));
-    const size_t n_regions = std::max<size_t>(p->n_chunks3, p->fo.tiles);
-    DMMT_CUDA(cudaMalloc(&p->tb.ntok, (size_t)p->n * n_regions * 4));
-    p->fo.tok = p->tb.tok;
-    p->fo.ntok = p->tb.ntok;
-    (void)cudaFree(p->fo.last_dc), p->fo.last_dc = nullptr;
-    (void)cudaFree(p->fo.dcpos), p->fo.dcpos = nullptr;
-    DMMT_CUDA(cudaMalloc(&p->fo.last_dc, (size_t)p->n * p->fo.tiles * 4 * sizeof(int16_t)));
-    DMMT_CUDA(cudaMalloc(&p->fo.dcpos, (size_t)p->n * p->fo.tiles * 2 * sizeof(uint32_t)));
+    n.tb.img_stride_words = img_words;
+    n.fo.img_stride_words = img_words;
+    const size_t n_regions = std::max<size_t>(n.n_chunks3, n.fo.tiles);
     // one zero-initialised region per run: hist | meta | lb3 | lb4 | tk3 | tk4
     const size_t o_hist = 0;
-    const size_t o_meta = o_hist + align_up((size_t)p->n * 1024 * sizeof(unsigned int), 16);
-    const size_t o_lb3 = o_meta + align_up((size_t)p->n * sizeof(ImgMeta), 16);
-    const size_t o_lb4 = o_lb3 + (size_t)p->n * std::max(p->n_chunks3, p->n_chunks3f) * 8;
-    const size_t o_tk3 = o_lb4 + (size_t)p->n * p->max_chunks4 * 8;
-    const size_t o_tk4 = o_tk3 + align_up((size_t)p->n * 4, 16);
-    p->zero_bytes = o_tk4 + align_up((size_t)p->n * 4, 16);
-    DMMT_CUDA(cudaMalloc(&p->zero_region, p->zero_bytes));
+    const size_t o_meta = o_hist + align_up((size_t)n.n * 1024 * sizeof(unsigned int), 16);
+    const size_t o_lb3 = o_meta + align_up((size_t)n.n * sizeof(ImgMeta), 16);
+    const size_t o_lb4 = o_lb3 + (size_t)n.n * std::max(n.n_chunks3, n.n_chunks3f) * 8;
+    const size_t o_tk3 = o_lb4 + (size_t)n.n * n.max_chunks4 * 8;
+    const size_t o_tk4 = o_tk3 + align_up((size_t)n.n * 4, 16);
+    n.zero_bytes = o_tk4 + align_up((size_t)n.n * 4, 16);
+
+    uint32_t *scan = nullptr, *tok = nullptr, *ntok = nullptr, *dcpos = nullptr;
+    int16_t* last_dc = nullptr;
+    uint8_t* zero_region = nullptr;
+    cudaError_t e = cudaMalloc(&scan, (size_t)n.n * n.scan_stride_words * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&tok, (size_t)n.n * img_words * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ntok, (size_t)n.n * n_regions * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&last_dc, (size_t)n.n * n.fo.tiles * 4 * sizeof(int16_t));
+    if (e == cudaSuccess) e = cudaMalloc(&dcpos, (size_t)n.n * n.fo.tiles * 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&zero_region, n.zero_bytes);
+    if (e != cudaSuccess) {
+        dmmt_set_cuda_error(e, "cudaMalloc of the plan's scan / token scratch", __FILE__, __LINE__);
+        (void)cudaFree(scan), (void)cudaFree(tok), (void)cudaFree(ntok), (void)cudaFree(last_dc), (void)cudaFree(dcpos);
+        (void)cudaFree(zero_region);
+        return e == cudaErrorMemoryAllocation ? DMMT_E_NOMEM : DMMT_E_CUDA;
+    }
+    // success: release the old buffers (and the arenas sized by the old out_stride) and install the new layout
+    (void)cudaFree(p->scan), (void)cudaFree(p->tb.tok), (void)cudaFree(p->tb.ntok), (void)cudaFree(p->zero_region);
+    (void)cudaFree(p->fo.last_dc), (void)cudaFree(p->fo.dcpos), (void)cudaFree(p->d_out_own), (void)cudaFree(p->d_dense);
+    *p = n;
+    p->d_out_own = nullptr, p->d_dense = nullptr, p->dense_cap = 0;
+    p->scan = scan;
+    p->tb.tok = p->fo.tok = tok;
+    p->tb.ntok = p->fo.ntok = ntok;
+    p->fo.last_dc = last_dc, p->fo.dcpos = dcpos;
+    p->zero_region = zero_region;
     p->hist = reinterpret_cast<unsigned int*>(p->zero_region + o_hist);
     p->meta = reinterpret_cast<ImgMeta*>(p->zero_region + o_meta);
     p->lb3 = reinterpret_cast<unsigned long long*>(p->zero_region + o_lb3);
@@ -663,6 +677,18 @@ extern "C" int dmmt_plan_fetch(dmmt_plan* p, int what, int index, void* dst, siz
             src = p->scan + (size_t)index * p->scan_stride_words, bytes = (size_t)((m.scan_bits + 7) / 8);
             break;
         case DMMT_FETCH_META: src = p->meta + index, bytes = sizeof(ImgMeta); break;
+        case DMMT_FETCH_TOKEN_COUNT: {
+            // tokens K1 / K2 wrote for this image (sum over its token regions): the live measure of the token traffic
+            const size_t regions = p->fused ? p->fo.tiles : p->n_chunks3;
+            std::vector<uint32_t> nt(regions);
+            DMMT_CUDA(cudaMemcpy(nt.data(), p->tb.ntok + (size_t)index * regions, regions * 4, cudaMemcpyDeviceToHost));
+            unsigned long long total = 0;
+            for (uint32_t v : nt) total += v;
+            if (got) *got = sizeof total;
+            if (cap_bytes < sizeof total) return DMMT_E_WRITE;
+            memcpy(dst, &total, sizeof total);
+            return DMMT_OK;
+        }
         default: return DMMT_E_INVALID;
     }
     if (got) *got = bytes;

@@ -97,9 +97,15 @@ struct K4HostArgs {
 cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStream_t st);
 
 cudaError_t launch_last_dc(const Geom& g, const int16_t* coef, int16_t* d_out3, cudaStream_t st);
+// single-process shard exchange over peer memory (see k_peer_exchange)
+constexpr int DMMT_MAX_PEER_SHARDS = 64;
+struct PeerPtrs {
+    const void* p[DMMT_MAX_PEER_SHARDS];
+};
+cudaError_t launch_peer_exchange(const PeerPtrs& srcs, int n, int elems, int mode, long long* out, cudaStream_t st);
 // device-resident shard exchange helpers
 cudaError_t launch_shard_widen(const int16_t* last_dc3, int* out4, const unsigned int* hist, long long* hist64,
-                               const ImgMeta* meta, long long* bits_out, cudaStream_t st);
+                               const ImgMeta* meta, long long* bits_out, cudaStream_t st, long long* err_out = nullptr);
 cudaError_t launch_shard_count_bytes(const uint8_t* scan, const ImgMeta* meta, const unsigned long long* seed_src,
                                      int owned_mode, const int* or_first_src, int is_first, int is_last,
                                      unsigned long long* ctr2, long long* n_bytes, cudaStream_t st);

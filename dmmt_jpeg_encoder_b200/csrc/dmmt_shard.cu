@@ -438,6 +438,17 @@ extern "C" int dmmt_shard_launch_stuff_into(dmmt_shard* s, const int64_t* d_all_
     return DMMT_OK;
 }
 
+// the device-side error flag of the phases so far as an int64 in device memory (asynchronous): travels with the
+// byte counts in the caller's all-gather, so that EVERY rank learns of a failed shard
+extern "C" int dmmt_shard_launch_error(dmmt_shard* s, int64_t* d_err) {
+    if (!s || !d_err) return DMMT_E_INVALID;
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    DMMT_CUDA(launch_shard_widen(nullptr, nullptr, nullptr, nullptr, p->meta, nullptr, p->stream, reinterpret_cast<long long*>(d_err)));
+    p->last_launches += 1;
+    return DMMT_OK;
+}
+
 // device-side error flag of the shard's phases so far (synchronises)
 extern "C" int dmmt_shard_status(dmmt_shard* s) {
     if (!s) return DMMT_E_INVALID;
@@ -451,7 +462,253 @@ extern "C" int dmmt_shard_status(dmmt_shard* s) {
 
 extern "C" int dmmt_shard_launch_count(const dmmt_shard* s) { return s ? s->plan->last_launches : 0; }
 
+// scan capacity of the shard's plan (see dmmt_plan_set_scan_capacity): DMMT_E_OVERFLOW from any phase means "grow and
+// run the phases again from dmmt_shard_transform / dmmt_shard_launch_transform"
+extern "C" size_t dmmt_shard_worst_case_scan_bytes(const dmmt_shard* s) {
+    return s ? dmmt_plan_worst_case_scan_bytes(s->plan) : 0;
+}
+extern "C" int dmmt_shard_set_scan_capacity(dmmt_shard* s, size_t bytes) {
+    if (!s) return DMMT_E_INVALID;
+    return dmmt_plan_set_scan_capacity(s->plan, bytes);
+}
+
 // ---- single-process driver: shards on the given contexts (devices may repeat) ------------------
+// Exchange buffers of one shard, in ITS device's memory; the other shards read them over peer access.
+struct ShardXchg {
+    int32_t last4[4];
+    long long hist[1024];
+    long long ghist[1024];
+    long long bits;
+    long long all_bits_offs[2 * DMMT_MAX_PEER_SHARDS];   // [0, n): bit counts, [n, 2n): exclusive bit offsets
+    int32_t tail2[2];
+    long long all_tail2[DMMT_MAX_PEER_SHARDS];           // {byte, bits} pairs as one 64-bit word each
+    long long n_bytes;
+    long long all_n_offs[2 * DMMT_MAX_PEER_SHARDS];      // [0, n): stuffed byte counts, [n, 2n): byte offsets in the file
+    long long res2[2];
+};
+
+namespace {
+struct ShardedJob {
+    dmmt_ctx* const* ctxs = nullptr;
+    int ns = 0;
+    std::vector<dmmt_shard*> sh;
+    std::vector<uint8_t*> d_px;
+    std::vector<ShardXchg*> x;
+    std::vector<cudaEvent_t> ev;   // one per shard, re-recorded phase by phase
+    uint8_t* d_file = nullptr;
+    size_t file_cap = 0;
+    ~ShardedJob() {
+        for (int i = 0; i < ns; i++) {
+            (void)cudaSetDevice(ctxs[i]->device);
+            (void)cudaStreamSynchronize(ctxs[i]->stream);
+        }
+        for (int i = 0; i < ns; i++) {
+            (void)cudaSetDevice(ctxs[i]->device);
+            if (i < (int)d_px.size() && d_px[i]) (void)cudaFree(d_px[i]);
+            if (i < (int)x.size() && x[i]) (void)cudaFree(x[i]);
+            if (i < (int)ev.size() && ev[i]) (void)cudaEventDestroy(ev[i]);
+            if (i < (int)sh.size()) dmmt_shard_destroy(sh[i]);
+        }
+        if (d_file) {
+            (void)cudaSetDevice(ctxs[0]->device);
+            (void)cudaFree(d_file);
+        }
+    }
+};
+
+// every pair of distinct devices of the job can read / write each other's memory
+int enable_peer_access(dmmt_ctx* const* ctxs, int ns, bool* ok) {
+    *ok = true;
+    for (int i = 0; i < ns && *ok; i++)
+        for (int j = 0; j < ns && *ok; j++) {
+            const int di = ctxs[i]->device, dj = ctxs[j]->device;
+            if (di == dj) continue;
+            int can = 0;
+            DMMT_CUDA(cudaDeviceCanAccessPeer(&can, di, dj));
+            if (!can) {
+                *ok = false;
+                break;
+            }
+            DMMT_CUDA(cudaSetDevice(di));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(dj, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+            else if (e != cudaSuccess) DMMT_CUDA(e);
+        }
+    return DMMT_OK;
+}
+
+// stream of shard r waits for the event of shard `of` (recorded on another device's stream of this process)
+int wait_for(ShardedJob& J, int r, int of) {
+    DMMT_CUDA(cudaSetDevice(J.ctxs[r]->device));
+    DMMT_CUDA(cudaStreamWaitEvent(J.ctxs[r]->stream, J.ev[of], 0));
+    return DMMT_OK;
+}
+int record(ShardedJob& J, int r) {
+    DMMT_CUDA(cudaSetDevice(J.ctxs[r]->device));
+    DMMT_CUDA(cudaEventRecord(J.ev[r], J.ctxs[r]->stream));
+    return DMMT_OK;
+}
+// one exchange step: every shard has recorded its event; every stream waits for all of them
+int all_wait_all(ShardedJob& J) {
+    for (int r = 0; r < J.ns; r++)
+        for (int o = 0; o < J.ns; o++)
+            if (o != r) DMMT_TRY(wait_for(J, r, o));
+    return DMMT_OK;
+}
+
+// The five phases with every exchanged value in device memory: asynchronous launches on the contexts' streams,
+// ordered across devices by events, the shards' K4 writing straight into the file on ctxs[0]'s device.  One host
+// synchronisation at the end.  *err receives the first device-side error of any shard.
+int sharded_run_peer(ShardedJob& J, uint64_t* file_len, int* err) {
+    const int n = J.ns;
+    PeerPtrs pp{};
+    auto ptrs = [&](auto member) {
+        for (int j = 0; j < n; j++) pp.p[j] = member(J.x[j]);
+        return pp;
+    };
+    // phase 1 + exchange 1 (last DCs -> predictor seeds of the next shard, categorize.rs:157-161)
+    for (int r = 0; r < n; r++) {
+        DMMT_TRY(dmmt_shard_launch_transform(J.sh[r], J.d_px[r], J.x[r]->last4));
+        DMMT_TRY(record(J, r));
+    }
+    // phase 2 + exchange 2 (sum of the histograms -> image-global tables, transformer.rs:201-217)
+    for (int r = 0; r < n; r++) {
+        if (r) DMMT_TRY(wait_for(J, r, r - 1));
+        DMMT_TRY(dmmt_shard_launch_histogram(J.sh[r], r ? J.x[r - 1]->last4 : nullptr, reinterpret_cast<int64_t*>(J.x[r]->hist)));
+    }
+    for (int r = 0; r < n; r++) DMMT_TRY(record(J, r));
+    DMMT_TRY(all_wait_all(J));
+    ptrs([](ShardXchg* x) { return static_cast<const void*>(x->hist); });
+    for (int r = 0; r < n; r++) {
+        DMMT_CUDA(cudaSetDevice(J.ctxs[r]->device));
+        DMMT_CUDA(launch_peer_exchange(pp, n, 1024, 0, J.x[r]->ghist, J.ctxs[r]->stream));
+        // phase 3 + exchange 3 (bit counts -> global bit offsets)
+        DMMT_TRY(dmmt_shard_launch_tables(J.sh[r], reinterpret_cast<const int64_t*>(J.x[r]->ghist), reinterpret_cast<int64_t*>(&J.x[r]->bits)));
+        DMMT_TRY(record(J, r));
+    }
+    DMMT_TRY(all_wait_all(J));
+    ptrs([](ShardXchg* x) { return static_cast<const void*>(&x->bits); });
+    for (int r = 0; r < n; r++) {
+        DMMT_CUDA(cudaSetDevice(J.ctxs[r]->device));
+        DMMT_CUDA(launch_peer_exchange(pp, n, 1, 2, J.x[r]->all_bits_offs, J.ctxs[r]->stream));
+        // phase 4 + exchange of the trailing partial bytes
+        DMMT_TRY(dmmt_shard_launch_pack(J.sh[r], reinterpret_cast<const int64_t*>(J.x[r]->all_bits_offs + n + r), r == n - 1, J.x[r]->tail2));
+        DMMT_TRY(record(J, r));
+    }
+    DMMT_TRY(all_wait_all(J));
+    ptrs([](ShardXchg* x) { return static_cast<const void*>(x->tail2); });
+    for (int r = 0; r < n; r++) {
+        DMMT_CUDA(cudaSetDevice(J.ctxs[r]->device));
+        DMMT_CUDA(launch_peer_exchange(pp, n, 1, 1, J.x[r]->all_tail2, J.ctxs[r]->stream));
+        // phase 5a + exchange 4 (stuffed byte counts -> byte offsets in the file), BEFORE K4 runs
+        DMMT_TRY(dmmt_shard_launch_count_bytes(J.sh[r], reinterpret_cast<const int32_t*>(J.x[r]->all_tail2),
+                                               reinterpret_cast<const int64_t*>(J.x[r]->all_bits_offs + n),
+                                               reinterpret_cast<const int64_t*>(J.x[r]->all_bits_offs), r, n,
+                                               reinterpret_cast<int64_t*>(&J.x[r]->n_bytes)));
+        DMMT_TRY(record(J, r));
+    }
+    DMMT_TRY(all_wait_all(J));
+    ptrs([](ShardXchg* x) { return static_cast<const void*>(&x->n_bytes); });
+    std::vector<long long> res((size_t)2 * n, 0);
+    for (int r = 0; r < n; r++) {
+        DMMT_CUDA(cudaSetDevice(J.ctxs[r]->device));
+        DMMT_CUDA(launch_peer_exchange(pp, n, 1, 2, J.x[r]->all_n_offs, J.ctxs[r]->stream));
+        // phase 5b: K4 into the file, at the shard's final byte offset (peer stores over NVLink for r > 0)
+        DMMT_TRY(dmmt_shard_launch_stuff_into(J.sh[r], reinterpret_cast<const int64_t*>(J.x[r]->all_bits_offs + n), r, n, J.d_file,
+                                              J.file_cap, reinterpret_cast<const int64_t*>(J.x[r]->all_n_offs + n + r),
+                                              reinterpret_cast<int64_t*>(J.x[r]->res2)));
+        DMMT_CUDA(cudaMemcpyAsync(&res[2 * r], J.x[r]->res2, 16, cudaMemcpyDeviceToHost, J.ctxs[r]->stream));
+    }
+    for (int r = 0; r < n; r++) {  // the only host synchronisation: completion + status of every shard
+        DMMT_CUDA(cudaSetDevice(J.ctxs[r]->device));
+        DMMT_CUDA(cudaStreamSynchronize(J.ctxs[r]->stream));
+    }
+    *err = DMMT_OK;
+    for (int r = 0; r < n; r++)
+        if (res[2 * r + 1]) {
+            *err = (int)res[2 * r + 1];
+            break;
+        }
+    *file_len = (uint64_t)res[2 * (n - 1)];
+    return DMMT_OK;
+}
+
+// Fallback when some pair of devices has no peer access: exchanged values pass through the host (4 synchronisations),
+// the shard outputs are gathered by D2H copies.  *err as above.
+int sharded_run_host(ShardedJob& J, uint8_t** out, uint64_t* out_len, int* err) {
+    const int ns = J.ns;
+    *err = DMMT_OK;
+#define SH_PHASE(expr)                              \
+    do {                                            \
+        const int rc__ = (expr);                    \
+        if (rc__ > DMMT_OK || rc__ == DMMT_E_CUDA || rc__ == DMMT_E_NOMEM || rc__ == DMMT_E_INVALID) return rc__; \
+        if (rc__ != DMMT_OK) {                      \
+            *err = rc__;                            \
+            return DMMT_OK;                         \
+        }                                           \
+    } while (0)
+    std::vector<int16_t> last_dc((size_t)ns * 3), seed((size_t)ns * 3, 0);
+    for (int r = 0; r < ns; r++) SH_PHASE(shard_transform_launch(J.sh[r], J.d_px[r]));
+    for (int r = 0; r < ns; r++) SH_PHASE(shard_transform_collect(J.sh[r], &last_dc[3 * r]));
+    for (int r = 1; r < ns; r++)
+        for (int c = 0; c < 3; c++) seed[3 * r + c] = last_dc[3 * (r - 1) + c];
+    std::vector<uint64_t> h((size_t)1024), g((size_t)1024, 0);
+    for (int r = 0; r < ns; r++) SH_PHASE(shard_histogram_launch(J.sh[r], &seed[3 * r]));
+    for (int r = 0; r < ns; r++) {
+        SH_PHASE(shard_histogram_collect(J.sh[r], h.data()));
+        for (int i = 0; i < 1024; i++) g[i] += h[i];
+    }
+    std::vector<uint64_t> bits((size_t)ns), bit_off((size_t)ns + 1, 0);
+    for (int r = 0; r < ns; r++) SH_PHASE(shard_tables_launch(J.sh[r], g.data()));
+    int first_err = DMMT_OK;
+    for (int r = 0; r < ns; r++) {  // collect from EVERY shard: one of them overflowing must not strand the others
+        const int rc = shard_tables_collect(J.sh[r], &bits[r]);
+        if (rc != DMMT_OK && first_err == DMMT_OK) first_err = rc;
+    }
+    SH_PHASE(first_err);
+    for (int r = 0; r < ns; r++) bit_off[r + 1] = bit_off[r] + bits[r];
+    std::vector<uint8_t> tail((size_t)ns, 0);
+    std::vector<int> tail_n((size_t)ns, 0);
+    for (int r = 0; r < ns; r++) SH_PHASE(shard_pack_launch(J.sh[r], bit_off[r], r == ns - 1));
+    for (int r = 0; r < ns; r++) SH_PHASE(shard_pack_collect(J.sh[r], r == ns - 1, &tail[r], &tail_n[r]));
+    // a shard that does not complete a byte hands its predecessor's bits on
+    for (int r = 1; r < ns; r++)
+        if (r < ns - 1 && (bit_off[r] & 7) + bits[r] < 8) tail[r] |= tail[r - 1];
+    std::vector<const uint8_t*> d_bytes((size_t)ns, nullptr);
+    std::vector<uint64_t> n_bytes((size_t)ns, 0);
+    for (int r = 0; r < ns; r++) SH_PHASE(shard_stuff_launch(J.sh[r], r ? tail[r - 1] : 0, r == 0, r == ns - 1));
+    first_err = DMMT_OK;
+    for (int r = 0; r < ns; r++) {
+        const int rc = shard_stuff_collect(J.sh[r], &d_bytes[r], &n_bytes[r]);
+        if (rc != DMMT_OK && first_err == DMMT_OK) first_err = rc;
+    }
+    SH_PHASE(first_err);
+#undef SH_PHASE
+    uint64_t total = 0;
+    for (int r = 0; r < ns; r++) total += n_bytes[r];
+    uint8_t* buf = static_cast<uint8_t*>(malloc(total ? total : 1));
+    if (!buf) return DMMT_E_NOMEM;
+    uint64_t at = 0;
+    for (int r = 0; r < ns; r++) {
+        cudaError_t e = cudaSetDevice(J.ctxs[r]->device);
+        if (e == cudaSuccess && n_bytes[r])
+            e = cudaMemcpyAsync(buf + at, d_bytes[r], n_bytes[r], cudaMemcpyDeviceToHost, J.ctxs[r]->stream);
+        if (e != cudaSuccess) {
+            dmmt_set_cuda_error(e, "gather of the shard outputs", __FILE__, __LINE__);
+            free(buf);
+            return DMMT_E_CUDA;
+        }
+        at += n_bytes[r];
+    }
+    for (int r = 0; r < ns; r++) {
+        (void)cudaSetDevice(J.ctxs[r]->device);
+        (void)cudaStreamSynchronize(J.ctxs[r]->stream);
+    }
+    *out = buf, *out_len = total;
+    return DMMT_OK;
+}
+}  // namespace
+
 extern "C" int dmmt_encode_sharded(dmmt_ctx* const* ctxs, int nctx, const dmmt_image* im, const dmmt_options* o,
                                    uint8_t** jpeg, size_t* len) {
     if (!ctxs || nctx <= 0 || !im || !o || !jpeg || !len || !im->pixels || o->subsampling > DMMT_P420)
@@ -459,104 +716,69 @@ extern "C" int dmmt_encode_sharded(dmmt_ctx* const* ctxs, int nctx, const dmmt_i
     *jpeg = nullptr, *len = 0;
     if (im->width == 0 || im->height == 0) return DMMT_E_INVALID;
     if (im->pixels_on_device) return DMMT_E_INVALID;  // the shards live on different devices: host pixels only
+    for (int i = 0; i < nctx; i++)
+        if (!ctxs[i]) return DMMT_E_INVALID;
     const int rows = mcu_rows_of(im->height, o->subsampling);
-    const int ns = std::min(nctx, rows);
-    std::vector<dmmt_shard*> sh((size_t)ns, nullptr);
-    std::vector<uint8_t*> d_px((size_t)ns, nullptr);
-    int rc = DMMT_OK;
-    auto cleanup = [&]() {
-        for (int i = 0; i < ns; i++) {
-            if (d_px[i]) {
-                (void)cudaSetDevice(ctxs[i]->device);
-                (void)cudaFree(d_px[i]);
-            }
-            dmmt_shard_destroy(sh[i]);
-        }
-    };
-#define SH_TRY(expr)            \
-    do {                        \
-        rc = (expr);            \
-        if (rc != DMMT_OK) {    \
-            cleanup();          \
-            return rc;          \
-        }                       \
-    } while (0)
-#define SH_CUDA(expr)                                            \
-    do {                                                         \
-        cudaError_t e__ = (expr);                                \
-        if (e__ != cudaSuccess) {                                \
-            dmmt_set_cuda_error(e__, #expr, __FILE__, __LINE__); \
-            cleanup();                                           \
-            return DMMT_E_CUDA;                                  \
-        }                                                        \
-    } while (0)
+    const int ns = std::min(std::min(nctx, rows), DMMT_MAX_PEER_SHARDS);
+    ShardedJob J;
+    J.ctxs = ctxs, J.ns = ns;
+    J.sh.assign((size_t)ns, nullptr), J.d_px.assign((size_t)ns, nullptr), J.x.assign((size_t)ns, nullptr);
+    J.ev.assign((size_t)ns, nullptr);
+    bool peer = false;
+    DMMT_TRY(enable_peer_access(ctxs, ns, &peer));
+    if (const char* e = getenv("DMMT_SHARDED_HOST_EXCHANGE")) peer = peer && e[0] != '1';  // tests: force the fallback
     // MCU rows [r*rows/ns, (r+1)*rows/ns)
     for (int r = 0; r < ns; r++) {
         const int b = (int)((long long)r * rows / ns), e = (int)((long long)(r + 1) * rows / ns);
-        SH_TRY(dmmt_shard_create(ctxs[r], im->width, im->height, im->fmt, im->max_value, o, b, e, &sh[r]));
-        SH_CUDA(cudaSetDevice(ctxs[r]->device));
-        SH_CUDA(cudaMalloc(&d_px[r], dmmt_shard_pixel_bytes(sh[r])));
-        SH_CUDA(cudaMemcpyAsync(d_px[r], static_cast<const uint8_t*>(im->pixels) + dmmt_shard_pixel_offset(sh[r]),
-                                dmmt_shard_pixel_bytes(sh[r]), cudaMemcpyHostToDevice, ctxs[r]->stream));
+        DMMT_TRY(dmmt_shard_create(ctxs[r], im->width, im->height, im->fmt, im->max_value, o, b, e, &J.sh[r]));
+        DMMT_CUDA(cudaSetDevice(ctxs[r]->device));
+        DMMT_CUDA(cudaMalloc(&J.d_px[r], dmmt_shard_pixel_bytes(J.sh[r])));
+        DMMT_CUDA(cudaMalloc(&J.x[r], sizeof(ShardXchg)));
+        DMMT_CUDA(cudaEventCreateWithFlags(&J.ev[r], cudaEventDisableTiming));
+        DMMT_CUDA(cudaMemcpyAsync(J.d_px[r], static_cast<const uint8_t*>(im->pixels) + dmmt_shard_pixel_offset(J.sh[r]),
+                                  dmmt_shard_pixel_bytes(J.sh[r]), cudaMemcpyHostToDevice, ctxs[r]->stream));
     }
-    // phase 1 on all shards, then exchange 1 (last DCs)
-    std::vector<int16_t> last_dc((size_t)ns * 3), seed((size_t)ns * 3, 0);
-    for (int r = 0; r < ns; r++) SH_TRY(shard_transform_launch(sh[r], d_px[r]));
-    for (int r = 0; r < ns; r++) SH_TRY(shard_transform_collect(sh[r], &last_dc[3 * r]));
-    for (int r = 1; r < ns; r++)
-        for (int c = 0; c < 3; c++) seed[3 * r + c] = last_dc[3 * (r - 1) + c];
-    // phase 2, exchange 2 (histogram sum)
-    std::vector<uint64_t> h((size_t)1024), g((size_t)1024, 0);
-    for (int r = 0; r < ns; r++) SH_TRY(shard_histogram_launch(sh[r], &seed[3 * r]));
-    for (int r = 0; r < ns; r++) {
-        SH_TRY(shard_histogram_collect(sh[r], h.data()));
-        for (int i = 0; i < 1024; i++) g[i] += h[i];
-    }
-    // phase 3, exchange 3 (bit counts -> global bit offsets)
-    std::vector<uint64_t> bits((size_t)ns), bit_off((size_t)ns + 1, 0);
-    for (int r = 0; r < ns; r++) SH_TRY(shard_tables_launch(sh[r], g.data()));
-    for (int r = 0; r < ns; r++) SH_TRY(shard_tables_collect(sh[r], &bits[r]));
-    for (int r = 0; r < ns; r++) bit_off[r + 1] = bit_off[r] + bits[r];
-    // phase 4 (+ tails)
-    std::vector<uint8_t> tail((size_t)ns, 0);
-    std::vector<int> tail_n((size_t)ns, 0);
-    for (int r = 0; r < ns; r++) SH_TRY(shard_pack_launch(sh[r], bit_off[r], r == ns - 1));
-    for (int r = 0; r < ns; r++) SH_TRY(shard_pack_collect(sh[r], r == ns - 1, &tail[r], &tail_n[r]));
-    // a shard that does not complete a byte hands its predecessor's bits on
-    for (int r = 1; r < ns; r++)
-        if (r < ns - 1 && (bit_off[r] & 7) + bits[r] < 8) tail[r] |= tail[r - 1];
-    // phase 5, exchange 4 (byte counts)
-    std::vector<const uint8_t*> d_bytes((size_t)ns, nullptr);
-    std::vector<uint64_t> n_bytes((size_t)ns, 0);
-    for (int r = 0; r < ns; r++) SH_TRY(shard_stuff_launch(sh[r], r ? tail[r - 1] : 0, r == 0, r == ns - 1));
-    for (int r = 0; r < ns; r++) SH_TRY(shard_stuff_collect(sh[r], &d_bytes[r], &n_bytes[r]));
-    uint64_t total = 0;
-    for (int r = 0; r < ns; r++) total += n_bytes[r];
-    uint8_t* buf = static_cast<uint8_t*>(malloc(total ? total : 1));
-    if (!buf) {
-        cleanup();
-        return DMMT_E_NOMEM;
-    }
-    uint64_t at = 0;
-    for (int r = 0; r < ns; r++) {
-        cudaError_t e = cudaSetDevice(ctxs[r]->device);
-        if (e == cudaSuccess && n_bytes[r])
-            e = cudaMemcpyAsync(buf + at, d_bytes[r], n_bytes[r], cudaMemcpyDeviceToHost, ctxs[r]->stream);
-        if (e != cudaSuccess) {
-            dmmt_set_cuda_error(e, "gather of the shard outputs", __FILE__, __LINE__);
-            free(buf);
-            cleanup();
-            return DMMT_E_CUDA;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        int err = DMMT_OK;
+        uint8_t* buf = nullptr;
+        uint64_t total = 0;
+        if (peer) {
+            if (!J.d_file) {
+                for (int r = 0; r < ns; r++) J.file_cap += dmmt_shard_out_stride(J.sh[r]);
+                DMMT_CUDA(cudaSetDevice(ctxs[0]->device));
+                DMMT_CUDA(cudaMalloc(&J.d_file, J.file_cap));
+            }
+            DMMT_TRY(sharded_run_peer(J, &total, &err));
+            if (err == DMMT_OK) {
+                buf = static_cast<uint8_t*>(malloc(total ? total : 1));
+                if (!buf) return DMMT_E_NOMEM;
+                DMMT_CUDA(cudaSetDevice(ctxs[0]->device));
+                const cudaError_t e = cudaMemcpy(buf, J.d_file, total, cudaMemcpyDeviceToHost);
+                if (e != cudaSuccess) {
+                    free(buf);
+                    DMMT_CUDA(e);
+                }
+            }
+        } else {
+            DMMT_TRY(sharded_run_host(J, &buf, &total, &err));
         }
-        at += n_bytes[r];
+        if (err == DMMT_OK) {
+            *jpeg = buf, *len = (size_t)total;
+            return DMMT_OK;
+        }
+        if (err != DMMT_E_OVERFLOW || attempt == 1) return err;
+        // denser than the default 128 B per block somewhere (the reference encodes any input): every shard gets the
+        // worst-case capacity and the phases run again from the transform
+        for (int r = 0; r < ns; r++) {
+            DMMT_CUDA(cudaSetDevice(ctxs[r]->device));
+            DMMT_CUDA(cudaStreamSynchronize(ctxs[r]->stream));
+        }
+        for (int r = 0; r < ns; r++) DMMT_TRY(dmmt_shard_set_scan_capacity(J.sh[r], dmmt_shard_worst_case_scan_bytes(J.sh[r])));
+        if (J.d_file) {
+            DMMT_CUDA(cudaSetDevice(ctxs[0]->device));
+            DMMT_CUDA(cudaFree(J.d_file));
+            J.d_file = nullptr, J.file_cap = 0;
+        }
     }
-    for (int r = 0; r < ns; r++) {
-        (void)cudaSetDevice(ctxs[r]->device);
-        (void)cudaStreamSynchronize(ctxs[r]->stream);
-    }
-    cleanup();
-    *jpeg = buf, *len = (size_t)total;
-    return DMMT_OK;
-#undef SH_TRY
-#undef SH_CUDA
+    return DMMT_E_OVERFLOW;
 }

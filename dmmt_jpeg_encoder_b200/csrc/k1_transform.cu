@@ -584,7 +584,7 @@ __device__ __forceinline__ void fast_arai2(f2 x0, f2 x1, f2 x2, f2 x3, f2 x4, f2
 }
 
 #ifndef K1_I2FP
-#define K1_I2FP 0   // bit ch set: channel ch of u8 input is converted by PRMT + I2FP.F32.U32 (integer pipe) instead of I2F.U8
+#define K1_I2FP 2   // bit ch set: channel ch of u8 input is converted by PRMT + I2FP.F32.U32 (integer pipe) instead of I2F.U8
 #endif
 // raw sample i (0..47) of a strip row as f32 (before normalisation)
 template <int FMT, int NW>
@@ -897,9 +897,6 @@ constexpr int SH_YDC = 0, SH_CDC = 16, SH_YAC = 32, SH_CAC = 288, SH_BINS = 544;
 #ifndef K1_HUNROLL
 #define K1_HUNROLL 0
 #endif
-#ifndef K1_PF
-#define K1_PF 0      // > 0: L2 prefetch of the tile K1_PF images ahead
-#endif
 // CTA = 96 threads = 3 warps, every one of them busy in every phase: 8 CTAs (24 warps) per SM at 80 registers.
 template <int FMT, bool FUSED, bool VEC>
 __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transform_p420(const __grid_constant__ K1Args a) {
@@ -926,22 +923,6 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
     const int tile_x = blockIdx.x, mrow = blockIdx.y, img = blockIdx.z;
     const uint8_t* __restrict__ pix = a.pixels + (size_t)img * a.img_stride_bytes;
     const size_t pitch = (size_t)a.W * Px<FMT>::kBytes;
-#if K1_PF > 0
-    // The pixel rows of the tile at the same place K1_PF images further on -- the CTA that takes them starts about one
-    // CTA lifetime from now (CTAs are issued x, then y, then image; an SM set holds ~2 frames of 1080p tiles) -- are
-    // requested into L2 now: one 128-byte line per thread covers the 16 rows x 768 B of a u8 tile, so the first
-    // strips of that CTA wait for L2, not for DRAM.
-    if (img + K1_PF < (int)gridDim.z) {
-        constexpr int LPR = (TILE_W * Px<FMT>::kBytes + 127) / 128;   // lines per tile row
-        for (int t = threadIdx.x; t < 16 * LPR; t += P420_THREADS) {
-            const int r = t / LPR, l = t - r * LPR;
-            const int y = mrow * 16 + r;
-            const size_t xoff = (size_t)tile_x * TILE_W * Px<FMT>::kBytes + (size_t)l * 128;
-            if (y < a.H && xoff < pitch)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(pix + (size_t)K1_PF * a.img_stride_bytes + (size_t)y * pitch + xoff));
-        }
-    }
-#endif
 
     // ---------------- phase A: strip = 8 px x 2 rows, both rows packed in one register pair ----------------
     // 256 strips per tile = 8 row pairs x 32 strips; a warp takes one whole row pair per round (rounds 0-1: all

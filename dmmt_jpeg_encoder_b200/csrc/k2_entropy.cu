@@ -933,6 +933,9 @@ struct K4Args {
     // peer-memory gather: `out` is the whole file (possibly another device's memory) and the shard's
     // bytes start *base_src bytes into it (after the header on the first shard)
     const unsigned long long* base_src;
+    // what an output slot that is too small is reported as: DMMT_E_OVERFLOW when the slot is the plan's own (its size
+    // follows from the scan capacity: the caller grows the plan and retries), DMMT_E_WRITE for a caller-sized file
+    int slot_err;
 };
 
 constexpr int K4_ROW = K4_BYTES_PER_THREAD + 16;              // padded row: conflict-free 128-bit access
@@ -1030,7 +1033,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_stuff(const K4Args a) {
         if (gs + n_out + 2ull > a.out_stride) {
             // Error::FailedToWriteImageData: the image's slot of the output arena is too small
             if (tid == 0) {
-                atomicCAS(&meta->error, 0, DMMT_E_WRITE);
+                atomicCAS(&meta->error, 0, a.slot_err);
                 if (last) {
                     meta->out_len = 0ull;
                     if (a.out_lens) a.out_lens[img] = 0ull;
@@ -1279,7 +1282,8 @@ cudaError_t launch_k3(uint32_t n_chunks, uint32_t n_segs, int n, const TokBuf& t
 cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStream_t st) {
     K4Args a{h.scan, h.scan_stride_bytes, h.meta, h.lb_state, h.ticket, h.max_chunks, h.out, h.out_stride,
              h.out_lens, h.first_byte, h.n_bytes_override, h.seed_bits, h.prepend_header, h.append_eoi,
-             h.or_first_byte, h.seed_src, h.owned_mode, h.or_first_src, h.base_src};
+             h.or_first_byte, h.seed_src, h.owned_mode, h.or_first_src, h.base_src,
+             h.base_src ? DMMT_E_WRITE : DMMT_E_OVERFLOW};
     // CTAs take chunks by ticket, so the grid only has to keep the device busy: about 8 CTAs per SM
     // over all images, never more than the chunks an image can have
     uint32_t per_image = (uint32_t)((sm_count() * 8 + n - 1) / n);
@@ -1293,11 +1297,12 @@ cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStre
 // ---- device-resident shard exchange helpers (dmmt_shard.cu) ------------------------------------
 namespace {
 __global__ void k_shard_widen(const int16_t* last_dc3, int* out4, const unsigned int* hist, long long* hist64,
-                              const ImgMeta* meta, long long* bits_out) {
+                              const ImgMeta* meta, long long* bits_out, long long* err_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (last_dc3 && i < 4) out4[i] = i < 3 ? (int)last_dc3[i] : 0;
     if (hist && i < 1024) hist64[i] = (long long)hist[i];
     if (bits_out && i == 0) *bits_out = (long long)meta->scan_bits;
+    if (err_out && i == 0) *err_out = (long long)meta->error;
 }
 __global__ void k_shard_narrow_seed(const int* seed4, int16_t* seed3) {
     if (threadIdx.x < 3) seed3[threadIdx.x] = seed4 ? (int16_t)seed4[threadIdx.x] : (int16_t)0;
@@ -1375,7 +1380,35 @@ __global__ void k_shard_result(const ImgMeta* meta, long long* out2) {
     out2[0] = (long long)meta->out_len;
     out2[1] = (long long)meta->error;
 }
+// ---- single-process exchange over peer memory (dmmt_encode_sharded): every shard reads the values of the other
+// shards straight from their devices (peer access over NVLink), so an exchange is one tiny kernel per shard
+// instead of a host round trip.  mode 0: out[i] = sum over shards of src_j[i] (i < elems: the 4 histograms);
+// mode 1: out[j * elems + i] = src_j[i] (all-gather); mode 2 (elems == 1): all-gather, then out[n + j] = the
+// exclusive prefix sum over the shards.
+__global__ void k_peer_exchange(PeerPtrs srcs, int n, int elems, int mode, long long* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode == 0) {
+        if (i >= elems) return;
+        long long acc = 0;
+        for (int j = 0; j < n; j++) acc += static_cast<const long long*>(srcs.p[j])[i];
+        out[i] = acc;
+    } else {
+        if (i < n * elems) out[i] = static_cast<const long long*>(srcs.p[i / elems])[i % elems];
+        if (mode == 2 && i == 0) {
+            long long run = 0;
+            for (int j = 0; j < n; j++) {
+                out[n + j] = run;
+                run += *static_cast<const long long*>(srcs.p[j]);
+            }
+        }
+    }
+}
 }  // namespace
+cudaError_t launch_peer_exchange(const PeerPtrs& srcs, int n, int elems, int mode, long long* out, cudaStream_t st) {
+    const int work = mode == 0 ? elems : n * elems;
+    k_peer_exchange<<<(work + 255) / 256, 256, 0, st>>>(srcs, n, elems, mode, out);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_shard_count_bytes(const uint8_t* scan, const ImgMeta* meta, const unsigned long long* seed_src,
                                      int owned_mode, const int* or_first_src, int is_first, int is_last,
@@ -1395,8 +1428,8 @@ cudaError_t launch_shard_result(const ImgMeta* meta, long long* out2, cudaStream
 }
 
 cudaError_t launch_shard_widen(const int16_t* last_dc3, int* out4, const unsigned int* hist, long long* hist64,
-                               const ImgMeta* meta, long long* bits_out, cudaStream_t st) {
-    k_shard_widen<<<4, 256, 0, st>>>(last_dc3, out4, hist, hist64, meta, bits_out);
+                               const ImgMeta* meta, long long* bits_out, cudaStream_t st, long long* err_out) {
+    k_shard_widen<<<4, 256, 0, st>>>(last_dc3, out4, hist, hist64, meta, bits_out, err_out);
     return cudaGetLastError();
 }
 cudaError_t launch_shard_narrow_seed(const int* seed4, int16_t* seed3, cudaStream_t st) {

@@ -196,6 +196,13 @@ class Plan:
             F.lib().dmmt_free(outs[i])
         return res
 
+    def encode_host_into(self, h_pixels: int, n: int, h_out: int, out_cap: int, offsets: np.ndarray, lens: np.ndarray):
+        """dmmt_plan_encode_host_into: host pixels (pointer, ideally pinned) -> packed files in the caller's host arena."""
+        assert offsets.dtype == np.uint64 and lens.dtype == np.uint64 and len(offsets) >= n and len(lens) >= n
+        F.check(F.lib().dmmt_plan_encode_host_into(self._h, C.c_void_p(h_pixels), n, C.c_void_p(h_out), out_cap,
+                                                   offsets.ctypes.data_as(F._U64P), lens.ctypes.data_as(F._U64P)),
+                "dmmt_plan_encode_host_into")
+
     def fetch(self, what: int, index: int = 0):
         L = F.lib()
         got = C.c_size_t()
@@ -203,6 +210,10 @@ class Plan:
             m = F.Meta()
             F.check(L.dmmt_plan_fetch(self._h, what, index, C.byref(m), C.sizeof(m), C.byref(got)), "dmmt_plan_fetch")
             return m
+        if what == F.FETCH_TOKEN_COUNT:
+            n = C.c_uint64()
+            F.check(L.dmmt_plan_fetch(self._h, what, index, C.byref(n), 8, C.byref(got)), "dmmt_plan_fetch")
+            return int(n.value)
         if what == F.FETCH_COEF:
             a = np.empty((self.stream_blocks, 64), np.int16)
         elif what == F.FETCH_HIST:

@@ -45,6 +45,7 @@ class ShardBackend:
     def tables(self, global_hist: np.ndarray) -> int: ...                    # -> local bits
     def pack(self, global_bit_offset: int, is_last: bool) -> tuple[int, int]: ...  # -> tail byte, nbits
     def stuff(self, prev_tail: int, prev_nbits: int, is_first: bool, is_last: bool) -> torch.Tensor: ...
+    def grow(self) -> None: ...                                              # worst-case capacity after an overflow
 
 
 class _DevPtr:
@@ -141,6 +142,15 @@ class CudaShardBackend(ShardBackend):
                                                      capacity, C.c_void_p(d_byte_offset), C.c_void_p(d_result2)),
                 "dmmt_shard_launch_stuff_into")
 
+    def launch_error(self, d_err: int):
+        F.check(F.lib().dmmt_shard_launch_error(self._h, C.c_void_p(d_err)), "dmmt_shard_launch_error")
+
+    def grow(self):
+        """worst-case scan capacity (after DMMT_E_OVERFLOW on ANY shard of the image; every rank calls it)"""
+        F.check(F.lib().dmmt_shard_set_scan_capacity(self._h, F.lib().dmmt_shard_worst_case_scan_bytes(self._h)),
+                "dmmt_shard_set_scan_capacity")
+        self._xbuf = self._pbuf = None
+
     @property
     def out_stride(self) -> int:
         return F.lib().dmmt_shard_out_stride(self._h)
@@ -160,39 +170,82 @@ class CudaShardBackend(ShardBackend):
             pass
 
 
+class _Phases:
+    """Runs the local phases of one rank so that a failure never strands the other ranks in a collective: the error
+    code of a failed phase rides on the NEXT exchange (an extra slot of its payload), every rank sees the codes of
+    all ranks and raises the same DmmtError -- or, for DMMT_E_OVERFLOW, grows its shard and runs again."""
+
+    def __init__(self):
+        self.err = 0
+
+    def run(self, fn, *args, default=None):
+        if self.err:
+            return default                      # already failed: keep going through the collectives with dummies
+        try:
+            return fn(*args)
+        except F.DmmtError as e:
+            self.err = e.code
+            return default
+
+
+def _raise_first(codes, where):
+    for c in codes:
+        if c:
+            raise F.DmmtError(int(c), where)
+
+
 def encode_sharded(backend: ShardBackend, device: torch.device, group=None, dst: int = 0,
                    timings: dict | None = None, to_host: bool = True):
     """Runs the phases of this rank's shard with the four exchanges; returns the file on `dst`
-    (bytes, or the uint8 tensor on `device` when to_host is False) and None on the other ranks."""
+    (bytes, or the uint8 tensor on `device` when to_host is False) and None on the other ranks.
+    A device-side failure of any shard raises the same DmmtError on EVERY rank; an overflow of the default scan
+    capacity makes every rank grow its shard to the worst case and run the phases once more."""
+    for attempt in range(2):
+        try:
+            return _encode_sharded_once(backend, device, group, dst, timings, to_host)
+        except F.DmmtError as e:
+            if e.code != F.E_OVERFLOW or attempt:
+                raise
+            backend.grow()                       # every rank arrives here: the code was all-gathered
+
+
+def _encode_sharded_once(backend, device, group, dst, timings, to_host):
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     is_first, is_last = rank == 0, rank == world - 1
+    ph = _Phases()
+
+    def gather(values):
+        """all-gather of this rank's int64 values + its error code; raises on every rank if any rank failed"""
+        t = torch.tensor(list(values) + [ph.err], dtype=torch.int64, device=device)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t, group=group)
+        rows = [x.cpu().tolist() for x in out]
+        _raise_first([r[-1] for r in rows], "sharded encode")
+        return [r[:-1] for r in rows]
 
     # phase 1 + exchange 1: DC predictor seeds (categorize.rs:157-161 never resets the chain)
-    last_dc = torch.from_numpy(backend.transform().astype(np.int64)).to(device)
-    all_dc = [torch.empty_like(last_dc) for _ in range(world)]
-    dist.all_gather(all_dc, last_dc, group=group)
-    seed = all_dc[rank - 1].cpu().numpy().astype(np.int16) if rank else np.zeros(3, np.int16)
+    last_dc = ph.run(backend.transform, default=np.zeros(3, np.int16))
+    all_dc = gather([int(v) for v in last_dc])
+    seed = np.array(all_dc[rank - 1], np.int16) if rank else np.zeros(3, np.int16)
 
-    # phase 2 + exchange 2: image-global histograms (transformer.rs:201-217)
-    hist = torch.from_numpy(backend.histogram(seed).astype(np.int64)).to(device)
+    # phase 2 + exchange 2: image-global histograms (transformer.rs:201-217); the error slot is summed too
+    h = ph.run(backend.histogram, seed, default=np.zeros(1024, np.uint64))
+    hist = torch.cat([torch.from_numpy(np.asarray(h).astype(np.int64)), torch.tensor([1 if ph.err else 0])]).to(device)
     dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    failed = int(hist[-1].item()) != 0
+    if failed:
+        gather([])                               # somebody failed: this exchange tells every rank the code and raises
 
     # phase 3 + exchange 3: bit offsets
-    bits = backend.tables(hist.cpu().numpy().astype(np.uint64))
-    t = torch.tensor([bits], dtype=torch.int64, device=device)
-    all_bits = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(all_bits, t, group=group)
-    all_bits = [int(x.item()) for x in all_bits]
+    bits = ph.run(backend.tables, hist[:-1].cpu().numpy().astype(np.uint64), default=0)
+    all_bits = [r[0] for r in gather([bits])]
     bit_off = [0]
     for b in all_bits:
         bit_off.append(bit_off[-1] + b)
 
     # phase 4 + exchange of the trailing partial bytes
-    tail_byte, tail_nbits = backend.pack(bit_off[rank], is_last)
-    t = torch.tensor([tail_byte, tail_nbits], dtype=torch.int64, device=device)
-    all_tail = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(all_tail, t, group=group)
-    tails = [int(x[0].item()) for x in all_tail]
+    tail_byte, tail_nbits = ph.run(backend.pack, bit_off[rank], is_last, default=(0, 0))
+    tails = [r[0] for r in gather([tail_byte, tail_nbits])]
     # a shard that does not complete a byte hands its predecessor's bits on
     for r in range(1, world - 1):
         if (bit_off[r] & 7) + all_bits[r] < 8:
@@ -201,11 +254,8 @@ def encode_sharded(backend: ShardBackend, device: torch.device, group=None, dst:
     prev_nbits = bit_off[rank] & 7
 
     # phase 5 + exchange 4: byte counts, then the bytes travel to dst
-    mine = backend.stuff(prev_tail, prev_nbits, is_first, is_last)
-    t = torch.tensor([mine.numel()], dtype=torch.int64, device=device)
-    all_n = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(all_n, t, group=group)
-    all_n = [int(x.item()) for x in all_n]
+    mine = ph.run(backend.stuff, prev_tail, prev_nbits, is_first, is_last, default=torch.empty(0, dtype=torch.uint8))
+    all_n = [r[0] for r in gather([mine.numel()])]
     if timings is not None:
         timings["bytes"] = all_n
         timings["bits"] = all_bits
@@ -225,11 +275,32 @@ def encode_sharded(backend: ShardBackend, device: torch.device, group=None, dst:
     return None
 
 
+def _retry_on_overflow(fn, backend, *args, **kw):
+    """fn raises the same DmmtError on every rank (the codes were all-gathered); on DMMT_E_OVERFLOW every rank grows
+    its shard to the worst-case capacity (and the peer file with it) and the phases run once more"""
+    for attempt in range(2):
+        try:
+            return fn(backend, *args, **kw)
+        except F.DmmtError as e:
+            if e.code != F.E_OVERFLOW or attempt:
+                raise
+            backend.grow()
+            for a in args:
+                if isinstance(a, PeerFile):
+                    a.regrow(backend)
+
+
 def encode_sharded_device(backend: CudaShardBackend, group=None, dst: int = 0, to_host: bool = True, mark=None):
     """Same result as encode_sharded, but every exchanged value stays in device memory: the five phases are
     asynchronous launches on the context's stream (which must be torch's current stream) and the collectives
     are NCCL calls on device tensors, so there is ONE host synchronisation in the whole encode (the byte
-    counts, needed to size the final send / recv).  The small exchange tensors are cached on the backend."""
+    counts, needed to size the final send / recv).  The small exchange tensors are cached on the backend.
+    Every rank's device error flag is all-gathered with the byte counts: a failed shard raises on every rank
+    (overflow: every rank grows its shard and the phases run once more)."""
+    return _retry_on_overflow(_encode_sharded_device_once, backend, group, dst, to_host, mark)
+
+
+def _encode_sharded_device_once(backend: CudaShardBackend, group=None, dst: int = 0, to_host: bool = True, mark=None):
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = torch.device("cuda", backend.ctx.device)
     buf = getattr(backend, "_xbuf", None)
@@ -239,7 +310,7 @@ def encode_sharded_device(backend: CudaShardBackend, group=None, dst: int = 0, t
                                "hist": torch.empty(1024, **i64), "bits": torch.empty(1, **i64),
                                "all_bits": torch.empty(world, **i64), "offs": torch.empty(world, **i64),
                                "tail": torch.empty(2, **i32), "all_tail": torch.empty(2 * world, **i32),
-                               "n_bytes": torch.empty(1, **i64), "all_n": torch.empty(world, **i64)}
+                               "n_bytes": torch.zeros(2, **i64), "all_n": torch.empty(2 * world, **i64)}
     b = buf
     mark = mark or (lambda name: None)                                           # optional phase probe (tools/bench_sharded.py)
     backend.launch_transform(b["last"].data_ptr())
@@ -258,12 +329,13 @@ def encode_sharded_device(backend: CudaShardBackend, group=None, dst: int = 0, t
     mark("pack")
     d_bytes = backend.launch_stuff(b["all_tail"].data_ptr(), b["offs"].data_ptr(), b["all_bits"].data_ptr(), rank, world,
                                    b["n_bytes"].data_ptr())
-    dist.all_gather_into_tensor(b["all_n"], b["n_bytes"], group=group)           # exchange 4: byte counts
+    backend.launch_error(b["n_bytes"].data_ptr() + 8)                            # {byte count, device error flag}
+    dist.all_gather_into_tensor(b["all_n"], b["n_bytes"], group=group)           # exchange 4: byte counts + status
     mark("stuff")
-    sizes = b["all_n"].tolist()                                                  # the only host synchronisation
+    res = b["all_n"].tolist()                                                    # the only host synchronisation
     mark("sync")
-    if min(sizes) <= 0:
-        backend.status()                                                         # a shard failed: raise its error
+    _raise_first(res[1::2], "sharded encode (device-resident exchange)")         # the same error on every rank
+    sizes = res[0::2]
     mine = (torch.as_tensor(_DevPtr(d_bytes, sizes[rank]), device=dev) if sizes[rank]
             else torch.empty(0, dtype=torch.uint8, device=dev))
     if rank == dst:
@@ -296,19 +368,37 @@ class PeerFile:
     def __init__(self, backend: CudaShardBackend, group=None, dst: int = 0, capacity: int | None = None):
         self.ctx, self.group, self.dst = backend.ctx, group, dst
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        strides = [None] * self.world
-        dist.all_gather_object(strides, int(backend.out_stride), group=group)
-        self.capacity = int(capacity) if capacity else sum(strides)
         self._ptr = C.c_void_p()
+        self.capacity = 0
+        self._allocate(int(capacity) if capacity else self._sum_of_strides(backend))
+
+    def _sum_of_strides(self, backend: CudaShardBackend) -> int:
+        strides = [None] * self.world
+        dist.all_gather_object(strides, int(backend.out_stride), group=self.group)
+        return sum(strides)
+
+    def _allocate(self, capacity: int):
+        self.capacity = capacity
         box = [None]
-        if self.rank == dst:
+        if self.rank == self.dst:
             F.check(F.lib().dmmt_device_alloc(self.ctx.handle, self.capacity, C.byref(self._ptr)), "dmmt_device_alloc")
             h = C.create_string_buffer(64)
             F.check(F.lib().dmmt_peer_export(self.ctx.handle, self._ptr, h), "dmmt_peer_export")
             box[0] = h.raw
-        dist.broadcast_object_list(box, src=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
-        if self.rank != dst:
+        src = dist.get_global_rank(self.group, self.dst) if self.group is not None else self.dst
+        dist.broadcast_object_list(box, src=src, group=self.group)
+        if self.rank != self.dst:
             F.check(F.lib().dmmt_peer_open(self.ctx.handle, box[0], C.byref(self._ptr)), "dmmt_peer_open")
+
+    def regrow(self, backend: CudaShardBackend):
+        """Collective: after the shards' scan capacity has grown, the file must hold the larger worst case too."""
+        need = self._sum_of_strides(backend)
+        if need > self.capacity:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)       # nobody still writes through the old mapping
+            self.close()
+            dist.barrier(group=self.group)       # every mapping is closed before the owner's next allocation is exported
+            self._allocate(need)
 
     @property
     def ptr(self) -> int:
@@ -336,6 +426,11 @@ class PeerFile:
 
 
 def encode_sharded_peer(backend: CudaShardBackend, file: PeerFile, to_host: bool = True, mark=None):
+    """see _encode_sharded_peer_once; DMMT_E_OVERFLOW on any shard: every rank grows its shard, runs once more"""
+    return _retry_on_overflow(_encode_sharded_peer_once, backend, file, to_host, mark)
+
+
+def _encode_sharded_peer_once(backend: CudaShardBackend, file: PeerFile, to_host: bool = True, mark=None):
     """encode_sharded_device without the gather: after the tail exchange every shard counts its stuffed bytes
     (phase 5a), the counts are all-gathered and summed, and K4 (phase 5b) writes straight into `file` at the
     shard's final offset -- on the destination rank's own memory or, from the other ranks, over NVLink.  The
@@ -381,9 +476,7 @@ def encode_sharded_peer(backend: CudaShardBackend, file: PeerFile, to_host: bool
     mark("stuff")
     res = b["all_res"].tolist()                                                  # the only host synchronisation
     mark("sync")
-    errs = [int(e) for e in res[1::2] if e]
-    if errs:
-        F.check(errs[0], "sharded encode (peer gather)")
+    _raise_first(res[1::2], "sharded encode (peer gather)")                      # the same error on every rank
     if rank != dst:
         return None
     out = file.tensor(int(res[2 * (world - 1)]))

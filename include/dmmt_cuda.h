@@ -30,7 +30,10 @@ extern "C" {
 #define DMMT_E_CUDA (-3)      /* CUDA runtime failure (see dmmt_last_cuda_error) */
 #define DMMT_E_NCCL (-4)      /* collective failure in the sharded path */
 #define DMMT_E_NOMEM (-5)     /* host or device allocation failed */
-#define DMMT_E_OVERFLOW (-6)  /* entropy-coded scan exceeded the plan's scan capacity (retry with dmmt_plan_set_scan_capacity) */
+#define DMMT_E_OVERFLOW (-6)  /* entropy-coded scan exceeded the plan's scan capacity, or its stuffed form the plan's output slot
+                               * (sized from that capacity): retry with dmmt_plan_set_scan_capacity(worst case), which also
+                               * sizes the slot for a scan of nothing but 0xFF bytes.  dmmt_encode, dmmt_plan_encode_host*,
+                               * dmmt_encode_sharded and the Python drivers do this themselves. */
 #define DMMT_E_SYMBOL (-7)    /* Error::HuffmanSymbolNotPresentInTranslator (error.rs:21) */
 #define DMMT_E_RANGE (-8)     /* coefficient not categorisable (categorize.rs:25-30 panics on -32768) */
 #define DMMT_E_WRITE (-9)     /* Error::FailedToWriteImageData / FailedToWriteBlock family: output arena too small */
@@ -91,7 +94,12 @@ int dmmt_encode(dmmt_ctx *, const dmmt_image *, const dmmt_options *, uint8_t **
 int dmmt_encode_batch(dmmt_ctx *const *ctxs, int nctx, const dmmt_image *imgs, int n,
                       const dmmt_options *, uint8_t **jpegs, size_t *lens);
 /* One large image split by MCU rows over nctx devices of this process (single-process
- * multi-device; the one-process-per-GPU variant is the dmmt_shard_* API below). */
+ * multi-device; the one-process-per-GPU variant is the dmmt_shard_* API below).  With peer access
+ * between the devices (NVLink / NVSwitch) every exchanged value stays in device memory: the shards
+ * read each other's last DCs, histograms, bit counts, tails and byte counts over peer loads, K4 of
+ * every shard stores straight into the file on ctxs[0]'s device, and there is ONE host
+ * synchronisation; without peer access the values pass through the host.  Retries once with the
+ * worst-case scan capacity on DMMT_E_OVERFLOW, like dmmt_encode. */
 int dmmt_encode_sharded(dmmt_ctx *const *ctxs, int nctx, const dmmt_image *, const dmmt_options *,
                         uint8_t **jpeg, size_t *len);
 void dmmt_free(void *);
@@ -181,6 +189,7 @@ int dmmt_plan_last_launch_count(const dmmt_plan *);
 #define DMMT_FETCH_TABLES 2    /* u8  [2][4][256]: symbols[4][256] then lengths[4][256], each table in the reference's Vec<SymbolCodeLength> order; counts via DMMT_FETCH_META */
 #define DMMT_FETCH_SCAN 3      /* unstuffed, 1-padded scan bytes */
 #define DMMT_FETCH_META 4      /* dmmt_image_meta */
+#define DMMT_FETCH_TOKEN_COUNT 5 /* u64: tokens (4 bytes each) the transform / tokenise stage wrote for this image */
 typedef struct {
     uint64_t scan_bits;        /* entropy-coded bits before padding */
     uint64_t out_len;          /* whole file length */
@@ -226,6 +235,11 @@ int dmmt_shard_pack(dmmt_shard *, uint64_t global_bit_offset, int is_last, uint8
 int dmmt_shard_stuff(dmmt_shard *, uint8_t prev_tail_byte, int prev_tail_nbits, int is_first,
                      int is_last, const uint8_t **d_bytes, uint64_t *n_bytes);
 
+/* Scan capacity of a shard (see dmmt_plan_set_scan_capacity).  A phase that reports DMMT_E_OVERFLOW means: give EVERY
+ * shard of the image dmmt_shard_worst_case_scan_bytes() and run the phases again from the transform.  The decision
+ * must be taken by all ranks together (all-reduce the status), dmmt_encode_sharded and sharded.py do so. */
+int dmmt_shard_set_scan_capacity(dmmt_shard *, size_t bytes);
+size_t dmmt_shard_worst_case_scan_bytes(const dmmt_shard *);
 int dmmt_shard_launch_count(const dmmt_shard *);  /* kernels launched by the phases so far */
 /* Device-resident exchange: the same five phases, ASYNCHRONOUS on the context's stream, with every exchanged
  * value in device memory, so the caller's collectives (NCCL all-gather / all-reduce on the same stream) need
@@ -240,6 +254,9 @@ int dmmt_shard_launch_pack(dmmt_shard *, const int64_t *d_global_bit_offset, int
 int dmmt_shard_launch_stuff(dmmt_shard *, const int32_t *d_all_tail2, const int64_t *d_all_bit_offsets,
                             const int64_t *d_all_bits, int rank, int world, const uint8_t **d_bytes, int64_t *d_n_bytes);
 int dmmt_shard_status(dmmt_shard *);              /* synchronises; device-side error of the phases so far or 0 */
+/* the same flag as an int64 in device memory, asynchronous: all-gather it with the byte counts so that every rank
+ * learns of a failed shard (a failed shard reports 0 bytes, which is also a legitimate count) */
+int dmmt_shard_launch_error(dmmt_shard *, int64_t *d_err);
 
 /* Peer-memory gather (one process per GPU on one NVLink / NVSwitch node): instead of dmmt_shard_launch_stuff +
  * a send / recv of the shard outputs, the destination rank allocates the whole file once

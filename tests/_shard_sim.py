@@ -115,6 +115,71 @@ class SimShard:
         return torch.frombuffer(bytearray(out), dtype=torch.uint8).clone() if out else torch.empty(0, dtype=torch.uint8)
 
 
+class FailingShard(SimShard):
+    """A shard whose `fail_phase` raises DmmtError(code) on rank `fail_rank` for the first `fail_times` attempts --
+    the device-side failure of one shard (scan overflow, missing symbol ...) as the C ABI reports it."""
+
+    def __init__(self, px, preset, row_begin, row_end, rank, fail_rank, fail_phase, code, fail_times):
+        super().__init__(px, preset, row_begin, row_end)
+        self.rank, self.fail_rank, self.fail_phase, self.code, self.left = rank, fail_rank, fail_phase, code, fail_times
+        self.grown = 0
+
+    def _maybe_fail(self, phase):
+        from dmmt_jpeg_encoder_b200 import _ffi as F
+
+        if self.rank == self.fail_rank and phase == self.fail_phase and self.left > 0:
+            self.left -= 1
+            raise F.DmmtError(self.code, f"simulated failure in {phase}")
+
+    def transform(self):
+        self._maybe_fail("transform")
+        return super().transform()
+
+    def histogram(self, seed_dc):
+        self._maybe_fail("histogram")
+        return super().histogram(seed_dc)
+
+    def tables(self, global_hist):
+        self._maybe_fail("tables")
+        return super().tables(global_hist)
+
+    def pack(self, global_bit_offset, is_last):
+        self._maybe_fail("pack")
+        return super().pack(global_bit_offset, is_last)
+
+    def stuff(self, prev_tail, prev_nbits, is_first, is_last):
+        self._maybe_fail("stuff")
+        return super().stuff(prev_tail, prev_nbits, is_first, is_last)
+
+    def grow(self):
+        self.grown += 1
+
+
+def failing_worker(rank, world, port, px, preset, q, fail_rank, fail_phase, code, fail_times):
+    """every rank reports (rank, outcome): the file / None, or the code of the DmmtError it raised, + grow() calls"""
+    import torch.distributed as dist
+
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+    from dmmt_jpeg_encoder_b200 import sharded as S
+    from dmmt_jpeg_encoder_b200.encoder import Options
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        opts = Options(preset, 8, 0)
+        rows = S.mcu_rows_total(px.shape[0], opts)
+        b, e = S.shard_rows(rows, world, rank)
+        sim = FailingShard(px, preset, b, e, rank, fail_rank, fail_phase, code, fail_times)
+        try:
+            out = S.encode_sharded(sim, torch.device("cpu"))
+            q.put((rank, "ok", out, sim.whole if rank == 0 else None, sim.grown))
+        except F.DmmtError as err:
+            q.put((rank, "error", err.code, None, sim.grown))
+    finally:
+        dist.destroy_process_group()
+
+
 def worker(rank, world, port, px, preset, q):
     import torch.distributed as dist
 

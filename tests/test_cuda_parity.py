@@ -557,14 +557,41 @@ def test_1080p_batch_properties(D, ctx, O):
     b.close()
 
 
-def test_large_image_sharded_equals_unsharded(D, ctx, O):
-    """Config 5 property at 8192x4096 (the oracle would need minutes): N-shard output is
-    independent of N and equal to the single-launch-chain output."""
+def test_large_image_sharded_equals_oracle(D, ctx, O):
+    """Config 5 at 8192x4096 (33.5 Mpx; the oracle needs a few seconds): the N-shard output is independent of N, equal
+    to the single-launch-chain output and byte-identical to the oracle's file."""
     px = synth_image("grad", 8192, 4096)
+    want = O.encode(px, 255, O.P420, nthreads=os.cpu_count() or 1).jpeg
     whole = ctx.encode(px, 255)
-    assert ctx.encode_sharded(px, 4, 255) == whole
-    assert ctx.encode_sharded(px, 7, 255) == whole
-    assert whole[:2] == b"\xff\xd8" and whole[-2:] == b"\xff\xd9"
+    assert whole == want
+    assert ctx.encode_sharded(px, 4, 255) == want
+    assert ctx.encode_sharded(px, 7, 255) == want
+
+
+def test_sharded_dense_content_grows_and_retries(D, ctx, O, monkeypatch):
+    """Noise with the Flat tables needs more than the default 128 B of scan / 32 tokens per block: the sharded driver
+    must grow every shard to the worst case and run again (the reference encodes any input), through the
+    peer-memory exchange and through the host-exchange fallback alike."""
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    px = np.random.default_rng(3).integers(0, 256, (160, 272, 3), dtype=np.uint8)
+    opt = D.Options(F.P420, 8, 1)
+    want = O.encode(px, 255, O.P420, 8, 1).jpeg
+    assert ctx.encode(px, 255, opt) == want
+    assert ctx.encode_sharded(px, 3, 255, opt) == want
+    monkeypatch.setenv("DMMT_SHARDED_HOST_EXCHANGE", "1")
+    assert ctx.encode_sharded(px, 3, 255, opt) == want
+    assert ctx.encode_sharded(synth_image("photo", 210, 333, 8), 4, 255) == O.encode(synth_image("photo", 210, 333, 8), 255, O.P420).jpeg
+
+
+def test_synth_generators_cpu_equals_cuda():
+    """tests/golden/config5_sha256.json was produced from CPU-generated rows: the generator must be device-independent"""
+    from dmmt_jpeg_encoder_b200 import synth
+
+    for kind in ("smooth", "grad", "uniform"):
+        a = synth.make(kind, 5, 64, 1000, "cpu", y0=4096)
+        b = synth.make(kind, 5, 64, 1000, "cuda", y0=4096).cpu()
+        assert torch.equal(a, b), kind
 
 
 def test_random_fuzz_against_oracle(D, ctx, O):
@@ -596,7 +623,7 @@ def test_random_fuzz_against_oracle(D, ctx, O):
 def test_config5_full_size_shards_equal_single_chain(D, ctx):
     """BASELINE config 5 at FULL size (32768 x 32768, 3.2 GB of pixels): the MCU-row-sharded encode
     (8 shards, here all on one GPU) is byte-identical to the single launch chain, the file is well formed
-    and every 0xFF of the scan is stuffed.  (The oracle would need ~50 GB and minutes at this size.)"""
+    and every 0xFF of the scan is stuffed; and the file is the oracle's, by its committed SHA-256."""
     import hashlib
 
     from dmmt_jpeg_encoder_b200 import synth
@@ -616,3 +643,6 @@ def test_config5_full_size_shards_equal_single_chain(D, ctx):
     assert b"\xff" not in body.replace(b"\xff\x00", b"")
     sharded = ctx.encode_sharded(px, 8, 255)
     assert hashlib.sha256(sharded).digest() == hashlib.sha256(whole).digest() and len(sharded) == len(whole)
+    # the ORACLE's file for the same rows (tests/golden/make_config5_sha.py ran it once: ~1 minute, ~30 GB of host memory)
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config5_sha256.json")))[str(n)]
+    assert len(whole) == gold["bytes"] and hashlib.sha256(whole).hexdigest() == gold["sha256"]

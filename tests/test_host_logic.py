@@ -348,6 +348,59 @@ def test_sharded_exchange_logic_over_gloo(world, preset, w, h):
     assert out == whole
 
 
+@pytest.mark.parametrize("phase", ["transform", "histogram", "tables", "pack", "stuff"])
+def test_sharded_failure_reaches_every_rank(phase):
+    """A shard that fails in any phase must not strand the other ranks in a collective: every rank raises the same
+    DmmtError (here E_SYMBOL on rank 1 of 3)."""
+    import torch.multiprocessing as mp
+
+    import _shard_sim
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    px = synth_image("photo", 40, 70, 3)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_sim.failing_worker, args=(r, 3, port, px, 2, q, 1, phase, F.E_SYMBOL, 9))
+             for r in range(3)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120)[:3] for _ in range(3))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert got == [(r, "error", F.E_SYMBOL) for r in range(3)]
+
+
+def test_sharded_overflow_is_retried_on_every_rank():
+    """DMMT_E_OVERFLOW on one shard: ALL ranks grow their shard and the phases run once more (the reference encodes
+    any input); a second overflow is reported on every rank."""
+    import torch.multiprocessing as mp
+
+    import _shard_sim
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    px = synth_image("photo", 40, 70, 4)
+    for times, want in ((1, "ok"), (2, "error")):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_shard_sim.failing_worker, args=(r, 2, port, px, 2, q, 1, "tables", F.E_OVERFLOW, times))
+                 for r in range(2)]
+        for p in procs:
+            p.start()
+        got = sorted(q.get(timeout=120) for _ in range(2))
+        for p in procs:
+            p.join(60)
+            assert p.exitcode == 0
+        assert [g[1] for g in got] == [want, want]
+        assert [g[4] for g in got] == [1, 1]                # grow() once on each rank
+        if want == "ok":
+            assert got[0][2] == got[0][3]                   # rank 0 holds the whole file
+        else:
+            assert [g[2] for g in got] == [F.E_OVERFLOW, F.E_OVERFLOW]
+
+
 def test_shard_row_partition():
     from dmmt_jpeg_encoder_b200 import sharded as S
     from dmmt_jpeg_encoder_b200.encoder import Options

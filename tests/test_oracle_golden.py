@@ -74,3 +74,20 @@ def test_all_quant_presets_run(q):
     px = synth_image("grad", 33, 17)
     j = O.encode(px, 255, O.P420, qpreset=q).jpeg
     assert j[25:25 + 64] == bytes(O.qtable(q, False)[O.zigzag()])
+
+
+def test_config5_digest_script_is_reproducible_at_4096():
+    """tests/golden/config5_sha256.json (oracle digests of the config-5 workload, made by make_config5_sha.py): the
+    4096 x 4096 entry is recomputed here, which pins generator + oracle + script for the 32768 x 32768 entry that the
+    GPU test compares the CUDA file with."""
+    from dmmt_jpeg_encoder_b200 import synth
+
+    gold = json.load(open(os.path.join(GOLDEN, "config5_sha256.json")))
+    g = gold["4096"]
+    n = g["width"]
+    px = np.empty((n, n, 3), np.uint8)
+    for y0 in range(0, n, g["slab_rows"]):
+        px[y0:y0 + g["slab_rows"]] = synth.make(g["kind"], g["index"], g["slab_rows"], n, "cpu", y0=y0).numpy()
+    r = O.encode(px, 255, O.P420, 8, 0, nthreads=os.cpu_count() or 1)
+    assert len(r.jpeg) == g["bytes"] and hashlib.sha256(r.jpeg).hexdigest() == g["sha256"]
+    assert set(gold["32768"]) == set(g) and gold["32768"]["bytes"] > 100e6
