@@ -78,6 +78,7 @@ SIGNATURES = {
     "dmmt_plan_worst_case_scan_bytes": (C.c_size_t, [_VP]),
     "dmmt_plan_encode_device": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
     "dmmt_plan_status": (C.c_int, [_VP]),
+    "dmmt_plan_set_graph": (C.c_int, [_VP, C.c_int]),
     "dmmt_plan_encode_host": (C.c_int, [_VP, _VP, C.c_int, C.POINTER(_U8P), C.POINTER(C.c_size_t)]),
     "dmmt_plan_encode_host_into": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_uint64, _U64P, _U64P]),
     "dmmt_batch_create": (C.c_int, [_VP, C.c_uint16, C.c_uint16, C.c_int, C.c_uint16, C.POINTER(Options),

@@ -82,6 +82,15 @@ struct dmmt_plan {
     unsigned long long* h_lens = nullptr;     // pinned [n]
     unsigned long long* h_offsets = nullptr;  // pinned [n + 1]
 
+    // CUDA graph of the launch chain for repeated calls with the same arguments (dmmt_plan_chain_replay)
+    cudaGraphExec_t gexec = nullptr;
+    const void* g_pixels = nullptr;      // arguments of the captured (or, before capture, of the previous) call
+    int g_n = 0;
+    uint8_t* g_out = nullptr;
+    unsigned long long* g_lens = nullptr;
+    int g_launches = 0;
+    int graphs = 1;                      // dmmt_plan_set_graph
+
     // profiling
     bool profiling = false;
     cudaEvent_t ev[DMMT_T_COUNT + 1] = {};
@@ -98,6 +107,10 @@ int dmmt_plan_create_impl(dmmt_ctx* ctx, int W, int H_rows, int mcus_y_override,
                           bool own_stream, dmmt_plan** out);
 // memset + K1 + K2 + K2b + K3 + K4 on the plan's stream (asynchronous)
 int dmmt_plan_chain(dmmt_plan* p, const void* d_pixels, int n, uint8_t* d_out, unsigned long long* d_lens);
+// the same chain, replayed from a CUDA graph once a call repeats the arguments of the previous one (one launch instead
+// of eight: what a latency-bound single frame is made of); plain launches while profiling or when graphs are off
+int dmmt_plan_chain_replay(dmmt_plan* p, const void* d_pixels, int n, uint8_t* d_out, unsigned long long* d_lens);
+void dmmt_plan_drop_graph(dmmt_plan* p);
 // chain + K5 packing into `dense`
 int dmmt_plan_encode_compact(dmmt_plan* p, const void* d_pixels, int n, uint8_t* d_dense,
                              unsigned long long dense_cap, unsigned long long* d_offsets,

@@ -162,6 +162,9 @@ class Plan:
     def set_profiling(self, on: bool):
         F.check(F.lib().dmmt_plan_set_profiling(self._h, int(on)), "dmmt_plan_set_profiling")
 
+    def set_graph(self, on: bool):
+        F.check(F.lib().dmmt_plan_set_graph(self._h, int(on)), "dmmt_plan_set_graph")
+
     def set_generic_path(self, on: bool):
         F.check(F.lib().dmmt_plan_set_generic_path(self._h, int(on)), "dmmt_plan_set_generic_path")
 

@@ -123,6 +123,10 @@ size_t dmmt_plan_worst_case_scan_bytes(const dmmt_plan *);
 int dmmt_plan_encode_device(dmmt_plan *, const void *d_pixels, int n_images, uint8_t *d_out,
                             uint64_t *d_lens);
 int dmmt_plan_status(dmmt_plan *);                /* synchronises; first device-side error or 0 */
+/* A call that repeats the device pointers of the previous one is replayed from a CUDA graph of the launch chain
+ * (memset, K1, DC fix-up, K2b, scan zeroing, K3, K4: one graph launch instead of eight launches -- what the latency
+ * of a single frame, BASELINE config 3, is made of).  On by default; 0 switches back to plain launches. */
+int dmmt_plan_set_graph(dmmt_plan *, int enabled);
 /* Host-buffer end-to-end: H2D of the pixels, encode, D2H of lengths + bytes.  jpegs[i] malloc'd
  * (release with dmmt_free).  Grows the scan capacity and retries once on DMMT_E_OVERFLOW. */
 int dmmt_plan_encode_host(dmmt_plan *, const void *h_pixels, int n_images, uint8_t **jpegs,

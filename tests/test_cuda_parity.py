@@ -520,6 +520,40 @@ def test_shards_peer_file_tiny_bit_counts_and_ff_runs(D, O):
 
 
 # ------------------------------------------------------------------------------- full sizes
+def test_graph_replay_follows_the_data(D, ctx, O):
+    """Repeated calls with the same device pointers are replayed from a CUDA graph of the launch chain: the replays must
+    re-read the pixels (new content, same buffer), survive a capacity change, and equal the plain launches."""
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    w, h = 333, 210
+    plan = D.Plan(ctx, w, h, F.FMT_U8, 255, D.Options(), 1)
+    d_px = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(plan.out_stride, dtype=torch.uint8, device="cuda")
+    d_len = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def run():
+        plan.encode_device(d_px.data_ptr(), 1, d_out.data_ptr(), d_len.data_ptr())
+        plan.status()
+        return d_out[: int(d_len.item())].cpu().numpy().tobytes()
+
+    for i, kind in enumerate(["photo", "grad", "uniform", "photo", "grad"]):     # call 3 onwards: graph launches
+        px = synth_image(kind, w, h, i)
+        d_px.copy_(torch.from_numpy(px))
+        torch.cuda.synchronize()
+        assert run() == O.encode(px, 255, O.P420).jpeg, (i, kind)
+    plan.set_scan_capacity(plan.worst_case_scan_bytes())                          # buffers move: the graph is dropped
+    d_out = torch.empty(plan.out_stride, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        assert run() == O.encode(px, 255, O.P420).jpeg
+    plan.set_graph(False)
+    assert run() == O.encode(px, 255, O.P420).jpeg
+    plan.close()
+    # the drop-in call with host pixels goes through the same replay (cached plan, own staging buffers)
+    for i in range(4):
+        px = synth_image("photo", 200, 120, 10 + i)
+        assert ctx.encode(px, 255) == O.encode(px, 255, O.P420).jpeg
+
+
 def test_4k_frame_matches_oracle_and_decodes(D, ctx, O):
     """BASELINE config 3 geometry (3840x2160)."""
     from PIL import Image

@@ -401,6 +401,18 @@ def test_sharded_overflow_is_retried_on_every_rank():
             assert [g[2] for g in got] == [F.E_OVERFLOW, F.E_OVERFLOW]
 
 
+def test_rust_shim_matches_the_header():
+    """rust/ cannot be compiled here (no rustc): its #[repr(C)] structs, extern "C" signatures and constants are
+    compared with include/dmmt_cuda.h by rust/check_layout.py instead."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "rust", "check_layout.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "OK" in r.stdout
+
+
 def test_shard_row_partition():
     from dmmt_jpeg_encoder_b200 import sharded as S
     from dmmt_jpeg_encoder_b200.encoder import Options
