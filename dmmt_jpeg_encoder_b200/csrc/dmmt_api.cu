@@ -160,6 +160,7 @@ static void plan_free_scratch(dmmt_plan* p) {
     (void)cudaFree(p->zero_region), p->zero_region = nullptr;
     (void)cudaFree(p->enc), p->enc = nullptr;
     (void)cudaFree(p->lens), p->lens = nullptr;
+    (void)cudaFree(p->lcount), p->lcount = nullptr;
     (void)cudaFree(p->scan), p->scan = nullptr;
     (void)cudaFree(p->tb.tok), p->tb.tok = nullptr;
     (void)cudaFree(p->tb.ntok), p->tb.ntok = nullptr;
@@ -316,6 +317,7 @@ int dmmt_plan_create_impl(dmmt_ctx* ctx, int W, int H_rows, int mcus_y_override,
     PLAN_CUDA(cudaMalloc(&p->coef, (size_t)n_images * p->coef_stride * sizeof(int16_t)));
     PLAN_CUDA(cudaMalloc(&p->enc, (size_t)n_images * sizeof(EncTables)));
     PLAN_CUDA(cudaMalloc(&p->lens, (size_t)n_images * sizeof(LenTables)));
+    PLAN_CUDA(cudaMalloc(&p->lcount, (size_t)n_images * 64));
     PLAN_CUDA(cudaMalloc(&p->d_lens, (size_t)n_images * 8));
     PLAN_CUDA(cudaMalloc(&p->d_offsets, (size_t)(n_images + 1) * 8));
     PLAN_CUDA(cudaMalloc(&p->d_seed_dc, 8 * sizeof(int16_t)));
@@ -400,9 +402,11 @@ int dmmt_plan_chain(dmmt_plan* p, const void* d_pixels, int n, uint8_t* d_out, u
                         p->meta, p->fused ? &p->fo : nullptr, p->hist, st));
     launches += 1;
     DMMT_CUDA(mark(1));
-    if (p->fused) DMMT_CUDA(launch_k2_fix_dc(p->fo, n, p->hist, p->meta, nullptr, st));
-    else DMMT_CUDA(launch_k2(p->g, p->coef, p->coef_stride, n, p->hist, p->meta, nullptr, p->tb, st));
-    launches += 1;
+    // fused path: the tile-boundary DC tokens are finished by the DC-table CTAs of K2b (no kernel of its own)
+    if (!p->fused) {
+        DMMT_CUDA(launch_k2(p->g, p->coef, p->coef_stride, n, p->hist, p->meta, nullptr, p->tb, st));
+        launches += 1;
+    }
     DMMT_CUDA(mark(2));
     K2bHostArgs b{};
     b.hist = p->hist, b.ghist = nullptr, b.enc = p->enc, b.lens = p->lens, b.meta = p->meta;
@@ -412,8 +416,10 @@ int dmmt_plan_chain(dmmt_plan* p, const void* d_pixels, int n, uint8_t* d_out, u
     b.qtab_luma = kQuantPresets[p->opt.qtable_preset][0];
     b.qtab_chroma = kQuantPresets[p->opt.qtable_preset][1];
     b.write_header = 1;
+    b.lcount = p->lcount;
+    b.fix = p->fused ? &p->fo : nullptr;
     DMMT_CUDA(launch_k2b(p->g, b, n, st));
-    launches += 2;
+    launches += 1;
     DMMT_CUDA(mark(3));
     const int zero_blocks = (int)std::min<size_t>(std::max<size_t>(p->scan_cap_bytes / 65536, 1), 128);
     DMMT_CUDA(launch_zero_scan(p->scan, p->scan_stride_words, p->meta, n, 0ull, zero_blocks, st));

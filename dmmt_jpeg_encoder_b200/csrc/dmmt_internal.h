@@ -62,6 +62,7 @@ struct dmmt_plan {
     unsigned int* tk4 = nullptr;
     dmmt::EncTables* enc = nullptr;
     dmmt::LenTables* lens = nullptr;
+    uint8_t* lcount = nullptr;                // [n][4][16] K2b scratch (codes per length)
     uint32_t* scan = nullptr;
     dmmt::TokBuf tb{};                        // K2 -> K3 token stream (generic path)
     dmmt::TileTok fo{};                       // fused K1 -> K3 token stream (4:2:0 fast path), shares tb.tok

@@ -45,7 +45,7 @@ cudaError_t launch_k2(const Geom& g, const int16_t* coef, size_t coef_img_stride
                       cudaStream_t st);
 
 struct K2bHostArgs {
-    const unsigned int* hist;         // [n][4][256] u32 local counts
+    unsigned int* hist;               // [n][4][256] u32 local counts (the fused DC fix-up adds its symbols)
     const unsigned long long* ghist;  // optional [4][256] u64 global counts (sharded mode)
     EncTables* enc;
     LenTables* lens;
@@ -57,6 +57,9 @@ struct K2bHostArgs {
     const uint8_t* qtab_luma;         // natural order
     const uint8_t* qtab_chroma;
     int write_header;
+    uint8_t* lcount;                  // [n][4][16] scratch: codes per length (DHT)
+    const TileTok* fix;               // fused 4:2:0 chain: the DC-table CTAs finish the tile-boundary DC tokens first
+                                      // (nullptr: done already, by launch_k2_fix_dc or by K2)
 };
 cudaError_t launch_k2b(const Geom& g, const K2bHostArgs& h, int n, cudaStream_t st);
 

@@ -168,8 +168,9 @@ static int shard_tables_launch(dmmt_shard* s, const uint64_t global_hist[1024]) 
     b.qtab_luma = kQuantPresets[p->opt.qtable_preset][0];
     b.qtab_chroma = kQuantPresets[p->opt.qtable_preset][1];
     b.write_header = 1;  // every shard writes the (identical) header into its arena; only the first one ships it
+    b.lcount = p->lcount, b.fix = nullptr;
     DMMT_CUDA(launch_k2b(p->g, b, 1, p->stream));
-    p->last_launches += 2;
+    p->last_launches += 1;
     return DMMT_OK;
 }
 static int shard_tables_collect(dmmt_shard* s, uint64_t* local_bits) {
@@ -303,10 +304,11 @@ extern "C" int dmmt_shard_launch_tables(dmmt_shard* s, const int64_t* d_global_h
     b.qtab_luma = kQuantPresets[p->opt.qtable_preset][0];
     b.qtab_chroma = kQuantPresets[p->opt.qtable_preset][1];
     b.write_header = 1;
+    b.lcount = p->lcount, b.fix = nullptr;
     DMMT_CUDA(launch_k2b(p->g, b, 1, p->stream));
     DMMT_CUDA(launch_shard_widen(nullptr, nullptr, nullptr, nullptr, p->meta, reinterpret_cast<long long*>(d_local_bits),
                                  p->stream));
-    p->last_launches += 3;
+    p->last_launches += 2;
     return DMMT_OK;
 }
 

@@ -189,11 +189,14 @@ __global__ void __launch_bounds__(EB) k2_tokenize(const K2Args a) {
 }
 
 // =========================================== K2b ==========================================
-// One CTA (256 threads) per (table, image).  Package-merge with limit 15 in shared memory:
+// One CTA (512 threads) per (table, image).  Package-merge with limit 15 in shared memory:
 // every level is a parallel merge-by-rank of the sorted leaves with the pairwise packages of the
-// previous level (Leaf < Package on equal frequency, length_limited.rs:7-26,104-115).
+// previous level (Leaf < Package on equal frequency, length_limited.rs:7-26,104-115): threads 0..255 place the
+// packages, threads 256..511 the leaves, at the same time.  On the fused 4:2:0 chain the two DC-table CTAs first finish
+// the tile-boundary DC tokens (what k2_fix_dc does as a kernel of its own on the sharded path) -- the AC tables, which
+// take longer anyway, do not depend on them.  The CTA that finishes last writes the header of the image.
 struct K2bArgs {
-    const unsigned int* hist;      // [n][4][256] local counts (u32)
+    unsigned int* hist;            // [n][4][256] local counts (u32); the DC fix-up adds its symbols
     const unsigned long long* ghist;  // optional [4][256] u64 GLOBAL counts (sharded mode), else nullptr
     EncTables* enc;                // [n]
     LenTables* lens;               // [n]
@@ -207,11 +210,15 @@ struct K2bArgs {
     uint8_t qzz[2][64];            // quantisation tables in zig-zag order for DQT
     uint32_t n_stream_blocks;
     int write_header;
+    uint8_t* lcount;               // [n][4][16]: codes per length of every table, for the DHT segments
+    int fix_dc;                    // 1: finish the tile-boundary DC tokens of the fused K1 (fo) first
+    TileTok fo;
 };
 
 constexpr int PM_LIMIT = 15;
+constexpr int K2B_THREADS = 512;
 
-__global__ void __launch_bounds__(256) k2b_tables(const __grid_constant__ K2bArgs a) {
+__global__ void __launch_bounds__(K2B_THREADS) k2b_tables(const __grid_constant__ K2bArgs a) {
     __shared__ unsigned long long s_freq[256];        // sorted leaf frequencies
     __shared__ uint8_t s_sym[256];                    // sorted symbols (ascending frequency, ties by symbol)
     __shared__ unsigned long long s_list[2][512];     // ping-pong merged lists (frequencies)
@@ -220,34 +227,51 @@ __global__ void __launch_bounds__(256) k2b_tables(const __grid_constant__ K2bArg
     __shared__ int s_nleaves[PM_LIMIT];               // back-trace: leaves taken at level k
     __shared__ int s_len[256];
     __shared__ uint32_t s_scan[256];
-    __shared__ unsigned int s_cnt[4];
     __shared__ unsigned int s_lcount[17];
+    __shared__ unsigned int s_fix[16];
     __shared__ unsigned long long s_bits;
-    __shared__ uint32_t s_warp[9];
-    __shared__ int s_err;
+    __shared__ uint32_t s_warp[K2B_THREADS / 32 + 1];
+    __shared__ int s_err, s_is_last;
 
     const int t = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
     const int nsym_max = (t & 1) ? 256 : 16;
-    const unsigned int* lh = a.hist + (size_t)img * 1024;
+    unsigned int* lh = a.hist + (size_t)img * 1024;
+    ImgMeta* meta = a.meta + img;
 
-    if (tid < 4) s_cnt[tid] = 0;
     if (tid < 17) s_lcount[tid] = 0;
+    if (tid < 16) s_fix[tid] = 0;
     if (tid == 0) s_bits = 0ull, s_err = 0;
     __syncthreads();
-    // symbol counts of all four tables (header offsets need them) -- symbol_counting.rs:25-32
-#pragma unroll
-    for (int tt = 0; tt < 4; tt++) {
-        const unsigned long long f = a.ghist ? a.ghist[tt * 256 + tid] : (unsigned long long)lh[tt * 256 + tid];
-        const bool nz = (tid < ((tt & 1) ? 256 : 16)) && f != 0ull;
-        const unsigned int bal = __ballot_sync(0xffffffffu, nz);
-        if ((tid & 31) == 0 && bal) atomicAdd(&s_cnt[tt], (unsigned)__popc(bal));
+    if (a.fix_dc && !(t & 1)) {
+        // DC difference of the first Y (table 0) / Cb and Cr (table 2) block of every tile against the last DC of the
+        // previous tile (tile 0: the chain starts at 0, categorize.rs:157): token patched, symbol counted
+        const TileTok& fo = a.fo;
+        for (uint32_t tile = tid; tile < fo.tiles; tile += K2B_THREADS) {
+            const size_t ti = (size_t)img * fo.tiles + tile;
+            if (fo.ntok[ti] == 0) continue;  // overflowed tile (error already flagged)
+            uint32_t* tok = fo.tok + (size_t)img * fo.img_stride_words + (size_t)tile * fo.tile_cap;
+            for (int c = (t == T_YDC ? 0 : 1); c < (t == T_YDC ? 1 : 3); c++) {
+                const int pred = tile ? (int)fo.last_dc[(ti - 1) * 4 + c] : 0;
+                const uint32_t pos = c == 0 ? 0u : fo.dcpos[ti * 2 + (c - 1)];
+                const int dc = (int)(short)(tok[pos] >> 16);
+                const int diff = (int)(short)(dc - pred);
+                int cat = 0;
+                uint32_t bits = 0;
+                if (diff != 0) cat_bits(diff, cat, bits);
+                if (cat > 15) atomicCAS(&meta->error, 0, DMMT_E_RANGE);
+                tok[pos] = make_token(t, cat & 15, 0, bits);
+                atomicAdd(&s_fix[cat & 15], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid < 16 && s_fix[tid]) lh[t * 256 + tid] += s_fix[tid];  // this CTA is the only one that touches these bins
+        __syncthreads();
     }
     const unsigned long long myf = (tid < nsym_max)
                                        ? (a.ghist ? a.ghist[t * 256 + tid] : (unsigned long long)lh[t * 256 + tid])
                                        : 0ull;
-    s_list[0][tid] = myf;  // scratch: raw frequencies by symbol
-    __syncthreads();
-    const int n = (int)s_cnt[t];
+    if (tid < 256) s_list[0][tid] = myf;  // scratch: raw frequencies by symbol
+    const int n = __syncthreads_count(myf != 0ull);  // symbol_counting.rs:25-32: symbols with a non-zero count
     // stable sort by frequency of the ascending-symbol list (symbol_counting.rs:92-94): rank sort
     if (myf != 0ull) {
         int rank = 0;
@@ -259,28 +283,22 @@ __global__ void __launch_bounds__(256) k2b_tables(const __grid_constant__ K2bArg
         s_sym[rank] = (uint8_t)tid;
     }
     __syncthreads();
-    if (n == 0) {  // no blocks at all: the reference panics (symbol_counting.rs:88 indexes [0])
-        if (tid == 0) atomicCAS(&a.meta[img].error, 0, DMMT_E_INVALID);
-        return;
-    }
+    bool ok_table = n != 0;
+    if (!ok_table && tid == 0) atomicCAS(&meta->error, 0, DMMT_E_INVALID);  // no blocks at all: the reference panics (symbol_counting.rs:88)
 
     // ---- package-merge levels (length_limited.rs:63-73,104-115) ----
-    int cur = 0;
+    int cur = 1;
     int len_prev = n;
     if (tid < n) s_list[1][tid] = s_freq[tid];
     if (tid == 0) s_npk[0] = 0;
-    cur = 1;
     __syncthreads();
-    for (int k = 1; k < PM_LIMIT; k++) {
+    for (int k = 1; k < PM_LIMIT && ok_table; k++) {
         const unsigned long long* prev = s_list[cur];
-        unsigned long long* nxt = s_list[cur ^ 1];
+        unsigned long long* nxt = s_list[cur ^ 1];   // last read in level k - 1, before that level's closing barrier
         const int np = len_prev >> 1;  // chunks_exact(2)
-        // package j
-        unsigned long long pf = 0ull;
-        if (tid < np) pf = prev[2 * tid] + prev[2 * tid + 1];
-        __syncthreads();  // everybody has read prev before anyone overwrites (nxt != prev, but keep levels apart)
         if (tid < np) {
-            // leaves with freq <= pf come first (leaf wins ties)
+            // package j = prev[2j] + prev[2j + 1]; leaves with freq <= pf come first (leaf wins ties)
+            const unsigned long long pf = prev[2 * tid] + prev[2 * tid + 1];
             int lo = 0, hi = n;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
@@ -290,11 +308,11 @@ __global__ void __launch_bounds__(256) k2b_tables(const __grid_constant__ K2bArg
             const int pos = tid + lo;
             nxt[pos] = pf;
             s_pkgpos[k][tid] = (uint16_t)pos;
-        }
-        if (tid < n) {
+        } else if (tid >= 256 && tid - 256 < n) {
             // packages with freq < leaf come first.  Package frequencies are non-decreasing in j
             // (pair sums of a sorted list), so binary search over j on the fly.
-            const unsigned long long lf = s_freq[tid];
+            const int i = tid - 256;
+            const unsigned long long lf = s_freq[i];
             int lo = 0, hi = np;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
@@ -302,32 +320,31 @@ __global__ void __launch_bounds__(256) k2b_tables(const __grid_constant__ K2bArg
                 if (pm < lf) lo = mid + 1;
                 else hi = mid;
             }
-            nxt[tid + lo] = lf;
+            nxt[i + lo] = lf;
         }
         if (tid == 0) s_npk[k] = np;
         len_prev = n + np;
         cur ^= 1;
         __syncthreads();
     }
-    // ---- back-trace (length_limited.rs:75-89,117-133): thread 0, 15 binary searches ----
-    if (tid == 0) {
+    // ---- back-trace (length_limited.rs:75-89,117-133): one warp, per level a 32-ary search in two rounds over the
+    // (increasing) package positions instead of a binary search ----
+    if (tid < 32 && ok_table) {
         int p = n - 1;
         for (int k = PM_LIMIT - 1; k >= 0; k--) {
             const int count = 2 * p;
-            const int len_k = n + s_npk[k];
-            if (count > len_k) {  // slice panic in the reference; impossible for n <= 2^15
-                s_err = DMMT_E_INVALID;
-                s_nleaves[k] = 0;
+            const int npk = s_npk[k];
+            if (count > n + npk) {  // slice panic in the reference; impossible for n <= 2^15
+                if (tid == 0) s_err = DMMT_E_INVALID, s_nleaves[k] = 0;
                 p = 0;
                 continue;
             }
-            int lo = 0, hi = s_npk[k];  // packages with position < count
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if ((int)s_pkgpos[k][mid] < count) lo = mid + 1;
-                else hi = mid;
-            }
-            s_nleaves[k] = count - lo;
+            // lo = number of packages with position < count
+            const int i1 = tid * 8 + 7;
+            const int c1 = __popc(__ballot_sync(0xffffffffu, i1 < npk && (int)s_pkgpos[k][i1] < count));
+            const int i2 = c1 * 8 + tid;
+            const int lo = c1 * 8 + __popc(__ballot_sync(0xffffffffu, tid < 8 && i2 < npk && (int)s_pkgpos[k][i2] < count));
+            if (tid == 0) s_nleaves[k] = count - lo;
             p = lo;
         }
     }
@@ -347,22 +364,24 @@ __global__ void __launch_bounds__(256) k2b_tables(const __grid_constant__ K2bArg
     const int ri = n - 1 - tid;  // reversed index handled by this thread
     uint32_t inc = 0;
     __syncthreads();
-    if (tid < n) inc = 1u << (16 - s_len[ri]);
+    if (tid < n) inc = 1u << (16 - min(max(s_len[ri], 0), 16));
     uint32_t total;
-    const uint32_t excl = block_exclusive_scan<256>(tid < n ? inc : 0u, s_warp, &total);
+    const uint32_t excl = block_exclusive_scan<K2B_THREADS>(tid < n ? inc : 0u, s_warp, &total);
     if (tid < n) {
         const int len = s_len[ri];
         if (excl > 0xFFFFu) s_err = DMMT_E_INVALID;
-        const uint32_t code = (excl & 0xFFFFu) >> (16 - len);  // right-aligned
+        const uint32_t code = (excl & 0xFFFFu) >> (16 - min(max(len, 0), 16));  // right-aligned
         s_scan[ri] = ((uint32_t)len << 16) | code;
     }
     __syncthreads();
     // LUT by symbol + length tables + this table's share of the scan bits
     EncTables* enc = a.enc + img;
     LenTables* lt = a.lens + img;
-    enc->e[t][tid] = 0u;
-    lt->sym[t][tid] = 0;
-    lt->len[t][tid] = 0;
+    if (tid < 256) {
+        enc->e[t][tid] = 0u;
+        lt->sym[t][tid] = 0;
+        lt->len[t][tid] = 0;
+    }
     __syncthreads();
     if (tid < n) {
         const int sym = s_sym[tid];
@@ -373,74 +392,77 @@ __global__ void __launch_bounds__(256) k2b_tables(const __grid_constant__ K2bArg
         const unsigned long long cnt = lh[t * 256 + sym];
         atomicAdd(&s_bits, cnt * (unsigned long long)(s_len[tid] + (sym & 15)));
     }
+    if (tid < 16) a.lcount[((size_t)img * 4 + t) * 16 + tid] = (uint8_t)s_lcount[tid + 1];
     __syncthreads();
-    ImgMeta* meta = a.meta + img;
     if (tid == 0) {
         atomicAdd(&meta->scan_bits, s_bits);
         meta->n_symbols[t] = (uint32_t)n;
         if (s_err) atomicCAS(&meta->error, 0, s_err);
+        __threadfence();  // tables, counts and bits of this table are visible before the arrival is
+        s_is_last = atomicAdd(&meta->reserved, 1u) == 3u;
     }
+    __syncthreads();
+    if (!s_is_last) return;
+    // ---- the last of the image's four CTAs: capacity check and headers (jpeg/encoder.rs:125-262) ----
+    __threadfence();
+    if (tid == 0 && *reinterpret_cast<volatile unsigned long long*>(&meta->scan_bits) + 8 > a.scan_cap_bits)
+        atomicCAS(&meta->error, 0, DMMT_E_OVERFLOW);
     if (!a.write_header) return;
-
-    // ---- headers (jpeg/encoder.rs:125-262) ----
     // layout: SOI(2) APP0(18) DQT(69) DQT(69) SOF0(19) | DHT YAC, YDC, CAC, CDC (21 + n each) | SOS(14)
     uint8_t* out = a.out + (size_t)img * a.out_stride;
-    const uint32_t nY_AC = s_cnt[T_YAC], nY_DC = s_cnt[T_YDC], nC_AC = s_cnt[T_CAC], nC_DC = s_cnt[T_CDC];
-    uint32_t off = 177;
-    if (t == T_YDC) off += 21 + nY_AC;
-    else if (t == T_CAC) off += 42 + nY_AC + nY_DC;
-    else if (t == T_CDC) off += 63 + nY_AC + nY_DC + nC_AC;
+    const volatile uint32_t* ns = meta->n_symbols;
+    const uint32_t nY_AC = ns[T_YAC], nY_DC = ns[T_YDC], nC_AC = ns[T_CAC], nC_DC = ns[T_CDC];
     const uint32_t hdr_len = 177 + 84 + nY_AC + nY_DC + nC_AC + nC_DC + 14;
     {
         // DHT: FF C4, len = 2 + 17 + n, Tc/Th id (encoder.rs:78-84), counts[16] (:92-98),
-        // symbols in REVERSE table order (:177)
-        uint8_t* p = out + off;
+        // symbols in REVERSE table order (:177); a quarter of the CTA per table, in file order
+        const int q = tid >> 7, j = tid & 127;
+        const int order[4] = {T_YAC, T_YDC, T_CAC, T_CDC};
         const uint8_t ids[4] = {0x00, 0x11, 0x02, 0x13};
-        if (tid == 0) {
+        const int tt = order[q];
+        const uint32_t nn = ns[tt];
+        uint32_t off = 177;
+        if (q >= 1) off += 21 + nY_AC;
+        if (q >= 2) off += 21 + nY_DC;
+        if (q >= 3) off += 21 + nC_AC;
+        uint8_t* p = out + off;
+        if (j == 0) {
             p[0] = 0xFF, p[1] = 0xC4;
-            p[2] = (uint8_t)((19 + n) >> 8), p[3] = (uint8_t)((19 + n) & 0xFF);
-            p[4] = ids[t];
+            p[2] = (uint8_t)((19 + nn) >> 8), p[3] = (uint8_t)((19 + nn) & 0xFF);
+            p[4] = ids[tt];
         }
-        if (tid < 16) p[5 + tid] = (uint8_t)s_lcount[tid + 1];
-        if (tid < n) p[21 + tid] = s_sym[n - 1 - tid];
+        if (j < 16) p[5 + j] = __ldcg(&a.lcount[((size_t)img * 4 + tt) * 16 + j]);
+        for (uint32_t i = j; i < nn; i += 128) p[21 + i] = __ldcg(&lt->sym[tt][nn - 1 - i]);
     }
-    if (t == 0) {
-        if (tid == 0) {
-            uint8_t* p = out;
-            const uint8_t fixed[20] = {0xFF, 0xD8, 0xFF, 0xE0, 0x00, 0x10, 'J', 'F', 'I', 'F', 0,
-                                       0x01, 0x02, 0x00, 0x00, 0x48, 0x00, 0x48, 0x00, 0x00};
-            for (int i = 0; i < 20; i++) p[i] = fixed[i];
-            p = out + 158;  // SOF0 (encoder.rs:227-245)
-            const uint8_t sof[19] = {0xFF, 0xC0, 0x00, 0x11, (uint8_t)a.bits_per_channel,
-                                     (uint8_t)(a.H >> 8), (uint8_t)a.H, (uint8_t)(a.W >> 8), (uint8_t)a.W,
-                                     0x03, 0x01, (uint8_t)((a.hr << 4) | a.vr), 0x00,
-                                     0x02, 0x11, 0x01, 0x03, 0x11, 0x01};
-            for (int i = 0; i < 19; i++) p[i] = sof[i];
-            p = out + hdr_len - 14;  // SOS (encoder.rs:247-262)
-            const uint8_t sos[14] = {0xFF, 0xDA, 0x00, 0x0C, 0x03, 0x01, 0x01, 0x02, 0x23, 0x03, 0x23,
-                                     0x00, 0x3F, 0x00};
-            for (int i = 0; i < 14; i++) p[i] = sos[i];
-            meta->header_len = hdr_len;
-            meta->n_stream_blocks = a.n_stream_blocks;
-        }
-        if (tid < 138) {  // two DQT segments (encoder.rs:190-209), 69 bytes each
-            const int which = tid / 69, i = tid % 69;
-            uint8_t v;
-            if (i == 0) v = 0xFF;
-            else if (i == 1) v = 0xDB;
-            else if (i == 2) v = 0x00;
-            else if (i == 3) v = 0x43;
-            else if (i == 4) v = (uint8_t)which;
-            else v = a.qzz[which][i - 5];
-            out[20 + tid] = v;
-        }
+    if (tid == 0) {
+        uint8_t* p = out;
+        const uint8_t fixed[20] = {0xFF, 0xD8, 0xFF, 0xE0, 0x00, 0x10, 'J', 'F', 'I', 'F', 0,
+                                   0x01, 0x02, 0x00, 0x00, 0x48, 0x00, 0x48, 0x00, 0x00};
+        for (int i = 0; i < 20; i++) p[i] = fixed[i];
+        p = out + 158;  // SOF0 (encoder.rs:227-245)
+        const uint8_t sof[19] = {0xFF, 0xC0, 0x00, 0x11, (uint8_t)a.bits_per_channel,
+                                 (uint8_t)(a.H >> 8), (uint8_t)a.H, (uint8_t)(a.W >> 8), (uint8_t)a.W,
+                                 0x03, 0x01, (uint8_t)((a.hr << 4) | a.vr), 0x00,
+                                 0x02, 0x11, 0x01, 0x03, 0x11, 0x01};
+        for (int i = 0; i < 19; i++) p[i] = sof[i];
+        p = out + hdr_len - 14;  // SOS (encoder.rs:247-262)
+        const uint8_t sos[14] = {0xFF, 0xDA, 0x00, 0x0C, 0x03, 0x01, 0x01, 0x02, 0x23, 0x03, 0x23,
+                                 0x00, 0x3F, 0x00};
+        for (int i = 0; i < 14; i++) p[i] = sos[i];
+        meta->header_len = hdr_len;
+        meta->n_stream_blocks = a.n_stream_blocks;
     }
-}
-
-// After K2b: flags images whose scan would not fit the plan's capacity (one thread per image)
-__global__ void k_check_capacity(ImgMeta* meta, int n, unsigned long long cap_bits) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && meta[i].scan_bits + 8 > cap_bits) atomicCAS(&meta[i].error, 0, DMMT_E_OVERFLOW);
+    if (tid >= 256 && tid < 256 + 138) {  // two DQT segments (encoder.rs:190-209), 69 bytes each
+        const int x = tid - 256, which = x / 69, i = x % 69;
+        uint8_t v;
+        if (i == 0) v = 0xFF;
+        else if (i == 1) v = 0xDB;
+        else if (i == 2) v = 0x00;
+        else if (i == 3) v = 0x43;
+        else if (i == 4) v = (uint8_t)which;
+        else v = a.qzz[which][i - 5];
+        out[20 + x] = v;
+    }
 }
 
 // Zeroes the words of the unstuffed scan buffers that K3 will OR into (sizes are only known on
@@ -1231,10 +1253,10 @@ cudaError_t launch_k2b(const Geom& g, const K2bHostArgs& h, int n, cudaStream_t 
     }
     a.n_stream_blocks = g.n_blocks;
     a.write_header = h.write_header;
-    k2b_tables<<<dim3(4, n), 256, 0, st>>>(a);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    k_check_capacity<<<(n + 127) / 128, 128, 0, st>>>(h.meta, n, h.scan_cap_bits);
+    a.lcount = h.lcount;
+    a.fix_dc = h.fix ? 1 : 0;
+    a.fo = h.fix ? *h.fix : TileTok{};
+    k2b_tables<<<dim3(4, n), K2B_THREADS, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -43,9 +43,38 @@ def test_batch_round_robin_two_ranks():
     import json
 
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "2", "--images", "48", "--steps", "2",
-                        "--warmup", "1", "--no-cpu-baseline"], capture_output=True, text=True, timeout=600)
+                        "--warmup", "1", "--no-cpu-baseline", "--config5-size", "4096"], capture_output=True, text=True,
+                       timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert line["n_gpus"] == 2 and line["config"]["images_per_rank"] == 24
-    assert line["config"]["verified"] == "image 0 byte-identical to oracle"
+    assert "byte-identical to the oracle" in line["config"]["verified"]
     assert line["e2e"]["value"] > 0 and line["gpu_launches"] > 0
+    assert 0.2 < line["e2e"]["frac_of_copy_ceiling"] < 1.3
+    # BASELINE config 5 through the same run: sharded over the two ranks, checked against the ORACLE's digest
+    c5 = line["extra"]["config5"]
+    assert c5["n_gpus"] == 2 and "equal the oracle's file" in c5["verified"], c5
+
+
+def test_c_abi_sharded_over_two_devices():
+    """dmmt_encode_sharded with one context per DEVICE of this process: the exchanges are peer loads between the two
+    GPUs, K4 of the second shard stores into the file in the first GPU's memory over NVLink."""
+    _need(2)
+    import numpy as np
+
+    import dmmt_jpeg_encoder_b200 as D
+    from conftest import synth_image
+    from oracle import oracle as O
+
+    c0, c1 = D.Context(0), D.Context(1)
+    try:
+        for (w, h, preset) in [(1000, 650, 2), (333, 97, 0), (640, 360, 1)]:
+            px = synth_image("photo", w, h, 3)
+            want = O.encode(px, 255, preset).jpeg
+            assert c0.encode_sharded(px, 2, 255, D.Options(preset, 8, 0), contexts=[c0, c1]) == want
+            assert c0.encode_sharded(px, 4, 255, D.Options(preset, 8, 0), contexts=[c0, c1, c1, c0]) == want
+        noise = np.random.default_rng(1).integers(0, 256, (160, 272, 3), dtype=np.uint8)      # overflow -> retry
+        assert c0.encode_sharded(noise, 2, 255, D.Options(2, 8, 1), contexts=[c0, c1]) == O.encode(noise, 255, 2, 8, 1).jpeg
+    finally:
+        c0.close()
+        c1.close()
