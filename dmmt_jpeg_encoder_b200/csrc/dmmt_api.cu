@@ -212,7 +212,7 @@ static int plan_alloc_scan(dmmt_plan* p, size_t scan_cap_bytes) {
     const size_t o_hist = 0;
     const size_t o_meta = o_hist + align_up((size_t)n.n * 1024 * sizeof(unsigned int), 16);
     const size_t o_lb3 = o_meta + align_up((size_t)n.n * sizeof(ImgMeta), 16);
-    const size_t o_lb4 = o_lb3 + (size_t)n.n * std::max(n.n_chunks3, n.n_chunks3f) * 8;
+    const size_t o_lb4 = o_lb3 + (size_t)n.n * std::max(n.n_chunks3, n.fo.tiles) * 8;  // K3: per chunk, or per tile (fused)
     const size_t o_tk3 = o_lb4 + (size_t)n.n * n.max_chunks4 * 8;
     const size_t o_tk4 = o_tk3 + align_up((size_t)n.n * 4, 16);
     n.zero_bytes = o_tk4 + align_up((size_t)n.n * 4, 16);

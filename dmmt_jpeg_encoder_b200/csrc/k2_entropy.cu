@@ -921,6 +921,119 @@ __global__ void __launch_bounds__(EB, 4) k3_pack(const K3Args a) {
     }
 }
 
+// K3 in TILE mode (fused K1: one token region per 256x16-pixel tile).  The unit of work, of the ticket and of the
+// decoupled look-back is ONE TILE taken by ONE WARP: a warp takes the next tile of the CTA's current image, packs it
+// into a private shared-memory buffer from bit 0, publishes its bit count and only then resolves the look-back of its
+// PREVIOUS tile and copies that one out -- so no warp ever waits for another warp of its CTA (the chunk-of-8-tiles
+// version spent 29 % of its stall samples at CTA barriers, waiting for the slowest of eight tiles), and a single
+// 4K frame (338 tiles) spreads over 338 warps at once.  A CTA keeps one image's code table in shared memory; CTA c
+// starts at image c * n / grid and moves on to the next images when its own has no tiles left (barriers only there).
+__global__ void __launch_bounds__(EB, 4) k3_pack_tiles(const K3Args a) {
+    __shared__ __align__(16) uint32_t s_wbuf[2][EB / 32][K3_WBUF_WORDS];
+    __shared__ __align__(8) uint2 s_enc2[4 * 256];
+    __shared__ int s_err_img;
+    __shared__ unsigned int s_left;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = (int)(a.n_items / a.n_chunks);  // images of this launch (n_chunks = tiles per image here)
+    const uint32_t tiles = a.n_segs;
+    const int first_img = (int)((unsigned long long)blockIdx.x * (unsigned)n / gridDim.x);
+    const unsigned long long seed = a.seed_src ? (*a.seed_src & 7ull) : a.seed_bits;
+    const int visits = n < 3 ? n : 3;  // own image, then help the next two
+    for (int v = 0; v < visits; v++) {
+        const int img = (first_img + v) % n;
+        if (tid == 0) {
+            s_left = *reinterpret_cast<volatile unsigned int*>(&a.ticket[img]) < tiles ? 1u : 0u;
+            s_err_img = *reinterpret_cast<volatile int32_t*>(&a.meta[img].error);
+        }
+        __syncthreads();  // also: every warp is done with the previous image's table
+        const int err = s_err_img;
+        const bool img_active = s_left != 0u && (err == 0 || err == DMMT_E_SYMBOL);
+        if (!img_active) continue;  // nothing left (or an image flagged by K1 / K2b: skipped, K3 only ever adds DMMT_E_SYMBOL)
+        for (int i = tid; i < 1024; i += EB) {
+            const uint32_t e = a.enc[img].e[i >> 8][i & 255];
+            const uint32_t len = e >> 16, cat = (uint32_t)i & 15u;
+            s_enc2[(i & 0x300) | tok_swz((uint32_t)i >> 8, (uint32_t)i & 255u)] =
+                len ? make_uint2((e & 0xFFFFu) << cat, len + cat)
+                    : make_uint2((uint32_t)i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
+        }
+        __syncthreads();
+        const uint32_t zl_y = s_enc2[T_YAC * 256 + tok_swz(T_YAC, 0xF0u)].y, zl_c = s_enc2[T_CAC * 256 + tok_swz(T_CAC, 0xF0u)].y;
+        unsigned long long* lb = a.lb_state + (size_t)img * a.n_chunks;
+        uint32_t* gscan = a.scan + (size_t)img * a.scan_img_stride_words;
+        const uint32_t* __restrict__ tok_img = a.tb.tok + (size_t)img * a.tb.img_stride_words;
+
+        bool pend = false;  // the previous tile of this warp is packed in s_wbuf[buf ^ 1][wid] and waits for its position
+        int buf = 0;
+        uint32_t p_tile = 0, p_bits = 0;
+        while (true) {
+            uint32_t tile = 0;
+            if (lane == 0) tile = atomicAdd(&a.ticket[img], 1u);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            const bool have = tile < tiles;
+            uint32_t wbits = 0;
+            bool cur_ovf = false;
+            const uint32_t* __restrict__ tok = tok_img + (size_t)tile * a.tb.chunk_cap;
+            uint32_t ntok = 0;
+            if (have) {
+                ntok = a.tb.ntok[(size_t)img * tiles + tile];
+                uint32_t* wbuf = s_wbuf[buf][wid];
+                for (int i = lane; i < K3_WBUF_WORDS / 4; i += 32) reinterpret_cast<uint4*>(wbuf)[i] = make_uint4(0, 0, 0, 0);
+                __syncwarp();
+                bool sym_ok = true, ovf = false;
+                wbits = (uint32_t)emit_range_fast(tok, 0u, ntok, s_enc2, zl_y, zl_c, wbuf,
+                                                  (unsigned long long)K3_WBUF_WORDS * 32 - 64, sym_ok, ovf);
+                if (!sym_ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_SYMBOL);
+                cur_ovf = ovf;
+                __syncwarp();
+                if (lane == 0) lookback_publish_aggregate(lb, (int)tile, wbits);
+            }
+            if (pend) {
+                // shifted copy of the private buffer to its place: destination word k holds relative bits
+                // [32k - s, 32k - s + 32); the first and last word are shared with the neighbours
+                const unsigned long long ex = lookback_resolve_warp(lb, (int)p_tile, p_bits);
+                const uint32_t* src = s_wbuf[buf ^ 1][wid];
+                const unsigned long long p0 = seed + ex;
+                const uint32_t sft = (uint32_t)(p0 & 31);
+                const uint32_t n_dst = (sft + p_bits + 31) >> 5;
+                uint32_t* dst = gscan + (p0 >> 5);
+                for (uint32_t k = lane; k < n_dst; k += 32) {
+                    const uint32_t cur = k < (uint32_t)K3_WBUF_WORDS ? src[k] : 0u;
+                    const uint32_t prv = k ? src[k - 1] : 0u;
+                    const uint32_t val = bswap32(__funnelshift_r(cur, prv, sft));
+                    if (k == 0 || k == n_dst - 1) {
+                        if (val) atomicOr(dst + k, val);
+                    } else {
+                        dst[k] = val;
+                    }
+                }
+                if (p_tile == tiles - 1 && a.pad_ones && lane == 0) {
+                    const uint32_t pad = (uint32_t)((8 - ((p0 + p_bits) & 7)) & 7);  // binary_stream.rs:89-96
+                    if (pad) or_bits<false>(gscan, p0 + p_bits, (1u << pad) - 1u, pad);
+                }
+                pend = false;
+                __syncwarp();
+            }
+            if (!have) break;
+            if (cur_ovf) {
+                // a tile too dense for the private buffer (rare): resolve it right away and make a second pass straight
+                // into the zeroed stream
+                const unsigned long long ex = lookback_resolve_warp(lb, (int)tile, wbits);
+                bool d0 = true, d1 = false;
+                (void)emit_range<false>(tok, 0u, ntok, s_enc2, zl_y, zl_c, gscan, seed + ex, ~0ull, d0, d1);
+                if (tile == tiles - 1 && a.pad_ones && lane == 0) {
+                    const uint32_t pad = (uint32_t)((8 - ((seed + ex + wbits) & 7)) & 7);
+                    if (pad) or_bits<false>(gscan, seed + ex + wbits, (1u << pad) - 1u, pad);
+                }
+            } else {
+                pend = true;
+                p_tile = tile, p_bits = wbits;
+                buf ^= 1;
+            }
+        }
+    }
+}
+
 // =========================================== K4 ===========================================
 // Byte stuffing (segment_marker_injector.rs:13-30) as scan + compaction.  A CTA takes 8 KB chunks of
 // the unstuffed scan by ticket (so a waiting chunk's predecessors are always running or done):
@@ -1295,6 +1408,23 @@ cudaError_t launch_k3(uint32_t n_chunks, uint32_t n_segs, int n, const TokBuf& t
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_pack, EB, 0);
         if (e != cudaSuccess) return e;
         resident = (per_sm > 0 ? per_sm : 1) * sm_count();
+    }
+    if (n_segs) {
+        // tile mode: the look-back runs over tiles (n_chunks := n_segs); as many CTAs as the device holds, but no more
+        // than one warp per tile
+        a.n_chunks = n_segs;
+        a.n_items = n_segs * (uint32_t)n;
+        static int resident_t = 0;
+        if (!resident_t) {
+            int per_sm = 0;
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_pack_tiles, EB, 0);
+            if (e != cudaSuccess) return e;
+            resident_t = (per_sm > 0 ? per_sm : 1) * sm_count();
+        }
+        const uint32_t want = (a.n_items + EB / 32 - 1) / (EB / 32);
+        const uint32_t grid_t = want < (uint32_t)resident_t ? want : (uint32_t)resident_t;
+        k3_pack_tiles<<<grid_t ? grid_t : 1u, EB, 0, st>>>(a);
+        return cudaGetLastError();
     }
     const uint32_t grid = a.n_items < (uint32_t)resident ? a.n_items : (uint32_t)resident;
     k3_pack<<<grid ? grid : 1u, EB, 0, st>>>(a);
