@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip extra.config3 / extra.config5")
+    ap.add_argument("--no-verify", action="store_true", help="kernel experiments only: do not compare with the oracle")
     ap.add_argument("--config5-size", type=int, default=32768)
     return ap.parse_args()
 
@@ -461,7 +462,9 @@ def run_ours(args):
 
     # ---- the checker (outside every timed region): image 0 of this rank byte-identical to the oracle
     verified = None
-    if rank == 0:
+    if rank == 0 and args.no_verify:
+        verified, want = "NOT VERIFIED (--no-verify)", None
+    elif rank == 0:
         from oracle import oracle as O
 
         check = sorted({0, 1, n // 2, n - 1})                 # first, second, middle and last image of this rank's share
@@ -515,7 +518,7 @@ def run_ours(args):
         for _ in range(max(min(WU, 2), 1)):
             estep()
         assert int(h_lens.sum()) == file_bytes
-        if rank == 0:
+        if rank == 0 and want is not None:
             assert h_out.array[int(h_offs[0]): int(h_offs[0] + h_lens[0])].tobytes() == want
         barrier()
         torch.cuda.synchronize()

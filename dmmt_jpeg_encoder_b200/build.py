@@ -7,6 +7,8 @@ Outputs (git-ignored, shipped to the GPU box by gpurun):
   dmmt_jpeg_encoder_b200/lib/libdmmt_cuda.a    the same objects as a static archive (what a Rust
                                                build.rs links)
   dmmt_jpeg_encoder_b200/lib/dmmt-jpeg-encoder the CLI front-end (mirrors src/cli.rs + src/main.rs)
+  dmmt_jpeg_encoder_b200/lib/dmmt-jpeg-batch   many files per process: parallel ingest, pipelined batches, direct
+                                               file writes from the pinned output arena (csrc/cli_batch.cpp)
 """
 from __future__ import annotations
 
@@ -21,6 +23,7 @@ OBJ = os.path.join(LIB, "obj")
 SO = os.path.join(LIB, "libdmmt_cuda.so")
 AR = os.path.join(LIB, "libdmmt_cuda.a")
 CLI = os.path.join(LIB, "dmmt-jpeg-encoder")
+CLI_BATCH = os.path.join(LIB, "dmmt-jpeg-batch")
 
 CU_SOURCES = ["k1_transform.cu", "k2_entropy.cu", "dmmt_api.cu", "dmmt_batch.cu", "dmmt_shard.cu"]
 # -fmad=false: the reference's f32 arithmetic never contracts a*b+c; the kernels also use
@@ -54,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     deps = _deps()
     have_cli = os.path.exists(os.path.join(CSRC, "cli_main.cpp"))
-    if not force and _newer(SO, deps) and _newer(AR, deps) and (not have_cli or _newer(CLI, deps)):
+    if not force and _newer(SO, deps) and _newer(AR, deps) and (not have_cli or (_newer(CLI, deps) and _newer(CLI_BATCH, deps))):
         return SO
     nvcc = _nvcc()
     objs = []
@@ -79,8 +82,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         os.remove(AR)
     subprocess.check_call(["ar", "rcs", AR, *objs])
     if have_cli:
-        subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(CSRC, "cli_main.cpp"), "-o", CLI,
-                               "-L" + LIB, "-ldmmt_cuda", "-Wl,-rpath,$ORIGIN", "-pthread"])
+        for src, exe in (("cli_main.cpp", CLI), ("cli_batch.cpp", CLI_BATCH)):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(CSRC, src), "-o", exe,
+                                   "-L" + LIB, "-ldmmt_cuda", "-Wl,-rpath,$ORIGIN", "-pthread"])
     return SO
 
 

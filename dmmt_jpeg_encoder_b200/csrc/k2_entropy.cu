@@ -668,21 +668,43 @@ __device__ __forceinline__ void load_run_padded(const uint32_t* __restrict__ tok
         for (int i = 0; i < K3_RUN; i++) t[i] = (base + i < end) ? __ldg(tok + base + i) : K3_PAD_TOKEN;
     }
 }
-__device__ __forceinline__ void or_quad(uint32_t* words, unsigned long long pos, unsigned long long v, uint32_t len) {
-    const unsigned long long left = v << ((64u - len) & 63u);  // len = 0 comes with v = 0
-    const uint32_t hi = (uint32_t)(left >> 32), lo = (uint32_t)left;
-    const uint32_t s = (uint32_t)pos & 31u;
-    uint32_t* w = words + (pos >> 5);
-    const uint32_t w0 = hi >> s, w1 = __funnelshift_r(lo, hi, s), w2 = __funnelshift_r(0u, lo, s);
-    if (w0) atomicOr(w, w0);
-    if (w1) atomicOr(w + 1, w1);
-    if (w2) atomicOr(w + 2, w2);
+// PTX shifts clamp the amount at 32 (a C shift by 32 is undefined); the pair / quad merges below rely on that
+__device__ __forceinline__ uint32_t shl32(uint32_t v, uint32_t n) {
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
+}
+__device__ __forceinline__ uint32_t shr32(uint32_t v, uint32_t n) {
+    uint32_t r;
+    asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
+}
+// OR into a shared-memory word unless the value is zero: one compare and one predicated reduction
+__device__ __forceinline__ void red_or_shared(uint32_t saddr, uint32_t v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.or.b32 [%0], %1;\n\t}" ::"r"(saddr), "r"(v) : "memory");
+}
+// ORs the `len` (<= 64) bits held right-aligned in (hi:lo) at bit position `pos` of the warp's private bit buffer
+// (shared address `wsa`, host byte order): up to three words
+__device__ __forceinline__ void or_quad(uint32_t wsa, uint32_t pos, uint32_t hi, uint32_t lo, uint32_t len) {
+    const unsigned long long left = (((unsigned long long)hi << 32) | lo) << ((64u - len) & 63u);  // len = 0 comes with 0
+    const uint32_t lhi = (uint32_t)(left >> 32), llo = (uint32_t)left;
+    const uint32_t sft = pos & 31u;
+    const uint32_t wa = wsa + ((pos >> 5) << 2);
+#ifdef K3_EXPERIMENT_NO_ATOMICS   // measurement only (wrong output): what the shared-memory reductions cost
+    if ((lhi >> sft) + __funnelshift_r(llo, lhi, sft) + __funnelshift_r(0u, llo, sft) == 0xFFFFFFFFu) red_or_shared(wa, 1u);
+#else
+    red_or_shared(wa, lhi >> sft);
+    red_or_shared(wa + 4, __funnelshift_r(llo, lhi, sft));
+    red_or_shared(wa + 8, __funnelshift_r(0u, llo, sft));
+#endif
 }
 __device__ __forceinline__ unsigned long long emit_range_fast(const uint32_t* __restrict__ tok, uint32_t begin,
                                                               uint32_t end, const uint2* s_enc2, uint32_t zl_y, uint32_t zl_c, uint32_t* words,
                                                               unsigned long long cap_bits, bool& sym_ok, bool& overflow) {
     const int lane = threadIdx.x & 31;
-    unsigned long long bitpos = 0ull;
+    const uint32_t wsa = (uint32_t)__cvta_generic_to_shared(words);
+    const uint32_t cap = (uint32_t)cap_bits;
+    uint32_t bitpos = 0u;  // the private buffer holds < 2^32 bits
     // the tokens of step k + 1 are requested before step k is processed (the chain of bit positions makes the
     // steps sequential, so the load latency would otherwise be exposed once per step)
     uint32_t tn[K3_RUN];
@@ -693,18 +715,36 @@ __device__ __forceinline__ unsigned long long emit_range_fast(const uint32_t* __
 #pragma unroll
         for (int i = 0; i < K3_RUN; i++) t[i] = tn[i];
         if (wbase + K3_STEP < end) load_run_padded(tok, base + K3_STEP, end, tn);
-        uint32_t val[K3_RUN], ln[K3_RUN], flags = 0, tor = 0;
+        uint32_t val[K3_RUN], ln[K3_RUN];
 #pragma unroll
         for (int i = 0; i < K3_RUN; i++) {
             const uint2 e = s_enc2[t[i] & 0x3FFu];
             val[i] = e.x | (t[i] >> 16);
             ln[i] = e.y;
-            flags |= e.x;
-            tor |= t[i];
+        }
+        const uint32_t tor = (t[0] | t[1] | t[2]) | (t[3] | t[4] | t[5]) | (t[6] | t[7]);
+        // a symbol without a code has bit 31 of its entry set (and length 0); category bits only reach bit 15
+        const uint32_t flags = (val[0] | val[1] | val[2]) | (val[3] | val[4] | val[5]) | (val[6] | val[7]);
+        bool hard = false;
+        if (__any_sync(0xffffffffu, (tor & 0xC00u) != 0u)) {
+            // some token of this step follows a run of 16.. zeros: ONE ZRL code (categorize.rs:139-142) goes in front
+            // of its own code; two or three of them (runs of 32.., very rare) take the general path
+#pragma unroll
+            for (int i = 0; i < K3_RUN; i++) {
+                const uint32_t nz = (t[i] >> 10) & 3u;
+                if (nz == 1u) {
+                    const uint2 z = s_enc2[(t[i] & 0x300u) | tok_swz(t[i] >> 8 & 3u, 0xF0u)];
+                    hard |= ln[i] + z.y > 32u || (z.x >> 31) != 0u;
+                    val[i] |= shl32(z.x & 0xFFFFu, ln[i]);
+                    ln[i] += z.y;
+                } else if (nz) {
+                    hard = true;
+                }
+            }
         }
         const uint32_t l01 = ln[0] + ln[1], l23 = ln[2] + ln[3], l45 = ln[4] + ln[5], l67 = ln[6] + ln[7];
         const uint32_t q0 = l01 + l23, q1 = l45 + l67, nb = q0 + q1;
-        const bool simple = (tor & 0xC00u) == 0u && max(max(l01, l23), max(l45, l67)) <= 32u;
+        const bool simple = !hard && max(max(l01, l23), max(l45, l67)) <= 32u;
         if (__all_sync(0xffffffffu, simple)) {
             if (flags >> 31) sym_ok = false;  // Error::HuffmanSymbolNotPresentInTranslator
             uint32_t inc = nb;
@@ -714,15 +754,15 @@ __device__ __forceinline__ unsigned long long emit_range_fast(const uint32_t* __
                 if (lane >= d) inc += u;
             }
             const uint32_t step_bits = __shfl_sync(0xffffffffu, inc, 31);
-            if (bitpos + step_bits > cap_bits) overflow = true;  // warp-uniform
+            if (bitpos + step_bits > cap) overflow = true;  // warp-uniform
             if (!overflow) {
-                const uint32_t p01 = (val[0] << ln[1]) | val[1], p23 = (val[2] << ln[3]) | val[3];
-                const uint32_t p45 = (val[4] << ln[5]) | val[5], p67 = (val[6] << ln[7]) | val[7];
-                const unsigned long long v0 = ((unsigned long long)p01 << l23) | p23;
-                const unsigned long long v1 = ((unsigned long long)p45 << l67) | p67;
-                const unsigned long long at = bitpos + (inc - nb);
-                or_quad(words, at, v0, q0);
-                or_quad(words, at + q0, v1, q1);
+                // (a "no code" marker in bit 31 of a value ends up above the quad's valid bits and is shifted out by
+                // or_quad's left alignment; the output of such an image is discarded anyway, encoder.rs:381-386)
+                const uint32_t p01 = shl32(val[0], ln[1]) | val[1], p23 = shl32(val[2], ln[3]) | val[3];
+                const uint32_t p45 = shl32(val[4], ln[5]) | val[5], p67 = shl32(val[6], ln[7]) | val[7];
+                const uint32_t at = bitpos + (inc - nb);
+                or_quad(wsa, at, shr32(p01, 32u - l23), shl32(p01, l23) | p23, q0);
+                or_quad(wsa, at + q0, shr32(p45, 32u - l67), shl32(p45, l67) | p67, q1);
             }
             bitpos += step_bits;
         } else {
@@ -928,7 +968,10 @@ __global__ void __launch_bounds__(EB, 4) k3_pack(const K3Args a) {
 // version spent 29 % of its stall samples at CTA barriers, waiting for the slowest of eight tiles), and a single
 // 4K frame (338 tiles) spreads over 338 warps at once.  A CTA keeps one image's code table in shared memory; CTA c
 // starts at image c * n / grid and moves on to the next images when its own has no tiles left (barriers only there).
-__global__ void __launch_bounds__(EB, 4) k3_pack_tiles(const K3Args a) {
+#ifndef K3_MINB
+#define K3_MINB 3
+#endif
+__global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
     __shared__ __align__(16) uint32_t s_wbuf[2][EB / 32][K3_WBUF_WORDS];
     __shared__ __align__(8) uint2 s_enc2[4 * 256];
     __shared__ int s_err_img;
@@ -1160,6 +1203,8 @@ __global__ void __launch_bounds__(K4_THREADS) k4_stuff(const K4Args a) {
         }
         uint32_t chunk_ff;
         const uint32_t ff_before = block_exclusive_scan<K4_THREADS>(nff, s_warp, &chunk_ff);
+        // one thread walks the predecessors: measured against the warp-wide look-back (32 predecessors per round trip)
+        // this is the faster one here, 0.60 vs 0.72 ms per 1024 frames -- the predecessor is almost always done already
         if (tid == 0) s_prefix = lookback_exclusive(a.lb_state + (size_t)img * a.max_chunks, (int)chunk, chunk_ff);
         __syncthreads();
         const unsigned long long gs = hdr + cbase + s_prefix;  // file offset of the chunk's first output byte

@@ -108,6 +108,49 @@ def test_cpp_cli_binary_writes_golden_files(tmp_path, name, pname):
     assert dst.read_bytes() == open(os.path.join(GOLDEN, "jpeg", f"{name}_{pname}.jpg"), "rb").read()
 
 
+def test_batch_front_end_writes_every_file(tmp_path, O):
+    """dmmt-jpeg-batch (csrc/cli_batch.cpp): many P3 files per process -- parallel ingest, one pipelined batch per
+    geometry, each <stem>.jpg written straight from the pinned output arena -- byte-identical to the oracle; a
+    broken input is reported with the reference's error text and does not stop the others."""
+    import subprocess
+
+    from dmmt_jpeg_encoder_b200 import build as B
+
+    B.build()
+    out = tmp_path / "out"
+    out.mkdir()
+    want, args = {}, []
+    for name in FIXTURES:                                   # the reference's own fixtures (mixed geometries)
+        text, px, mx = load_fixture(name)
+        (tmp_path / f"{name}.ppm").write_bytes(text)
+        want[name] = O.encode(px, mx, O.P422).jpeg
+        args.append(str(tmp_path / f"{name}.ppm"))
+    for i in range(5):                                      # five equal-sized frames: one batch
+        px = synth_image("photo", 123, 77, i)
+        body = " ".join(str(int(v)) for v in px.reshape(-1))
+        (tmp_path / f"f{i}.ppm").write_text(f"P3\n123 77\n255\n{body}\n")
+        want[f"f{i}"] = O.encode(px, 255, O.P422).jpeg
+        args.append(str(tmp_path / f"f{i}.ppm"))
+    noise = np.random.default_rng(2).integers(0, 1024, (64, 48, 3))     # 10-bit samples, dense content -> u16 + retry
+    (tmp_path / "n.ppm").write_text("P3 48 64 1023 " + " ".join(str(int(v)) for v in noise.reshape(-1)))
+    want["n"] = O.encode(noise.astype(np.uint16), 1023, O.P422, 8, 1).jpeg
+    (tmp_path / "bad.ppm").write_text("P3 4 4 255 1 2 3 4")
+    r = subprocess.run([B.CLI_BATCH, "-p", "P422", "-t", "4", str(out), *args, str(tmp_path / "bad.ppm"),
+                        str(tmp_path / "missing.ppm")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == f"Converted {len(args)} of {len(args) + 2} files", (r.stdout, r.stderr)
+    assert "bad.ppm failed because of: Incomplete pixel parsed" in r.stderr
+    assert "missing.ppm failed because of: Unable to open input file" in r.stderr
+    for name, data in want.items():
+        if name == "n":
+            continue
+        assert (out / f"{name}.jpg").read_bytes() == data, name
+    # the Flat tables make the 10-bit noise dense enough for the overflow retry
+    r = subprocess.run([B.CLI_BATCH, "-p", "P422", "-q", "Flat", str(out), str(tmp_path / "n.ppm")], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "Converted 1 of 1 files", r.stderr
+    assert (out / "n.jpg").read_bytes() == want["n"]
+
+
 def test_jpeg_image_writer_f32_image_equals_sample_image(D, O):
     """Image<f32> (already normalised dots) and raw samples + max give the same bytes."""
     px = synth_image("photo", 77, 45, 5)

@@ -401,6 +401,19 @@ def test_sharded_overflow_is_retried_on_every_rank():
             assert [g[2] for g in got] == [F.E_OVERFLOW, F.E_OVERFLOW]
 
 
+def test_batch_front_end_usage_errors():
+    """dmmt-jpeg-batch keeps the options of the reference CLI; usage errors exit with status 2 like clap."""
+    import subprocess
+
+    from dmmt_jpeg_encoder_b200 import build as B
+
+    B.build()
+    for bad in ([], ["outdir"], ["-p", "P411", "outdir", "a.ppm"], ["--nope", "outdir", "a.ppm"], ["-b", "12", "o", "a.ppm"]):
+        r = subprocess.run([B.CLI_BATCH, *bad], capture_output=True, text=True)
+        assert r.returncode == 2, (bad, r.stderr)
+        assert "error:" in r.stderr
+
+
 def test_rust_shim_matches_the_header():
     """rust/ cannot be compiled here (no rustc): its #[repr(C)] structs, extern "C" signatures and constants are
     compared with include/dmmt_cuda.h by rust/check_layout.py instead."""
