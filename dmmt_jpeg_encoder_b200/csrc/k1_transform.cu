@@ -773,6 +773,13 @@ __device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, 
     return ok;
 }
 
+#ifndef K1_BULK
+#define K1_BULK 1   // 1: the tile's tokens (cp.async.bulk) and symbol counts (cp.reduce.async.bulk .add) leave through the
+                    // bulk-copy engine; 0: copy loop + per-bin global reductions
+#endif
+#ifndef K1_BRED
+#define K1_BRED 1   // (with K1_BULK) histogram flush by cp.reduce.async.bulk; 0: per-bin REDG loop
+#endif
 #ifndef K1_WALK2
 #define K1_WALK2 1   // 1: reversed masks from VIMNMX + IMAD, run LUT, 28-instruction walk step; 0: round-1 walk
 #endif
@@ -782,13 +789,11 @@ __device__ __forceinline__ bool p420_tokenize_block(uint32_t* __restrict__ dst, 
 // plus the ZRL count -- and F[0] itself is the EOB token.
 __device__ __forceinline__ uint32_t k1_run_lut_entry(int chroma, int run) {
     const uint32_t tac = chroma ? T_CAC : T_YAC, r = (uint32_t)run & 15u;
-    return (tac << 8) | (((uint32_t)run >> 4) << 10) | (r << 4) | (r ^ (chroma ? 8u : 0u));
+    // low half: the token's symbol part; high half: byte offset of the PLAIN symbol row (run nibble << 4) in the tile
+    // histogram, which is kept in plain symbol order so that it can be added to the image histogram as it is
+    return (tac << 8) | (((uint32_t)run >> 4) << 10) | (r << 4) | (r ^ (chroma ? 8u : 0u)) | ((r << 6) << 16);
 }
 
-// The walk of one block over REVERSED occupancy masks: bit 31 - p of mrl = coefficient p (0..31) is non-zero, bit
-// 63 - p of mrh for p in 32..63.  The staged block holds the coefficient of zig-zag position p at int16 index
-// (p ^ 1) (the halves of a word are swapped, see the mask construction) of chunk (p >> 3) ^ (slot & 7).
-// CHECK: categories above 15 are possible (f32 input only: integer samples bound every coefficient by 8 * 128).
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // HOT: the token destination is the tile's shared-memory buffer (32-bit shared addresses, always stored).  The cold
@@ -797,11 +802,11 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 template <bool CHECK, bool HOT>
 __device__ __forceinline__ bool p420_walk(uint32_t* __restrict__ dst, bool store, uint32_t off, unsigned short dcq, int slot,
                                           int m, int k, int comp, uint32_t mrl, uint32_t mrh, const short* s_dc,
-                                          const uint4* s_stage, unsigned int* s_hist, const unsigned short* s_flut,
+                                          const uint4* s_stage, unsigned int* s_hist, const uint32_t* s_flut,
                                           uint32_t* dcpos, uint32_t nz_bits) {
     const int tdc = comp ? T_CDC : T_YDC;
     unsigned int* const h_dc = s_hist + (comp ? 16 : 0);
-    const uint32_t hac_a = smem_u32(s_hist + (comp ? 288 : 32));   // AC bins, indexed by the low byte of the token
+    const uint32_t hac_a = smem_u32(s_hist + (comp ? 288 : 32));   // AC bins of this component class, plain symbol order
     const uint32_t lut_a = smem_u32(s_flut + (comp ? 64 : 0));
     bool ok = true;
     {
@@ -841,7 +846,7 @@ __device__ __forceinline__ bool p420_walk(uint32_t* __restrict__ dst, bool store
             asm("bfind.u32 %0, %1;" : "=r"(h) : "r"(mk));
             asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(sbase + ((h ^ cs) << 1)));
             const int run = hp - (int)h - 1;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(F) : "r"(lut_a + ((uint32_t)run << 1)));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(F) : "r"(lut_a + ((uint32_t)run << 2)));
             const uint32_t bit = c_one << h;
             more = bit != mk;
             mk ^= bit;
@@ -849,8 +854,8 @@ __device__ __forceinline__ bool p420_walk(uint32_t* __restrict__ dst, bool store
             nzrl_total += (uint32_t)run >> 4;
             asm("bfind.u32 %0, %1;" : "=r"(f) : "r"((uint32_t)abs(v)));   // category - 1
             if (CHECK) ok &= f < 15u;
-            const uint32_t sym = F ^ (f + 1u);
-            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hac_a + ((sym & 0xFFu) << 2)) : "memory");
+            const uint32_t sym = (F ^ (f + 1u)) & 0xFFFFu;
+            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hac_a + (F >> 16) + ((f + 1u) << 2)) : "memory");
             // v > 0: v; v < 0: v - 1; the low `cat` bits of it (categorize.rs:22-41)
             const uint32_t bits = (uint32_t)(v + (v >> 31)) & ~(c_m2 << f);
             const uint32_t tok = bits * 65536u + sym;
@@ -864,10 +869,10 @@ __device__ __forceinline__ bool p420_walk(uint32_t* __restrict__ dst, bool store
         }
         hp += 32;
     }
-    if (nzrl_total) atomicAdd(&s_hist[(comp ? 288 : 32) + (comp ? 0xF7 : 0xFF)], nzrl_total);  // ZRL 0xF0, swizzled
+    if (nzrl_total) atomicAdd(&s_hist[(comp ? 288 : 32) + 0xF0], nzrl_total);  // ZRL
     if (hp != 32) {                                                                             // coefficient 63 is zero: EOB 0x00
-        atomicAdd(&s_hist[(comp ? 288 : 32) + (comp ? 8 : 0)], 1u);
-        const uint32_t eob = k1_run_lut_entry(comp, 0);
+        atomicAdd(&s_hist[(comp ? 288 : 32)], 1u);
+        const uint32_t eob = k1_run_lut_entry(comp, 0) & 0xFFFFu;
         if (HOT) asm volatile("st.shared.u32 [%0], %1;" ::"r"(dpa), "r"(eob) : "memory");
         else if (store) dst[off] = eob;
     }
@@ -876,7 +881,7 @@ __device__ __forceinline__ bool p420_walk(uint32_t* __restrict__ dst, bool store
 template <bool CHECK>
 __device__ __noinline__ bool p420_walk_cold(uint32_t* __restrict__ dst, bool store, uint32_t off, unsigned short dcq, int slot,
                                             int m, int k, int comp, uint32_t mrl, uint32_t mrh, const short* s_dc,
-                                            const uint4* s_stage, unsigned int* s_hist, const unsigned short* s_flut,
+                                            const uint4* s_stage, unsigned int* s_hist, const uint32_t* s_flut,
                                             uint32_t* dcpos, uint32_t nz_bits) {
     return p420_walk<CHECK, false>(dst, store, off, dcq, slot, m, k, comp, mrl, mrh, s_dc, s_stage, s_hist, s_flut, dcpos, nz_bits);
 }
@@ -913,7 +918,7 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
     __shared__ __align__(16) unsigned int s_hist[FUSED ? SH_BINS : 4];   // fused path: symbol counts of the tile
     __shared__ uint32_t s_cnt[FUSED ? 100 : 1];         // tokens per block, then exclusive offsets (+ total)
     __shared__ short s_dc[FUSED ? 96 : 1];
-    __shared__ unsigned short s_flut[FUSED && K1_WALK2 ? 128 : 1];   // k1_run_lut_entry: luma | chroma
+    __shared__ uint32_t s_flut[FUSED && K1_WALK2 ? 128 : 1];   // k1_run_lut_entry: luma | chroma
     __shared__ int s_flag;
     constexpr int BPM = 6, MPT = 16, NUNITS = 96;
     if constexpr (FMT == DMMT_RGB_F32_NORM) {
@@ -1128,7 +1133,7 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
         constexpr uint32_t S_CTOK_CAP = sizeof(s_planes) / 4 - 96 * 8 * 4;
         for (int i = threadIdx.x; i < SH_BINS / 4; i += P420_THREADS) reinterpret_cast<uint4*>(s_hist)[i] = make_uint4(0, 0, 0, 0);
         if constexpr (K1_WALK2)
-            for (int i = threadIdx.x; i < 128; i += P420_THREADS) s_flut[i] = (unsigned short)k1_run_lut_entry(i >> 6, i & 63);
+            for (int i = threadIdx.x; i < 128; i += P420_THREADS) s_flut[i] = k1_run_lut_entry(i >> 6, i & 63);
         uint32_t cnt = 0;
         if (active) {
             // DC + one token per non-zero AC (ZRLs ride on it) + EOB unless coefficient 63 is non-zero
@@ -1180,11 +1185,31 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
             }
             if (!ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_RANGE);
         }
+#if K1_BULK
+        // the token stores of this thread (generic proxy) must be visible to the bulk-copy engine (async proxy)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
         __syncthreads();
         if (in_smem && fits) {  // compact tile -> one coalesced run (tile_cap is a multiple of 8 words)
+#if K1_BULK
+            // ONE bulk copy (TMA engine, UBLKCP) moves the tile's tokens from shared to global memory: no LDS / STG loop,
+            // the three warps go on with the histogram flush; the issuing thread only waits until the engine has READ
+            // the shared buffer (the CTA may then retire), not for the global write
+            if (threadIdx.x == 32) {
+                const uint32_t bytes = ((total + 3u) / 4u) * 16u;
+                if (bytes) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_tok), "r"(smem_u32(s_ctok)),
+                                 "r"(bytes)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+            }
+#else
             uint4* dst = reinterpret_cast<uint4*>(g_tok);
             const uint4* src = reinterpret_cast<const uint4*>(s_ctok);
             for (uint32_t i = threadIdx.x; i < (total + 3) / 4; i += P420_THREADS) dst[i] = src[i];
+#endif
         }
         if (threadIdx.x == 0) {
             a.fo.ntok[(size_t)img * a.fo.tiles + tile] = fits ? total : 0u;
@@ -1194,25 +1219,36 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
             ld[0] = s_dc[lm + 3], ld[1] = s_dc[lm + 4], ld[2] = s_dc[lm + 5], ld[3] = 0;
         }
         unsigned int* gh = a.hist + (size_t)img * 1024;
+#if K1_BULK && K1_WALK2 && K1_BRED
+        // the tile's symbol counts are in plain symbol order: four bulk reductions (add.u32, performed at L2) fold them
+        // into the image's [4][256] histogram -- Y-DC, Y-AC, C-DC, C-AC -- without a single per-bin instruction
+        if (threadIdx.x == 64) {
+            const uint32_t hs = smem_u32(s_hist);
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u32 [%0], [%1], 64;" ::"l"(gh + T_YDC * 256), "r"(hs + 4 * SH_YDC) : "memory");
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u32 [%0], [%1], 64;" ::"l"(gh + T_CDC * 256), "r"(hs + 4 * SH_CDC) : "memory");
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u32 [%0], [%1], 1024;" ::"l"(gh + T_YAC * 256), "r"(hs + 4 * SH_YAC) : "memory");
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u32 [%0], [%1], 1024;" ::"l"(gh + T_CAC * 256), "r"(hs + 4 * SH_CAC) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+#else
         for (int q4 = threadIdx.x; q4 < SH_BINS / 4; q4 += P420_THREADS) {  // 4 bins per 128-bit load; most bins of a tile are empty
             const uint4 v = reinterpret_cast<const uint4*>(s_hist)[q4];
             if (v.x | v.y | v.z | v.w) {
-                // tile layout -> [4][256] of the image: Y-DC 0.., C-DC 512.., Y-AC 256.., C-AC 768..  The AC bins are
-                // indexed by symp = sym ^ (run nibble): within four neighbouring bins only the low two bits move, so
-                // the plain symbols are the same aligned group of four, permuted by k & 3 (k = the run nibble)
+                // tile layout -> [4][256] of the image: Y-DC 0.., C-DC 512.., Y-AC 256.., C-AC 768..
                 const int b = 4 * q4;
-                int g0 = b, k = 0;
-                if (b >= SH_CAC) g0 = T_CAC * 256 + ((b - SH_CAC) ^ (K1_WALK2 ? 8 : 0)), k = (b - SH_CAC) >> 4;
-                else if (b >= SH_YAC) g0 = T_YAC * 256 + (b - SH_YAC), k = (b - SH_YAC) >> 4;
+                int g0 = b;
+                if (b >= SH_CAC) g0 = T_CAC * 256 + (b - SH_CAC);
+                else if (b >= SH_YAC) g0 = T_YAC * 256 + (b - SH_YAC);
                 else if (b >= SH_CDC) g0 = T_CDC * 256 + (b - SH_CDC);
-                unsigned int* g = gh + (g0 ^ (k & 12));
-                k &= 3;
-                if (v.x) atomicAdd(g + k, v.x);
-                if (v.y) atomicAdd(g + (1 ^ k), v.y);
-                if (v.z) atomicAdd(g + (2 ^ k), v.z);
-                if (v.w) atomicAdd(g + (3 ^ k), v.w);
+                unsigned int* g = gh + g0;
+                if (v.x) atomicAdd(g, v.x);
+                if (v.y) atomicAdd(g + 1, v.y);
+                if (v.z) atomicAdd(g + 2, v.z);
+                if (v.w) atomicAdd(g + 3, v.w);
             }
         }
+#endif
     }
 }
 

@@ -1038,17 +1038,17 @@ __global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
                 const uint32_t* src = s_wbuf[buf ^ 1][wid];
                 const unsigned long long p0 = seed + ex;
                 const uint32_t sft = (uint32_t)(p0 & 31);
-                const uint32_t n_dst = (sft + p_bits + 31) >> 5;
+                const uint32_t n_dst = (sft + p_bits + 31) >> 5;   // <= 575: the buffer is filled to 64 bits short of its 576 words
                 uint32_t* dst = gscan + (p0 >> 5);
-                for (uint32_t k = lane; k < n_dst; k += 32) {
-                    const uint32_t cur = k < (uint32_t)K3_WBUF_WORDS ? src[k] : 0u;
-                    const uint32_t prv = k ? src[k - 1] : 0u;
-                    const uint32_t val = bswap32(__funnelshift_r(cur, prv, sft));
-                    if (k == 0 || k == n_dst - 1) {
-                        if (val) atomicOr(dst + k, val);
-                    } else {
-                        dst[k] = val;
-                    }
+                for (uint32_t k = lane + 1; k + 1 < n_dst; k += 32)   // interior words: this tile's bits only
+                    dst[k] = bswap32(__funnelshift_r(src[k], src[k - 1], sft));
+                if (lane == 0 && n_dst) {                             // first word: shared with the previous tile
+                    const uint32_t val = bswap32(src[0] >> sft);
+                    if (val) atomicOr(dst, val);
+                }
+                if (lane == 1 && n_dst > 1) {                         // last word: shared with the next tile
+                    const uint32_t val = bswap32(__funnelshift_r(src[n_dst - 1], src[n_dst - 2], sft));
+                    if (val) atomicOr(dst + (n_dst - 1), val);
                 }
                 if (p_tile == tiles - 1 && a.pad_ones && lane == 0) {
                     const uint32_t pad = (uint32_t)((8 - ((p0 + p_bits) & 7)) & 7);  // binary_stream.rs:89-96
