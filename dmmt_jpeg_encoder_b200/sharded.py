@@ -17,10 +17,33 @@ import ctypes as C
 
 import numpy as np
 import torch
-import torch.distributed as dist
+import torch.distributed as _dist
 
 from . import _ffi as F
 from .encoder import Context, Options
+
+
+class _Collectives:
+    """torch.distributed with the library's error model: a collective that fails (NCCL / gloo error, a rank that went
+    away, a time-out) surfaces as DmmtError(DMMT_E_NCCL), the code include/dmmt_cuda.h reserves for the exchanges of
+    the sharded path, instead of a backend-specific exception."""
+
+    def __getattr__(self, name):
+        fn = getattr(_dist, name)
+        if not callable(fn) or isinstance(fn, type) or name in ("get_rank", "get_world_size", "get_global_rank", "isend", "irecv"):
+            return fn
+
+        def call(*a, **kw):
+            try:
+                return fn(*a, **kw)
+            except F.DmmtError:
+                raise
+            except Exception as e:  # noqa: BLE001 -- every backend raises its own type
+                raise F.DmmtError(F.E_NCCL, f"torch.distributed.{name}: {type(e).__name__}: {e}") from e
+        return call
+
+
+dist = _Collectives()
 
 
 def shard_rows(total_mcu_rows: int, world: int, rank: int) -> tuple[int, int]:

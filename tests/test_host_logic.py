@@ -426,6 +426,20 @@ def test_rust_shim_matches_the_header():
     assert "OK" in r.stdout
 
 
+def test_failed_collective_is_dmmt_e_nccl():
+    """A collective of the sharded drivers that fails (here: no process group) surfaces as DmmtError(DMMT_E_NCCL),
+    the code include/dmmt_cuda.h reserves for the exchanges of the sharded path."""
+    import torch
+
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+    from dmmt_jpeg_encoder_b200 import sharded as S
+
+    with pytest.raises(F.DmmtError) as e:
+        S.dist.all_reduce(torch.zeros(4))
+    assert e.value.code == F.E_NCCL and "all_reduce" in str(e.value)
+    assert S.dist.ReduceOp.SUM is not None        # classes and constants pass through untouched
+
+
 def test_shard_row_partition():
     from dmmt_jpeg_encoder_b200 import sharded as S
     from dmmt_jpeg_encoder_b200.encoder import Options
