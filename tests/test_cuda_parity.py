@@ -331,6 +331,33 @@ def test_sample_above_max_is_rejected(D, ctx):
     assert e.value.code == F.E_INVALID
 
 
+def test_one_bad_image_does_not_spoil_its_batch(D, ctx, O):
+    """A launch over several images where ONE has a sample above the max value (color.rs:62-65 panics in the
+    reference): that image is flagged and gets length 0, every other image of the same launch chain -- same K1 grid,
+    same K2b / K3 / K4 launches, per-image tickets and look-back chains -- is still byte-identical to the oracle."""
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    n, w, h, mx = 6, 300, 70, 200
+    px = np.stack([(synth_image("photo", w, h, i).astype(np.uint16) * mx // 255).astype(np.uint8) for i in range(n)])
+    px[3, 11, 17, 1] = 201
+    plan = D.Plan(ctx, w, h, F.FMT_U8, mx, D.Options(), n)
+    d_px = torch.from_numpy(px).cuda()
+    d_out = torch.zeros(n * plan.out_stride, dtype=torch.uint8, device="cuda")
+    d_len = torch.zeros(n, dtype=torch.int64, device="cuda")
+    for _ in range(3):                                   # plain launches, then graph replays
+        plan.encode_device(d_px.data_ptr(), n, d_out.data_ptr(), d_len.data_ptr())
+        with pytest.raises(D.DmmtError) as e:
+            plan.status()
+        assert e.value.code == F.E_INVALID
+        lens = d_len.cpu().numpy()
+        assert lens[3] == 0
+        for i in range(n):
+            if i != 3:
+                got = d_out[i * plan.out_stride: i * plan.out_stride + int(lens[i])].cpu().numpy().tobytes()
+                assert got == O.encode(px[i], mx, O.P420).jpeg, i
+    plan.close()
+
+
 def test_scan_overflow_is_detected_and_retried(D, ctx, O):
     from dmmt_jpeg_encoder_b200 import _ffi as F
 
