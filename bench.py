@@ -54,8 +54,8 @@ def parse_args():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--kind", default="photo", choices=["photo", "grad", "uniform"])
-    ap.add_argument("--sub-batch", type=int, default=128)
-    ap.add_argument("--depth", type=int, default=3)
+    ap.add_argument("--sub-batch", type=int, default=256)
+    ap.add_argument("--depth", type=int, default=2)
     ap.add_argument("--exact-sub-batch", action="store_true", help="use --sub-batch as given (no per-rank heuristic)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="images of the batch timed on the CPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")

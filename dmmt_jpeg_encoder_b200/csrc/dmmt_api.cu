@@ -314,7 +314,9 @@ int dmmt_plan_create_impl(dmmt_ctx* ctx, int W, int H_rows, int mcus_y_override,
             return fail(e__ == cudaErrorMemoryAllocation ? DMMT_E_NOMEM : DMMT_E_CUDA); \
         }                                                        \
     } while (0)
-    PLAN_CUDA(cudaMalloc(&p->coef, (size_t)n_images * p->coef_stride * sizeof(int16_t)));
+    // the coefficient stream (6 B per padded pixel) only exists on the generic path: a fused 4:2:0 plan allocates it
+    // when somebody asks for that path (dmmt_plan_set_generic_path, dmmt_plan_debug_dct)
+    if (!k1_fused_supported(g, p->k1c)) PLAN_CUDA(cudaMalloc(&p->coef, (size_t)n_images * p->coef_stride * sizeof(int16_t)));
     PLAN_CUDA(cudaMalloc(&p->enc, (size_t)n_images * sizeof(EncTables)));
     PLAN_CUDA(cudaMalloc(&p->lens, (size_t)n_images * sizeof(LenTables)));
     PLAN_CUDA(cudaMalloc(&p->lcount, (size_t)n_images * 64));
@@ -367,10 +369,16 @@ extern "C" int dmmt_plan_set_scan_capacity(dmmt_plan* p, size_t bytes_per_image)
 
 extern "C" int dmmt_plan_uses_fused_path(const dmmt_plan* p) { return p && p->fused ? 1 : 0; }
 
+static int plan_ensure_coef(dmmt_plan* p) {
+    if (!p->coef) DMMT_CUDA(cudaMalloc(&p->coef, (size_t)p->n * p->coef_stride * sizeof(int16_t)));
+    return DMMT_OK;
+}
+
 extern "C" int dmmt_plan_set_generic_path(dmmt_plan* p, int generic) {
     if (!p) return DMMT_E_INVALID;
     DMMT_CUDA(cudaSetDevice(p->ctx->device));
     DMMT_CUDA(cudaStreamSynchronize(p->stream));
+    if (generic) DMMT_TRY(plan_ensure_coef(p));
     dmmt_plan_drop_graph(p);
     p->force_generic = generic ? 1 : 0;
     p->fused = k1_fused_supported(p->g, p->k1c) && !p->force_generic;
@@ -734,6 +742,7 @@ extern "C" int dmmt_plan_fetch(dmmt_plan* p, int what, int index, void* dst, siz
     DMMT_CUDA(cudaMemcpy(&m, p->meta + index, sizeof m, cudaMemcpyDeviceToHost));
     switch (what) {
         case DMMT_FETCH_COEF:
+            if (!p->coef) return DMMT_E_INVALID;  // the fused path never wrote one: dmmt_plan_set_generic_path first
             src = p->coef + (size_t)index * p->coef_stride, bytes = p->coef_stride * sizeof(int16_t);
             break;
         case DMMT_FETCH_HIST: src = p->hist + (size_t)index * 1024, bytes = 1024 * sizeof(unsigned int); break;
@@ -766,6 +775,7 @@ extern "C" int dmmt_plan_debug_dct(dmmt_plan* p, const void* d_pixels, int index
     if (!p || !d_pixels || !dst || index < 0 || index >= p->n) return DMMT_E_INVALID;
     if (cap_floats < p->coef_stride) return DMMT_E_WRITE;
     DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    DMMT_TRY(plan_ensure_coef(p));
     float* d_dbg = nullptr;
     DMMT_CUDA(cudaMalloc(&d_dbg, p->coef_stride * sizeof(float)));
     const uint8_t* px = static_cast<const uint8_t*>(d_pixels) + (size_t)index * p->pixel_bytes;
