@@ -520,6 +520,7 @@ __device__ __forceinline__ void or_bits(uint32_t* words, unsigned long long pos,
 
 constexpr int K3_RUN = 8;                    // consecutive tokens per lane and step
 constexpr int K3_STEP = 32 * K3_RUN;         // tokens per warp step
+constexpr int K3_HALF_STEP = K3_STEP / 2;    // the fast path's tail step: 4 tokens per lane
 
 // tokens [base, base + 8) into registers; tokens at or beyond `end` read as 0
 __device__ __forceinline__ void load_run(const uint32_t* __restrict__ tok, uint32_t base, uint32_t end,
@@ -656,18 +657,6 @@ __device__ __forceinline__ unsigned long long emit_range(const uint32_t* __restr
 // as up to three words.  Tokens beyond the range read as K3_PAD_TOKEN, whose LUT entry is {0, 0}; a symbol
 // without a code has bit 31 set in its entry (the output of such an image is discarded, encoder.rs:381-386).
 // Any other step (ZRLs, very long codes) goes through emit_step.
-// tokens [base, base + 8) into registers; tokens at or beyond `end` read as the pad token
-__device__ __forceinline__ void load_run_padded(const uint32_t* __restrict__ tok, uint32_t base, uint32_t end,
-                                                uint32_t (&t)[K3_RUN]) {
-    if (base + K3_RUN <= end) {
-        const uint4* p = reinterpret_cast<const uint4*>(tok + base);  // chunk bases and `base` are multiples of 8
-        const uint4 v0 = __ldg(p), v1 = __ldg(p + 1);
-        t[0] = v0.x, t[1] = v0.y, t[2] = v0.z, t[3] = v0.w, t[4] = v1.x, t[5] = v1.y, t[6] = v1.z, t[7] = v1.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < K3_RUN; i++) t[i] = (base + i < end) ? __ldg(tok + base + i) : K3_PAD_TOKEN;
-    }
-}
 // PTX shifts clamp the amount at 32 (a C shift by 32 is undefined); the pair / quad merges below rely on that
 __device__ __forceinline__ uint32_t shl32(uint32_t v, uint32_t n) {
     uint32_t r;
@@ -698,6 +687,84 @@ __device__ __forceinline__ void or_quad(uint32_t wsa, uint32_t pos, uint32_t hi,
     red_or_shared(wa + 8, __funnelshift_r(0u, llo, sft));
 #endif
 }
+// `RUN` (8 or 4) tokens of every lane = one warp step of the fast path; tokens beyond the range are pad tokens
+template <int RUN>
+__device__ __forceinline__ void load_run_fast(const uint32_t* __restrict__ tok, uint32_t base, uint32_t end, uint32_t (&t)[K3_RUN]) {
+    if (base + RUN <= end) {
+        const uint4* p = reinterpret_cast<const uint4*>(tok + base);  // region bases and `base` are multiples of RUN
+        const uint4 v0 = __ldg(p);
+        t[0] = v0.x, t[1] = v0.y, t[2] = v0.z, t[3] = v0.w;
+        if constexpr (RUN == 8) {
+            const uint4 v1 = __ldg(p + 1);
+            t[4] = v1.x, t[5] = v1.y, t[6] = v1.z, t[7] = v1.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < RUN; i++) t[i] = (base + i < end) ? __ldg(tok + base + i) : K3_PAD_TOKEN;
+    }
+}
+template <int RUN>
+__device__ __forceinline__ uint32_t emit_step_fast(const uint32_t (&t)[K3_RUN], uint32_t base, uint32_t end, const uint2* s_enc2,
+                                                   uint32_t zl_y, uint32_t zl_c, uint32_t* words, uint32_t wsa, uint32_t bitpos,
+                                                   uint32_t cap, bool& sym_ok, bool& overflow) {
+    const int lane = threadIdx.x & 31;
+    uint32_t val[RUN], ln[RUN];
+    uint32_t tor = 0u, flags = 0u;
+    // ONE 64-bit LUT read per token, indexed by table | symbol | "one ZRL in front" (token bit 10): the second half of
+    // the LUT holds every AC symbol with its table's ZRL code (categorize.rs:139-142) already in front of it, so a
+    // run of 16..31 zeros costs nothing here.  Entries that do not fit 31 bits read as length 64 and fail the pair
+    // test below; two or three ZRLs (token bit 11, runs of 32.., rare) take the general path as well.
+#pragma unroll
+    for (int i = 0; i < RUN; i++) {
+        const uint2 e = s_enc2[t[i] & 0x7FFu];
+        val[i] = e.x | (t[i] >> 16);
+        ln[i] = e.y;
+        tor |= t[i];
+        // a symbol without a code has bit 31 of its entry set (and length 0); category bits only reach bit 15
+        flags |= val[i];
+    }
+    const bool hard = (tor & 0x800u) != 0u;
+    uint32_t lp[RUN / 2], lmax = 0u, nb = 0u;
+#pragma unroll
+    for (int i = 0; i < RUN / 2; i++) {
+        lp[i] = ln[2 * i] + ln[2 * i + 1];
+        lmax = max(lmax, lp[i]);
+        nb += lp[i];
+    }
+    const bool simple = !hard && lmax <= 32u;
+    if (__all_sync(0xffffffffu, simple)) {
+        if (flags >> 31) sym_ok = false;  // Error::HuffmanSymbolNotPresentInTranslator
+        uint32_t inc = nb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += u;
+        }
+        const uint32_t step_bits = __shfl_sync(0xffffffffu, inc, 31);
+        if (bitpos + step_bits > cap) overflow = true;  // warp-uniform
+        if (!overflow) {
+            // (a "no code" marker in bit 31 of a value ends up above the quad's valid bits and is shifted out by
+            // or_quad's left alignment; the output of such an image is discarded anyway, encoder.rs:381-386)
+            uint32_t at = bitpos + (inc - nb);
+#pragma unroll
+            for (int qd = 0; qd < RUN / 4; qd++) {
+                const uint32_t pa = shl32(val[4 * qd], ln[4 * qd + 1]) | val[4 * qd + 1];
+                const uint32_t pb = shl32(val[4 * qd + 2], ln[4 * qd + 3]) | val[4 * qd + 3];
+                const uint32_t lb = lp[2 * qd + 1], lq = lp[2 * qd] + lb;
+                or_quad(wsa, at, shr32(pa, 32u - lb), shl32(pa, lb) | pb, lq);
+                at += lq;
+            }
+        }
+        return step_bits;
+    }
+    uint32_t t8[K3_RUN];
+#pragma unroll
+    for (int i = 0; i < K3_RUN; i++) t8[i] = i < RUN ? t[i] : K3_PAD_TOKEN;
+    const int n = base < end ? (int)min((uint32_t)RUN, end - base) : 0;
+    return emit_step<true>(t8, n, s_enc2, zl_y, zl_c, words, bitpos, cap, sym_ok, overflow);
+}
+// The last 128 or fewer tokens of a range go as a HALF step (4 tokens per lane, one quad): a tile of the `photo` batch
+// holds 343 tokens on average, which two full steps would pad to 512.
 __device__ __forceinline__ unsigned long long emit_range_fast(const uint32_t* __restrict__ tok, uint32_t begin,
                                                               uint32_t end, const uint2* s_enc2, uint32_t zl_y, uint32_t zl_c, uint32_t* words,
                                                               unsigned long long cap_bits, bool& sym_ok, bool& overflow) {
@@ -708,71 +775,44 @@ __device__ __forceinline__ unsigned long long emit_range_fast(const uint32_t* __
     // the tokens of step k + 1 are requested before step k is processed (the chain of bit positions makes the
     // steps sequential, so the load latency would otherwise be exposed once per step)
     uint32_t tn[K3_RUN];
-    load_run_padded(tok, begin + lane * K3_RUN, end, tn);
-    for (uint32_t wbase = begin; wbase < end; wbase += K3_STEP) {
-        const uint32_t base = wbase + lane * K3_RUN;
+#pragma unroll
+    for (int i = 0; i < K3_RUN; i++) tn[i] = K3_PAD_TOKEN;
+    uint32_t wbase = begin;
+    bool full = wbase < end && end - wbase > K3_HALF_STEP;  // warp-uniform
+    if (wbase < end) {
+        if (full) load_run_fast<8>(tok, wbase + lane * 8, end, tn);
+        else load_run_fast<4>(tok, wbase + lane * 4, end, tn);
+    }
+    while (wbase < end) {
         uint32_t t[K3_RUN];
 #pragma unroll
         for (int i = 0; i < K3_RUN; i++) t[i] = tn[i];
-        if (wbase + K3_STEP < end) load_run_padded(tok, base + K3_STEP, end, tn);
-        uint32_t val[K3_RUN], ln[K3_RUN];
-#pragma unroll
-        for (int i = 0; i < K3_RUN; i++) {
-            const uint2 e = s_enc2[t[i] & 0x3FFu];
-            val[i] = e.x | (t[i] >> 16);
-            ln[i] = e.y;
+        const bool cur_full = full;
+        const uint32_t nxt = wbase + (cur_full ? (uint32_t)K3_STEP : (uint32_t)K3_HALF_STEP);
+        if (nxt < end) {
+            full = end - nxt > K3_HALF_STEP;
+            if (full) load_run_fast<8>(tok, nxt + lane * 8, end, tn);
+            else load_run_fast<4>(tok, nxt + lane * 4, end, tn);
         }
-        const uint32_t tor = (t[0] | t[1] | t[2]) | (t[3] | t[4] | t[5]) | (t[6] | t[7]);
-        // a symbol without a code has bit 31 of its entry set (and length 0); category bits only reach bit 15
-        const uint32_t flags = (val[0] | val[1] | val[2]) | (val[3] | val[4] | val[5]) | (val[6] | val[7]);
-        bool hard = false;
-        if (__any_sync(0xffffffffu, (tor & 0xC00u) != 0u)) {
-            // some token of this step follows a run of 16.. zeros: ONE ZRL code (categorize.rs:139-142) goes in front
-            // of its own code; two or three of them (runs of 32.., very rare) take the general path
-#pragma unroll
-            for (int i = 0; i < K3_RUN; i++) {
-                const uint32_t nz = (t[i] >> 10) & 3u;
-                if (nz == 1u) {
-                    const uint2 z = s_enc2[(t[i] & 0x300u) | tok_swz(t[i] >> 8 & 3u, 0xF0u)];
-                    hard |= ln[i] + z.y > 32u || (z.x >> 31) != 0u;
-                    val[i] |= shl32(z.x & 0xFFFFu, ln[i]);
-                    ln[i] += z.y;
-                } else if (nz) {
-                    hard = true;
-                }
-            }
-        }
-        const uint32_t l01 = ln[0] + ln[1], l23 = ln[2] + ln[3], l45 = ln[4] + ln[5], l67 = ln[6] + ln[7];
-        const uint32_t q0 = l01 + l23, q1 = l45 + l67, nb = q0 + q1;
-        const bool simple = !hard && max(max(l01, l23), max(l45, l67)) <= 32u;
-        if (__all_sync(0xffffffffu, simple)) {
-            if (flags >> 31) sym_ok = false;  // Error::HuffmanSymbolNotPresentInTranslator
-            uint32_t inc = nb;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += u;
-            }
-            const uint32_t step_bits = __shfl_sync(0xffffffffu, inc, 31);
-            if (bitpos + step_bits > cap) overflow = true;  // warp-uniform
-            if (!overflow) {
-                // (a "no code" marker in bit 31 of a value ends up above the quad's valid bits and is shifted out by
-                // or_quad's left alignment; the output of such an image is discarded anyway, encoder.rs:381-386)
-                const uint32_t p01 = shl32(val[0], ln[1]) | val[1], p23 = shl32(val[2], ln[3]) | val[3];
-                const uint32_t p45 = shl32(val[4], ln[5]) | val[5], p67 = shl32(val[6], ln[7]) | val[7];
-                const uint32_t at = bitpos + (inc - nb);
-                or_quad(wsa, at, shr32(p01, 32u - l23), shl32(p01, l23) | p23, q0);
-                or_quad(wsa, at + q0, shr32(p45, 32u - l67), shl32(p45, l67) | p67, q1);
-            }
-            bitpos += step_bits;
-        } else {
-            const int n = base < end ? (int)min((uint32_t)K3_RUN, end - base) : 0;
-            bitpos += emit_step<true>(t, n, s_enc2, zl_y, zl_c, words, bitpos, cap_bits, sym_ok, overflow);
-        }
+        if (cur_full) bitpos += emit_step_fast<8>(t, wbase + lane * 8, end, s_enc2, zl_y, zl_c, words, wsa, bitpos, cap, sym_ok, overflow);
+        else bitpos += emit_step_fast<4>(t, wbase + lane * 4, end, s_enc2, zl_y, zl_c, words, wsa, bitpos, cap, sym_ok, overflow);
+        wbase = nxt;
     }
     return bitpos;
 }
 
+// Installs LUT entries of raw code-table entry `e` (len << 16 | code) of (table, symbol) = i: the token's own
+// {code << cat, len + cat}, and at + 0x400 the same token behind ONE ZRL of its table (raw entry `ez`)
+__device__ __forceinline__ void k3_install(uint2* s_enc2, uint32_t i, uint32_t e, uint32_t ez) {
+    const uint32_t len = e >> 16, code = e & 0xFFFFu, cat = i & 15u, tbl = i >> 8;
+    const uint32_t at = (i & 0x300u) | tok_swz(tbl, i & 255u);
+    s_enc2[at] = len ? make_uint2(code << cat, len + cat) : make_uint2(i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
+    const uint32_t zlen = ez >> 16, tot = len + cat + zlen;
+    const bool fast = (tbl == T_YAC || tbl == T_CAC) && len && zlen && tot <= 31u;
+    s_enc2[0x400u | at] = fast ? make_uint2(((ez & 0xFFFFu) << (len + cat)) | (code << cat), tot) : make_uint2(0u, 64u);
+}
+
+constexpr size_t K3_LUT_BYTES = 2 * 4 * 256 * sizeof(uint2);  // dynamic shared memory of both K3 kernels
 constexpr int K3_WBUF_WORDS = 576;  // per-warp private bit buffer: 18432 bits; two of them per warp (pipelined chunks)
 
 __device__ __forceinline__ uint32_t k3_load_ntok(const K3Args& a, int img, uint32_t chunk, int wid) {
@@ -791,7 +831,7 @@ __device__ __forceinline__ uint32_t k3_load_ntok(const K3Args& a, int img, uint3
 // token counts are requested while the current chunk is being packed.
 __global__ void __launch_bounds__(EB, 4) k3_pack(const K3Args a) {
     __shared__ __align__(16) uint32_t s_wbuf[2][EB / 32][K3_WBUF_WORDS];
-    __shared__ __align__(8) uint2 s_enc2[4 * 256];
+    extern __shared__ __align__(16) uint2 s_enc2[];   // K3_LUT_BYTES: [one ZRL in front][table][symbol, swizzled]
     __shared__ uint32_t s_wsum[EB / 32];
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned int s_next;
@@ -810,11 +850,7 @@ __global__ void __launch_bounds__(EB, 4) k3_pack(const K3Args a) {
     // images flagged by K1/K2/K2b (range / capacity) are skipped; K3 itself only ever adds DMMT_E_SYMBOL
     if (tid == 0) s_err_next = *reinterpret_cast<volatile int32_t*>(&a.meta[cur_img].error);
     for (int i = tid; i < 1024; i += EB) {
-        const uint32_t e = a.enc[cur_img].e[i >> 8][i & 255];
-        const uint32_t len = e >> 16, cat = (uint32_t)i & 15u;
-        s_enc2[(i & 0x300) | tok_swz((uint32_t)i >> 8, (uint32_t)i & 255u)] =
-            len ? make_uint2((e & 0xFFFFu) << cat, len + cat)
-                : make_uint2((uint32_t)i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
+        k3_install(s_enc2, (uint32_t)i, a.enc[cur_img].e[i >> 8][i & 255], a.enc[cur_img].e[i >> 8][0xF0]);
     }
     uint32_t ntok_cur = k3_load_ntok(a, cur_img, item % a.n_chunks, wid);
     __syncthreads();
@@ -883,10 +919,13 @@ __global__ void __launch_bounds__(EB, 4) k3_pack(const K3Args a) {
             }
         }
         // requests for the next chunk: code table and error flag if the image changes, token count
-        uint32_t e_next[1024 / EB];
+        uint32_t e_next[1024 / EB], z_next[1024 / EB];
         if (nimg != cur_img) {
 #pragma unroll
-            for (int k = 0; k < 1024 / EB; k++) e_next[k] = a.enc[nimg].e[(tid + k * EB) >> 8][(tid + k * EB) & 255];
+            for (int k = 0; k < 1024 / EB; k++) {
+                e_next[k] = a.enc[nimg].e[(tid + k * EB) >> 8][(tid + k * EB) & 255];
+                z_next[k] = a.enc[nimg].e[(tid + k * EB) >> 8][0xF0];
+            }
             if (tid == 0) s_err_next = *reinterpret_cast<volatile int32_t*>(&a.meta[nimg].error);
         }
         const uint32_t ntok_next = nhave ? k3_load_ntok(a, nimg, nitem % a.n_chunks, wid) : 0u;
@@ -942,11 +981,7 @@ __global__ void __launch_bounds__(EB, 4) k3_pack(const K3Args a) {
         if (nimg != cur_img) {  // every warp is past its emission: install the next image's table
 #pragma unroll
             for (int k = 0; k < 1024 / EB; k++) {
-                const uint32_t i = (uint32_t)tid + k * EB, e = e_next[k];
-                const uint32_t len = e >> 16, cat = i & 15u;
-                s_enc2[(i & 0x300u) | tok_swz(i >> 8, i & 255u)] =
-                    len ? make_uint2((e & 0xFFFFu) << cat, len + cat)
-                        : make_uint2(i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
+                k3_install(s_enc2, (uint32_t)tid + k * EB, e_next[k], z_next[k]);
             }
         }
         __syncthreads();  // (c) table, error flag ready; s_wsum / s_next / s_prefix may be rewritten
@@ -973,7 +1008,7 @@ __global__ void __launch_bounds__(EB, 4) k3_pack(const K3Args a) {
 #endif
 __global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
     __shared__ __align__(16) uint32_t s_wbuf[2][EB / 32][K3_WBUF_WORDS];
-    __shared__ __align__(8) uint2 s_enc2[4 * 256];
+    extern __shared__ __align__(16) uint2 s_enc2[];   // K3_LUT_BYTES: [one ZRL in front][table][symbol, swizzled]
     __shared__ int s_err_img;
     __shared__ unsigned int s_left;
 
@@ -994,11 +1029,7 @@ __global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
         const bool img_active = s_left != 0u && (err == 0 || err == DMMT_E_SYMBOL);
         if (!img_active) continue;  // nothing left (or an image flagged by K1 / K2b: skipped, K3 only ever adds DMMT_E_SYMBOL)
         for (int i = tid; i < 1024; i += EB) {
-            const uint32_t e = a.enc[img].e[i >> 8][i & 255];
-            const uint32_t len = e >> 16, cat = (uint32_t)i & 15u;
-            s_enc2[(i & 0x300) | tok_swz((uint32_t)i >> 8, (uint32_t)i & 255u)] =
-                len ? make_uint2((e & 0xFFFFu) << cat, len + cat)
-                    : make_uint2((uint32_t)i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
+            k3_install(s_enc2, (uint32_t)i, a.enc[img].e[i >> 8][i & 255], a.enc[img].e[i >> 8][0xF0]);
         }
         __syncthreads();
         const uint32_t zl_y = s_enc2[T_YAC * 256 + tok_swz(T_YAC, 0xF0u)].y, zl_c = s_enc2[T_CAC * 256 + tok_swz(T_CAC, 0xF0u)].y;
@@ -1447,10 +1478,20 @@ cudaError_t launch_k3(uint32_t n_chunks, uint32_t n_segs, int n, const TokBuf& t
              n_chunks * (uint32_t)n};
     // persistent CTAs, exactly as many as the device holds at once (a larger grid would run a second,
     // partly empty wave)
+    // 37 KB of static + 16 KB of dynamic shared memory: above the 48 KB default, so both kernels opt in (per device)
+    static bool opted[64] = {};
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !opted[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k3_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_LUT_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k3_pack_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3_LUT_BYTES);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) opted[dev] = true;
+    }
     static int resident = 0;
     if (!resident) {
         int per_sm = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_pack, EB, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_pack, EB, K3_LUT_BYTES);
         if (e != cudaSuccess) return e;
         resident = (per_sm > 0 ? per_sm : 1) * sm_count();
     }
@@ -1462,17 +1503,17 @@ cudaError_t launch_k3(uint32_t n_chunks, uint32_t n_segs, int n, const TokBuf& t
         static int resident_t = 0;
         if (!resident_t) {
             int per_sm = 0;
-            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_pack_tiles, EB, 0);
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_pack_tiles, EB, K3_LUT_BYTES);
             if (e != cudaSuccess) return e;
             resident_t = (per_sm > 0 ? per_sm : 1) * sm_count();
         }
         const uint32_t want = (a.n_items + EB / 32 - 1) / (EB / 32);
         const uint32_t grid_t = want < (uint32_t)resident_t ? want : (uint32_t)resident_t;
-        k3_pack_tiles<<<grid_t ? grid_t : 1u, EB, 0, st>>>(a);
+        k3_pack_tiles<<<grid_t ? grid_t : 1u, EB, K3_LUT_BYTES, st>>>(a);
         return cudaGetLastError();
     }
     const uint32_t grid = a.n_items < (uint32_t)resident ? a.n_items : (uint32_t)resident;
-    k3_pack<<<grid ? grid : 1u, EB, 0, st>>>(a);
+    k3_pack<<<grid ? grid : 1u, EB, K3_LUT_BYTES, st>>>(a);
     return cudaGetLastError();
 }
 
