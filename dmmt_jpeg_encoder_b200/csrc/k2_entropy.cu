@@ -668,9 +668,13 @@ __device__ __forceinline__ uint32_t shr32(uint32_t v, uint32_t n) {
     asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
     return r;
 }
-// OR into a shared-memory word unless the value is zero: one compare and one predicated reduction
+// OR into a shared-memory word (unconditionally: ptxas turns a predicated reduction into a branch around it)
 __device__ __forceinline__ void red_or_shared(uint32_t saddr, uint32_t v) {
+#ifdef K3_COND_RED   // A/B: skip zero values (compare + branch around the reduction): 2.5 % slower
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.or.b32 [%0], %1;\n\t}" ::"r"(saddr), "r"(v) : "memory");
+#else
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+#endif
 }
 // ORs the `len` (<= 64) bits held right-aligned in (hi:lo) at bit position `pos` of the warp's private bit buffer
 // (shared address `wsa`, host byte order): up to three words
@@ -1040,17 +1044,20 @@ __global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
         bool pend = false;  // the previous tile of this warp is packed in s_wbuf[buf ^ 1][wid] and waits for its position
         int buf = 0;
         uint32_t p_tile = 0, p_bits = 0;
+        // the ticket and the token count of the NEXT tile are requested while the current one is packed / copied out
+        // (a ticket holder only ever waits for lower tickets, all of which are held by running warps)
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(&a.ticket[img], 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        uint32_t ntok = tile < tiles ? a.tb.ntok[(size_t)img * tiles + tile] : 0u;
         while (true) {
-            uint32_t tile = 0;
-            if (lane == 0) tile = atomicAdd(&a.ticket[img], 1u);
-            tile = __shfl_sync(0xffffffffu, tile, 0);
             const bool have = tile < tiles;
+            uint32_t next_raw = 0;
+            if (have && lane == 0) next_raw = atomicAdd(&a.ticket[img], 1u);
             uint32_t wbits = 0;
             bool cur_ovf = false;
             const uint32_t* __restrict__ tok = tok_img + (size_t)tile * a.tb.chunk_cap;
-            uint32_t ntok = 0;
             if (have) {
-                ntok = a.tb.ntok[(size_t)img * tiles + tile];
                 uint32_t* wbuf = s_wbuf[buf][wid];
                 for (int i = lane; i < K3_WBUF_WORDS / 4; i += 32) reinterpret_cast<uint4*>(wbuf)[i] = make_uint4(0, 0, 0, 0);
                 __syncwarp();
@@ -1062,6 +1069,8 @@ __global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
                 __syncwarp();
                 if (lane == 0) lookback_publish_aggregate(lb, (int)tile, wbits);
             }
+            const uint32_t tile_next = have ? __shfl_sync(0xffffffffu, next_raw, 0) : tile;
+            const uint32_t ntok_next = tile_next < tiles ? a.tb.ntok[(size_t)img * tiles + tile_next] : 0u;
             if (pend) {
                 // shifted copy of the private buffer to its place: destination word k holds relative bits
                 // [32k - s, 32k - s + 32); the first and last word are shared with the neighbours
@@ -1104,6 +1113,7 @@ __global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
                 p_tile = tile, p_bits = wbits;
                 buf ^= 1;
             }
+            tile = tile_next, ntok = ntok_next;
         }
     }
 }
@@ -1150,7 +1160,10 @@ struct K4Args {
 constexpr int K4_ROW = K4_BYTES_PER_THREAD + 16;              // padded row: conflict-free 128-bit access
 constexpr int K4_OUT_WORDS = (2 * K4_CHUNK + 16 + 16) / 4;    // worst case: every byte is 0xFF
 
-__global__ void __launch_bounds__(K4_THREADS) k4_stuff(const K4Args a) {
+#ifndef K4_MINB
+#define K4_MINB 8
+#endif
+__global__ void __launch_bounds__(K4_THREADS, K4_MINB) k4_stuff(const K4Args a) {
     __shared__ __align__(16) uint8_t s_in[K4_THREADS * K4_ROW];
     __shared__ __align__(16) uint32_t s_out[K4_OUT_WORDS];
     __shared__ uint32_t s_warp[K4_THREADS / 32 + 1];
