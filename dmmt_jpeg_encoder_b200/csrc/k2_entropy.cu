@@ -769,24 +769,30 @@ __device__ __forceinline__ uint32_t emit_step_fast(const uint32_t (&t)[K3_RUN], 
 }
 // The last 128 or fewer tokens of a range go as a HALF step (4 tokens per lane, one quad): a tile of the `photo` batch
 // holds 343 tokens on average, which two full steps would pad to 512.
+// first step of a range: its tokens requested ahead of time (`full`: a full step follows, else the half step)
+__device__ __forceinline__ void emit_first_run(const uint32_t* __restrict__ tok, uint32_t begin, uint32_t end, uint32_t (&tn)[K3_RUN],
+                                               bool& full) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < K3_RUN; i++) tn[i] = K3_PAD_TOKEN;
+    full = begin < end && end - begin > K3_HALF_STEP;  // warp-uniform
+    if (begin < end) {
+        if (full) load_run_fast<8>(tok, begin + lane * 8, end, tn);
+        else load_run_fast<4>(tok, begin + lane * 4, end, tn);
+    }
+}
+// `tn` / `full` come from emit_first_run(tok, begin, end, ..) -- called by the caller as early as it knows the range
 __device__ __forceinline__ unsigned long long emit_range_fast(const uint32_t* __restrict__ tok, uint32_t begin,
                                                               uint32_t end, const uint2* s_enc2, uint32_t zl_y, uint32_t zl_c, uint32_t* words,
-                                                              unsigned long long cap_bits, bool& sym_ok, bool& overflow) {
+                                                              unsigned long long cap_bits, bool& sym_ok, bool& overflow,
+                                                              uint32_t (&tn)[K3_RUN], bool full) {
     const int lane = threadIdx.x & 31;
     const uint32_t wsa = (uint32_t)__cvta_generic_to_shared(words);
     const uint32_t cap = (uint32_t)cap_bits;
     uint32_t bitpos = 0u;  // the private buffer holds < 2^32 bits
     // the tokens of step k + 1 are requested before step k is processed (the chain of bit positions makes the
     // steps sequential, so the load latency would otherwise be exposed once per step)
-    uint32_t tn[K3_RUN];
-#pragma unroll
-    for (int i = 0; i < K3_RUN; i++) tn[i] = K3_PAD_TOKEN;
     uint32_t wbase = begin;
-    bool full = wbase < end && end - wbase > K3_HALF_STEP;  // warp-uniform
-    if (wbase < end) {
-        if (full) load_run_fast<8>(tok, wbase + lane * 8, end, tn);
-        else load_run_fast<4>(tok, wbase + lane * 4, end, tn);
-    }
     while (wbase < end) {
         uint32_t t[K3_RUN];
 #pragma unroll
@@ -895,8 +901,11 @@ __global__ void __launch_bounds__(EB, 4) k3_pack(const K3Args a) {
             for (int i = lane; i < K3_WBUF_WORDS / 4; i += 32) reinterpret_cast<uint4*>(wbuf)[i] = make_uint4(0, 0, 0, 0);
             __syncwarp();
             bool sym_ok = true, ovf = false;
+            uint32_t tn[K3_RUN];
+            bool full;
+            emit_first_run(tok, begin, end, tn, full);
             wbits = (uint32_t)emit_range_fast(tok, begin, end, s_enc2, zl_y, zl_c, wbuf,
-                                              (unsigned long long)K3_WBUF_WORDS * 32 - 64, sym_ok, ovf);
+                                              (unsigned long long)K3_WBUF_WORDS * 32 - 64, sym_ok, ovf, tn, full);
             if (!sym_ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_SYMBOL);
             if (ovf && lane == 0) s_ovf_tag = item + 1u;
         }
@@ -1050,6 +1059,9 @@ __global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
         if (lane == 0) tile = atomicAdd(&a.ticket[img], 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         uint32_t ntok = tile < tiles ? a.tb.ntok[(size_t)img * tiles + tile] : 0u;
+        uint32_t tn[K3_RUN];  // first tokens of `tile`: requested before the previous tile is copied out
+        bool tn_full = false;
+        if (tile < tiles) emit_first_run(tok_img + (size_t)tile * a.tb.chunk_cap, 0u, ntok, tn, tn_full);
         while (true) {
             const bool have = tile < tiles;
             uint32_t next_raw = 0;
@@ -1063,7 +1075,7 @@ __global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
                 __syncwarp();
                 bool sym_ok = true, ovf = false;
                 wbits = (uint32_t)emit_range_fast(tok, 0u, ntok, s_enc2, zl_y, zl_c, wbuf,
-                                                  (unsigned long long)K3_WBUF_WORDS * 32 - 64, sym_ok, ovf);
+                                                  (unsigned long long)K3_WBUF_WORDS * 32 - 64, sym_ok, ovf, tn, tn_full);
                 if (!sym_ok) atomicCAS(&a.meta[img].error, 0, DMMT_E_SYMBOL);
                 cur_ovf = ovf;
                 __syncwarp();
@@ -1071,6 +1083,7 @@ __global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
             }
             const uint32_t tile_next = have ? __shfl_sync(0xffffffffu, next_raw, 0) : tile;
             const uint32_t ntok_next = tile_next < tiles ? a.tb.ntok[(size_t)img * tiles + tile_next] : 0u;
+            if (have && tile_next < tiles) emit_first_run(tok_img + (size_t)tile_next * a.tb.chunk_cap, 0u, ntok_next, tn, tn_full);
             if (pend) {
                 // shifted copy of the private buffer to its place: destination word k holds relative bits
                 // [32k - s, 32k - s + 32); the first and last word are shared with the neighbours
