@@ -791,3 +791,60 @@ extern "C" int dmmt_plan_debug_dct(dmmt_plan* p, const void* d_pixels, int index
     }
     return DMMT_OK;
 }
+
+extern "C" int dmmt_debug_stuff(dmmt_ctx* ctx, const uint8_t* scan, size_t n, int misalign, uint8_t* out, size_t cap,
+                                size_t* got) {
+    if (!ctx || (!scan && n) || !out || !got || misalign < 0 || misalign > 15) return DMMT_E_INVALID;
+    DMMT_CUDA(cudaSetDevice(ctx->device));
+    const size_t out_cap = 2 * n + 64;
+    const uint32_t chunks = k4_max_chunks(n + 1);
+    uint8_t *d_scan = nullptr, *d_out = nullptr;
+    ImgMeta* d_meta = nullptr;
+    unsigned long long* d_lb = nullptr;
+    unsigned int* d_tk = nullptr;
+    auto release = [&]() {
+        (void)cudaFree(d_scan), (void)cudaFree(d_out), (void)cudaFree(d_meta), (void)cudaFree(d_lb), (void)cudaFree(d_tk);
+    };
+    ImgMeta m{};
+    m.scan_bits = 8ull * n;
+    cudaError_t e = cudaMalloc(&d_scan, n + 64);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, out_cap + 16);
+    if (e == cudaSuccess) e = cudaMalloc(&d_meta, sizeof(ImgMeta));
+    if (e == cudaSuccess) e = cudaMalloc(&d_lb, (size_t)chunks * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d_tk, 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_scan, 0xA5, n + 64, ctx->stream);  // bytes past the end are not zero
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(d_scan, scan, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_out, 0xEE, out_cap + 16, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_meta, &m, sizeof(m), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_lb, 0, (size_t)chunks * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_tk, 0, 4, ctx->stream);
+    if (e == cudaSuccess) {
+        K4HostArgs k{};
+        k.scan = d_scan, k.scan_stride_bytes = n + 64, k.meta = d_meta, k.lb_state = d_lb, k.ticket = d_tk;
+        k.max_chunks = chunks, k.out = d_out + misalign, k.out_stride = out_cap, k.out_lens = nullptr;
+        k.first_byte = 0, k.n_bytes_override = (long long)n, k.seed_bits = 0, k.prepend_header = 0, k.append_eoi = 1;
+        e = launch_k4(k, 1, chunks, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&m, d_meta, sizeof(m), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    int rc = DMMT_OK;
+    if (e == cudaSuccess) {
+        if (m.error) rc = m.error;
+        else if (m.out_len > cap) rc = DMMT_E_WRITE;
+        else {
+            *got = (size_t)m.out_len;
+            // one byte before and after the file as well: the kernel must not touch them
+            e = cudaMemcpy(out, d_out + misalign, (size_t)m.out_len, cudaMemcpyDeviceToHost);
+            uint8_t guard[2] = {0, 0};
+            if (e == cudaSuccess && misalign) e = cudaMemcpy(&guard[0], d_out + misalign - 1, 1, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(&guard[1], d_out + misalign + m.out_len, 1, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess && ((misalign && guard[0] != 0xEE) || guard[1] != 0xEE)) rc = DMMT_E_WRITE;  // a byte outside the file was written
+        }
+    }
+    release();
+    if (e != cudaSuccess) {
+        dmmt_set_cuda_error(e, "debug K4", __FILE__, __LINE__);
+        return DMMT_E_CUDA;
+    }
+    return rc;
+}

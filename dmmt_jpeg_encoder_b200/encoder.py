@@ -60,6 +60,15 @@ class Context:
     def synchronize(self):
         F.check(F.lib().dmmt_ctx_synchronize(self._h), "dmmt_ctx_synchronize")
 
+    def debug_stuff(self, scan: bytes, misalign: int = 0) -> bytes:
+        """dmmt_debug_stuff: K4 alone on an unstuffed scan -> stuffed bytes + EOI (test hook)."""
+        src = np.frombuffer(scan, np.uint8) if len(scan) else np.zeros(1, np.uint8)
+        dst = np.empty(2 * len(scan) + 64, np.uint8)
+        got = C.c_size_t(0)
+        F.check(F.lib().dmmt_debug_stuff(self._h, src.ctypes.data_as(C.c_void_p), len(scan), misalign,
+                                         dst.ctypes.data_as(C.c_void_p), dst.size, C.byref(got)), "dmmt_debug_stuff")
+        return dst[:got.value].tobytes()
+
     def encode(self, pixels: np.ndarray, max_value: int = 255, options: Options = Options()) -> bytes:
         """dmmt_encode on host pixels [H, W, 3] (u8 / u16 / f32 normalised)."""
         px = np.ascontiguousarray(pixels)

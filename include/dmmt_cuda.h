@@ -209,6 +209,10 @@ int dmmt_plan_fetch(dmmt_plan *, int what, int index, void *dst, size_t cap_byte
  * of image `index`: runs the debug variant of K1 on d_pixels (device) and copies to host. */
 int dmmt_plan_debug_dct(dmmt_plan *, const void *d_pixels, int index, float *dst, size_t cap_floats);
 size_t dmmt_plan_stream_blocks(const dmmt_plan *);
+/* test hook, K4 alone: stuffs the `n` bytes of an unstuffed scan (host memory) the way the last stage of dmmt_encode
+ * does (segment_marker_injector.rs:13-30: 0x00 after every 0xFF; EOI appended, encoder.rs:164-167) into a device buffer
+ * that starts `misalign` (0..15) bytes after a 16-byte boundary, and copies the result to `out`. */
+int dmmt_debug_stuff(dmmt_ctx *, const uint8_t *scan, size_t n, int misalign, uint8_t *out, size_t cap, size_t *got);
 
 /* ---- one-process-per-GPU sharding of ONE image by MCU rows -------------------- */
 /* A shard plan covers MCU rows [mcu_row_begin, mcu_row_end) of a full_width x full_height image.

@@ -321,6 +321,43 @@ def test_all_ff_scan_stuffing(D, ctx, O):
     assert found > 0
 
 
+def test_stuffing_kernel_alone_on_nasty_scans(D, ctx, O):
+    """K4 by itself (dmmt_debug_stuff) against the oracle's byte stuffing (segment_marker_injector.rs:13-30): scans made
+    of 0xFF only, 0xFF at every chunk / thread / word boundary, random densities, lengths around the 8 KB chunk size,
+    every alignment of the destination."""
+    rng = np.random.default_rng(11)
+    K = 8192
+
+    def check(scan: bytes, misalign: int = 0):
+        got = ctx.debug_stuff(scan, misalign)
+        want = scan.replace(b"\xff", b"\xff\x00") + b"\xff\xd9"
+        assert got == want, (len(scan), misalign, next(i for i in range(min(len(got), len(want)) + 1)
+                                                       if i >= min(len(got), len(want)) or got[i] != want[i]))
+
+    assert O.stuff_bytes(b"\x01\xff\xff\x02") == b"\x01\xff\x00\xff\x00\x02"   # the replace() above is the oracle's rule
+    check(b"")
+    for n in (1, 2, 15, 16, 17, 31, 32, 33, 255, K - 1, K, K + 1, 2 * K - 1, 2 * K, 2 * K + 1, 5 * K + 123):
+        check(bytes([0xFF]) * n)                                                  # every byte stuffed
+        check(bytes(rng.integers(0, 256, n, dtype=np.uint8)), misalign=n % 16)     # about 0.4 % of 0xFF
+        a = rng.integers(0, 255, n, dtype=np.uint8)                                # no 0xFF at all
+        check(a.tobytes(), misalign=(n * 7) % 16)
+        a[::2] = 0xFF                                                              # alternating
+        check(a.tobytes(), misalign=(n * 3) % 16)
+    for period in (4, 16, 32, 33, 512, K, K + 1):                                  # 0xFF at word / thread / chunk boundaries
+        a = rng.integers(0, 255, 3 * K + 77, dtype=np.uint8)
+        a[period - 1::period] = 0xFF
+        check(a.tobytes(), misalign=5)
+        a[period::period] = 0xFF                                                   # ... and pairs across the boundary
+        check(a.tobytes(), misalign=11)
+    for dens in (0.02, 0.1, 0.3, 0.7):
+        a = rng.integers(0, 255, 4 * K + 1000, dtype=np.uint8)
+        a[rng.random(a.size) < dens] = 0xFF
+        for mis in range(16):
+            check(a[: a.size - mis * 37].tobytes(), misalign=mis)
+    big = rng.integers(0, 256, 3_000_000, dtype=np.uint8)                          # 367 chunks: the look-back chain
+    check(big.tobytes(), misalign=9)
+
+
 # ------------------------------------------------------------------------------- errors
 def test_sample_above_max_is_rejected(D, ctx):
     from dmmt_jpeg_encoder_b200 import _ffi as F
