@@ -1346,6 +1346,220 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINB) k4_stuff(const K4Args a) 
     }
 }
 
+// K4, output-centric ("gather") form -- the one that is launched.  Same chunking, ticket, look-back and file layout as
+// k4_stuff above; what differs is how a chunk's bytes reach the file.  k4_stuff pushes: every thread ORs its 32 input bytes,
+// spread around their 0xFF bytes, into a zeroed shared tile (8 x 3 shared-memory atomics, 8-way bank conflicts), and the
+// tile is copied out afterwards.  Here every thread PULLS one 16-byte unit of the FILE at a time:
+//   1. the chunk is staged linearly; the thread that loads a 16-byte unit also derives its 16 0xFF flags (bitmap)
+//   2. 0xFF count per 32-byte group (one popc), CTA scan -> s_ex[g] = stuffing zeros in front of group g; look-back
+//   3. unit u of the file holds chunk-output offsets [16u - mis, 16u - mis + 16): find the group g with
+//      32 g + s_ex[g] <= o (guess o / 32, step down), then the source byte inside the group from the group's flags;
+//      two aligned 128-bit shared loads + a realignment give the 16 source bytes, the bitmap their 0xFF flags;
+//      a unit without a stuffing zero (93 % of them) is done -- otherwise one byte-insertion per zero (PRMT);
+//      one aligned 128-bit store (byte stores only in the first and last unit of the chunk).
+// No zeroed tile, no atomics, no second pass: 360 instead of 800 instructions per thread and chunk.
+#ifndef K4_GATHER
+#define K4_GATHER 1
+#endif
+#ifndef K4G_MINB
+#define K4G_MINB 6
+#endif
+// inserts a zero byte at byte position pk (0..15) of the 16 bytes in r[0..3]; the bytes from pk on move up, byte 15 drops out
+__device__ __forceinline__ void k4_insert_zero(uint32_t (&r)[4], uint32_t pk) {
+    uint32_t o[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const int d = (int)pk - 4 * w;                     // position of the zero relative to this word
+        const uint32_t dc = (uint32_t)max(d, 0);
+        // output byte j of the word comes from pair byte 4 + j (j < d) or 3 + j (j >= d), pair = {r[w - 1], r[w]}
+        const uint32_t sel = 0x7654u - (0x1111u & shl32(0xFFFFu, 4u * dc));
+        const uint32_t v = __byte_perm(w ? r[w - 1] : 0u, r[w], sel);
+        o[w] = v & ~shl32(0xFFu, 8u * (uint32_t)d);        // d outside 0..3: the shift clamps to 0, nothing is cleared
+    }
+#pragma unroll
+    for (int w = 0; w < 4; w++) r[w] = o[w];
+}
+__global__ void __launch_bounds__(K4_THREADS, K4G_MINB) k4_stuff_gather(const K4Args a) {
+    __shared__ __align__(16) uint8_t s_in[K4_CHUNK + 32];      // the chunk, linear; the 32 bytes behind it stay zero
+    __shared__ __align__(4) uint16_t s_bm16[K4_CHUNK / 16 + 4];  // 0xFF flags, 16 per staged unit (= one u32 per 32-byte group)
+    __shared__ uint32_t s_ex[K4_THREADS + 1];
+    __shared__ uint32_t s_warp[K4_THREADS / 32 + 1];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_chunk;
+    const uint32_t* s_bm = reinterpret_cast<const uint32_t*>(s_bm16);
+    const int img = blockIdx.y, tid = threadIdx.x;
+    ImgMeta* meta = a.meta + img;
+    if (meta->error) {
+        if (blockIdx.x == 0 && tid == 0 && a.out_lens) a.out_lens[img] = 0ull;
+        return;
+    }
+    const unsigned long long seed = a.seed_src ? (*a.seed_src & 7ull) : a.seed_bits;
+    const unsigned long long total_bytes =
+        a.owned_mode == 1 ? (seed + meta->scan_bits) / 8
+        : a.owned_mode == 2 ? (seed + meta->scan_bits + 7) / 8
+        : a.n_bytes_override >= 0 ? (unsigned long long)a.n_bytes_override
+                                  : (seed + meta->scan_bits + 7) / 8 - a.first_byte;
+    const uint32_t or_first = a.or_first_src ? (uint32_t)(*a.or_first_src & 0xFF) : (uint32_t)a.or_first_byte;
+    const uint32_t n_chunks = (uint32_t)((total_bytes + K4_CHUNK - 1) / K4_CHUNK);
+    const unsigned long long hdr = (a.prepend_header ? meta->header_len : 0u) + (a.base_src ? *a.base_src : 0ull);
+    uint8_t* out = a.out + (size_t)img * a.out_stride;
+    if (n_chunks == 0) {  // nothing owned (possible for a shard); still terminate the file
+        if (blockIdx.x == 0 && tid == 0) {
+            unsigned long long len = hdr;
+            if (a.append_eoi) out[len] = 0xFF, out[len + 1] = 0xD9, len += 2;
+            meta->out_len = len;
+            if (a.out_lens) a.out_lens[img] = len;
+        }
+        return;
+    }
+    const uint8_t* __restrict__ src = a.scan + (size_t)img * a.scan_img_stride_bytes + a.first_byte;
+    const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    if (tid < 8) reinterpret_cast<uint32_t*>(s_in + K4_CHUNK)[tid] = 0u;
+    if (tid < 4) s_bm16[K4_CHUNK / 16 + tid] = 0;
+
+    while (true) {
+        __syncthreads();  // the previous chunk's staging area is free
+        if (tid == 0) s_chunk = atomicAdd(&a.ticket[img], 1u);
+        __syncthreads();
+        const uint32_t chunk = s_chunk;
+        if (chunk >= n_chunks) return;
+        const unsigned long long cbase = (unsigned long long)chunk * K4_CHUNK;
+        const uint32_t cvalid = (uint32_t)min((unsigned long long)K4_CHUNK, total_bytes - cbase);
+
+        // 1. stage the chunk and its 0xFF flags (reads may run past cvalid inside the padded scan buffer: masked)
+#pragma unroll
+        for (int it = 0; it < K4_CHUNK / 16 / K4_THREADS; it++) {
+            const int j = it * K4_THREADS + tid;  // 16-byte unit of the chunk
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            const int nv = (int)cvalid - 16 * j;  // valid bytes of this unit
+            if (nv > 0) {
+                const uint8_t* p = src + cbase + (size_t)j * 16;
+                if (src_aligned) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(p);
+                    w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        w[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) |
+                               ((uint32_t)p[4 * k + 3] << 24);
+                }
+                if (nv < 16) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int vw = nv - 4 * k;
+                        if (vw < 4) w[k] &= vw <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - vw)));  // bytes past the end: 0 (never 0xFF)
+                    }
+                }
+                if (j == 0 && chunk == 0) w[0] |= or_first;
+            }
+            *reinterpret_cast<uint4*>(s_in + j * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            uint32_t flags = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; k++)  // 0xFF per matching byte -> one bit per byte
+                flags |= (((__vcmpeq4(w[k], 0xFFFFFFFFu) & 0x08040201u) * 0x01010101u) >> 24) << (4 * k);
+            s_bm16[j] = (uint16_t)flags;
+        }
+        __syncthreads();
+
+        // 2. stuffing zeros in front of every 32-byte group, and of the chunk (look-back)
+        uint32_t chunk_ff;
+        const uint32_t ff_before = block_exclusive_scan<K4_THREADS>((uint32_t)__popc(s_bm[tid]), s_warp, &chunk_ff);
+        s_ex[tid] = ff_before;
+        if (tid == 0) {
+            s_ex[K4_THREADS] = chunk_ff;
+            s_prefix = lookback_exclusive(a.lb_state + (size_t)img * a.max_chunks, (int)chunk, chunk_ff);
+        }
+        __syncthreads();
+        const unsigned long long gs = hdr + cbase + s_prefix;  // file offset of the chunk's first output byte
+        const uint32_t n_out = cvalid + chunk_ff;
+        const bool last = chunk == n_chunks - 1;
+        if (gs + n_out + 2ull > a.out_stride) {
+            // Error::FailedToWriteImageData: the image's slot of the output arena is too small
+            if (tid == 0) {
+                atomicCAS(&meta->error, 0, a.slot_err);
+                if (last) {
+                    meta->out_len = 0ull;
+                    if (a.out_lens) a.out_lens[img] = 0ull;
+                }
+            }
+            continue;
+        }
+        const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(out) + gs) & 15);
+        uint8_t* dst16 = out + gs - mis;  // 16-byte aligned; unit u of the chunk is dst16 + 16 u
+        const uint32_t n_units = (mis + n_out + 15u) >> 4;
+
+        // 3. one 16-byte unit of the file per thread and round
+        for (uint32_t u = tid; u < n_units; u += K4_THREADS) {
+            const int o_lo = (int)(16u * u) - (int)mis;            // chunk-output offset of the unit's first byte
+            const uint32_t o = (uint32_t)max(o_lo, 0);
+            // group: the last one that starts at or before o
+            uint32_t g = min(o >> 5, (uint32_t)K4_THREADS - 1u);
+            uint32_t gstart = 32u * g + s_ex[g];
+            while (gstart > o) {
+                --g;
+                gstart = 32u * g + s_ex[g];
+            }
+            const uint32_t op = o - gstart;                        // offset inside the group's output
+            // source byte of the group that output offset op shows, or the stuffing zero in front of it (pending)
+            uint32_t mm = s_bm[g], cnt = 0u;
+            bool pending = false;
+            while (mm) {
+                const uint32_t z = (uint32_t)__ffs((int)mm) + cnt;  // output offset of the zero behind this 0xFF
+                if (z > op) break;
+                if (z == op) {
+                    pending = true;
+                    break;
+                }
+                ++cnt;
+                mm &= mm - 1u;
+            }
+            const uint32_t i = 32u * g + (op - cnt);               // next source byte of the chunk
+            // 16 source bytes from i on: two aligned 128-bit loads, word select, byte shift
+            uint32_t r[4];
+            {
+                const uint4 lo = *reinterpret_cast<const uint4*>(s_in + (i & ~15u));
+                const uint4 hi = *reinterpret_cast<const uint4*>(s_in + (i & ~15u) + 16);
+                const uint32_t W[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                uint32_t X[6], Y[5];
+#pragma unroll
+                for (int k = 0; k < 6; k++) X[k] = (i & 8u) ? W[k + 2] : W[k];
+#pragma unroll
+                for (int k = 0; k < 5; k++) Y[k] = (i & 4u) ? X[k + 1] : X[k];
+                const uint32_t bs = 8u * (i & 3u);
+#pragma unroll
+                for (int k = 0; k < 4; k++) r[k] = __funnelshift_r(Y[k], Y[k + 1], bs);
+            }
+            // their 0xFF flags; bit k of `ins`: a zero goes in front of source byte k of the window
+            const uint32_t q = __funnelshift_r(s_bm[i >> 5], s_bm[(i >> 5) + 1], i & 31u);
+            uint32_t ins = ((q << 1) | (pending ? 1u : 0u)) & 0xFFFFu;
+            uint32_t c = 0u;
+            while (ins) {
+                const uint32_t pk = (uint32_t)__ffs((int)ins) - 1u + c;
+                if (pk >= 16u) break;
+                ins &= ins - 1u;
+                k4_insert_zero(r, pk);
+                ++c;
+            }
+            if (o_lo >= 0 && (uint32_t)o_lo + 16u <= n_out) {
+                *reinterpret_cast<uint4*>(dst16 + 16u * u) = make_uint4(r[0], r[1], r[2], r[3]);
+            } else {
+                // first / last unit of the chunk: only the bytes of this chunk (the neighbours write the others)
+                const uint32_t cntb = min((uint32_t)(o_lo + 16), n_out) - o;
+                uint8_t* d = dst16 + 16u * u + (o - (uint32_t)o_lo);
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    if ((uint32_t)k < cntb) d[k] = (uint8_t)(r[k >> 2] >> (8 * (k & 3)));
+            }
+        }
+        if (last && tid == 0) {
+            unsigned long long len = gs + n_out;
+            if (a.append_eoi) out[len] = 0xFF, out[len + 1] = 0xD9, len += 2;
+            meta->out_len = len;
+            if (a.out_lens) a.out_lens[img] = len;
+        }
+    }
+}
+
 // extracts the quantised DC of the last Y / Cb / Cr block (shard hand-over)
 __global__ void k_last_dc(const int16_t* coef, uint32_t n_blocks, int ypm, int bpm, int16_t* out3) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -1554,7 +1768,11 @@ cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStre
     if (per_image < 8) per_image = 8;
     if (grid_chunks == 0) grid_chunks = 1;
     if (per_image > grid_chunks) per_image = grid_chunks;
+#if K4_GATHER
+    k4_stuff_gather<<<dim3(per_image, n), K4_THREADS, 0, st>>>(a);
+#else
     k4_stuff<<<dim3(per_image, n), K4_THREADS, 0, st>>>(a);
+#endif
     return cudaGetLastError();
 }
 
