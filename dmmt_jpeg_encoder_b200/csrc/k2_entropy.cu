@@ -1362,7 +1362,17 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINB) k4_stuff(const K4Args a) 
 #define K4_GATHER 1
 #endif
 #ifndef K4G_MINB
-#define K4G_MINB 6
+#define K4G_MINB 8
+#endif
+// input bytes per chunk: 128 short of the 8 KB the CTA stages, so that the output (input + stuffing zeros + misalignment)
+// still fits 512 file units = two full rounds of the 256 threads (8192 bytes of input made round three a 3-unit straggler)
+#ifndef K4G_CHUNK_BYTES
+#define K4G_CHUNK_BYTES 8064
+#endif
+constexpr int K4G_CHUNK = K4G_CHUNK_BYTES;
+static_assert(K4G_CHUNK % 32 == 0 && K4G_CHUNK <= K4_CHUNK, "whole 32-byte groups, at most one per thread");
+#ifndef K4G_WARP_LB
+#define K4G_WARP_LB 0
 #endif
 // inserts a zero byte at byte position pk (0..15) of the 16 bytes in r[0..3]; the bytes from pk on move up, byte 15 drops out
 __device__ __forceinline__ void k4_insert_zero(uint32_t (&r)[4], uint32_t pk) {
@@ -1380,7 +1390,7 @@ __device__ __forceinline__ void k4_insert_zero(uint32_t (&r)[4], uint32_t pk) {
     for (int w = 0; w < 4; w++) r[w] = o[w];
 }
 __global__ void __launch_bounds__(K4_THREADS, K4G_MINB) k4_stuff_gather(const K4Args a) {
-    __shared__ __align__(16) uint8_t s_in[K4_CHUNK + 32];      // the chunk, linear; the 32 bytes behind it stay zero
+    __shared__ __align__(16) uint8_t s_in[K4_CHUNK + 32];       // the chunk, linear; the 32 bytes behind it stay zero
     __shared__ __align__(4) uint16_t s_bm16[K4_CHUNK / 16 + 4];  // 0xFF flags, 16 per staged unit (= one u32 per 32-byte group)
     __shared__ uint32_t s_ex[K4_THREADS + 1];
     __shared__ uint32_t s_warp[K4_THREADS / 32 + 1];
@@ -1400,7 +1410,7 @@ __global__ void __launch_bounds__(K4_THREADS, K4G_MINB) k4_stuff_gather(const K4
         : a.n_bytes_override >= 0 ? (unsigned long long)a.n_bytes_override
                                   : (seed + meta->scan_bits + 7) / 8 - a.first_byte;
     const uint32_t or_first = a.or_first_src ? (uint32_t)(*a.or_first_src & 0xFF) : (uint32_t)a.or_first_byte;
-    const uint32_t n_chunks = (uint32_t)((total_bytes + K4_CHUNK - 1) / K4_CHUNK);
+    const uint32_t n_chunks = (uint32_t)((total_bytes + K4G_CHUNK - 1) / K4G_CHUNK);
     const unsigned long long hdr = (a.prepend_header ? meta->header_len : 0u) + (a.base_src ? *a.base_src : 0ull);
     uint8_t* out = a.out + (size_t)img * a.out_stride;
     if (n_chunks == 0) {  // nothing owned (possible for a shard); still terminate the file
@@ -1416,28 +1426,39 @@ __global__ void __launch_bounds__(K4_THREADS, K4G_MINB) k4_stuff_gather(const K4
     const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
     if (tid < 8) reinterpret_cast<uint32_t*>(s_in + K4_CHUNK)[tid] = 0u;
     if (tid < 4) s_bm16[K4_CHUNK / 16 + tid] = 0;
+    constexpr int UPT = K4_CHUNK / 16 / K4_THREADS;  // 16-byte units staged per thread
 
-    while (true) {
-        __syncthreads();  // the previous chunk's staging area is free
+    // The ticket and the bytes of the NEXT chunk are requested while the current one is scanned and written: a chunk
+    // otherwise pays two dependent memory round trips (ticket, scan bytes) before its first instruction of real work.
+    uint4 pre[UPT];  // raw units of `chunk` (aligned scans only)
+    auto request = [&](uint32_t c) {
+#pragma unroll
+        for (int it = 0; it < UPT; it++) {
+            const int j = it * K4_THREADS + tid;
+            pre[it] = make_uint4(0, 0, 0, 0);
+            if (src_aligned && c < n_chunks && (unsigned long long)c * K4G_CHUNK + (unsigned)j * 16u < total_bytes)
+                pre[it] = *reinterpret_cast<const uint4*>(src + (unsigned long long)c * K4G_CHUNK + (size_t)j * 16);
+        }
+    };
+    if (tid == 0) s_chunk = atomicAdd(&a.ticket[img], 1u);
+    __syncthreads();
+    uint32_t chunk = s_chunk;
+    request(chunk);
+    while (chunk < n_chunks) {
+        __syncthreads();  // everybody has read s_chunk and is done with the previous chunk's staging area
         if (tid == 0) s_chunk = atomicAdd(&a.ticket[img], 1u);
-        __syncthreads();
-        const uint32_t chunk = s_chunk;
-        if (chunk >= n_chunks) return;
-        const unsigned long long cbase = (unsigned long long)chunk * K4_CHUNK;
-        const uint32_t cvalid = (uint32_t)min((unsigned long long)K4_CHUNK, total_bytes - cbase);
+        const unsigned long long cbase = (unsigned long long)chunk * K4G_CHUNK;
+        const uint32_t cvalid = (uint32_t)min((unsigned long long)K4G_CHUNK, total_bytes - cbase);
 
         // 1. stage the chunk and its 0xFF flags (reads may run past cvalid inside the padded scan buffer: masked)
 #pragma unroll
-        for (int it = 0; it < K4_CHUNK / 16 / K4_THREADS; it++) {
+        for (int it = 0; it < UPT; it++) {
             const int j = it * K4_THREADS + tid;  // 16-byte unit of the chunk
-            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            uint32_t w[4] = {pre[it].x, pre[it].y, pre[it].z, pre[it].w};
             const int nv = (int)cvalid - 16 * j;  // valid bytes of this unit
             if (nv > 0) {
-                const uint8_t* p = src + cbase + (size_t)j * 16;
-                if (src_aligned) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(p);
-                    w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
-                } else {
+                if (!src_aligned) {
+                    const uint8_t* p = src + cbase + (size_t)j * 16;
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         w[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) |
@@ -1451,6 +1472,8 @@ __global__ void __launch_bounds__(K4_THREADS, K4G_MINB) k4_stuff_gather(const K4
                     }
                 }
                 if (j == 0 && chunk == 0) w[0] |= or_first;
+            } else {
+                w[0] = w[1] = w[2] = w[3] = 0u;
             }
             *reinterpret_cast<uint4*>(s_in + j * 16) = make_uint4(w[0], w[1], w[2], w[3]);
             uint32_t flags = 0u;
@@ -1459,16 +1482,40 @@ __global__ void __launch_bounds__(K4_THREADS, K4G_MINB) k4_stuff_gather(const K4
                 flags |= (((__vcmpeq4(w[k], 0xFFFFFFFFu) & 0x08040201u) * 0x01010101u) >> 24) << (4 * k);
             s_bm16[j] = (uint16_t)flags;
         }
-        __syncthreads();
+        __syncthreads();  // the chunk, its flags and the next ticket are visible
+        const uint32_t next = s_chunk;
+        request(next);
 
-        // 2. stuffing zeros in front of every 32-byte group, and of the chunk (look-back)
-        uint32_t chunk_ff;
-        const uint32_t ff_before = block_exclusive_scan<K4_THREADS>((uint32_t)__popc(s_bm[tid]), s_warp, &chunk_ff);
-        s_ex[tid] = ff_before;
-        if (tid == 0) {
-            s_ex[K4_THREADS] = chunk_ff;
-            s_prefix = lookback_exclusive(a.lb_state + (size_t)img * a.max_chunks, (int)chunk, chunk_ff);
+        // 2. stuffing zeros in front of every 32-byte group (warp scan + the warp totals, re-added by every warp: one
+        //    barrier), and in front of the chunk (look-back)
+        const int lane = tid & 31, wid = tid >> 5;
+        const uint32_t nff = (uint32_t)__popc(s_bm[tid]);
+        uint32_t inc = nff;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
         }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        uint32_t wbase = 0u, chunk_ff = 0u;
+#pragma unroll
+        for (int w = 0; w < K4_THREADS / 32; w++) {
+            const uint32_t v = s_warp[w];
+            if (w < wid) wbase += v;
+            chunk_ff += v;
+        }
+        s_ex[tid] = wbase + inc - nff;
+#if K4G_WARP_LB
+        if (wid == 0) {
+            unsigned long long* lb = a.lb_state + (size_t)img * a.max_chunks;
+            if (lane == 0) lookback_publish_aggregate(lb, (int)chunk, chunk_ff);
+            const unsigned long long ex = lookback_resolve_warp(lb, (int)chunk, chunk_ff);
+            if (lane == 0) s_prefix = ex;
+        }
+#else
+        if (tid == 0) s_prefix = lookback_exclusive(a.lb_state + (size_t)img * a.max_chunks, (int)chunk, chunk_ff);
+#endif
         __syncthreads();
         const unsigned long long gs = hdr + cbase + s_prefix;  // file offset of the chunk's first output byte
         const uint32_t n_out = cvalid + chunk_ff;
@@ -1482,6 +1529,7 @@ __global__ void __launch_bounds__(K4_THREADS, K4G_MINB) k4_stuff_gather(const K4
                     if (a.out_lens) a.out_lens[img] = 0ull;
                 }
             }
+            chunk = next;
             continue;
         }
         const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(out) + gs) & 15);
@@ -1557,6 +1605,7 @@ __global__ void __launch_bounds__(K4_THREADS, K4G_MINB) k4_stuff_gather(const K4
             meta->out_len = len;
             if (a.out_lens) a.out_lens[img] = len;
         }
+        chunk = next;
     }
 }
 
@@ -1696,7 +1745,10 @@ cudaError_t launch_zero_scan(uint32_t* scan, size_t stride_words, const ImgMeta*
     return cudaGetLastError();
 }
 
-uint32_t k4_max_chunks(size_t scan_cap_bytes) { return (uint32_t)((scan_cap_bytes + K4_CHUNK - 1) / K4_CHUNK); }
+uint32_t k4_max_chunks(size_t scan_cap_bytes) {
+    constexpr size_t chunk = K4_GATHER ? K4G_CHUNK : K4_CHUNK;
+    return (uint32_t)((scan_cap_bytes + chunk - 1) / chunk);
+}
 
 // SMs of the current device (queried once per device; every context of this library sets its device first)
 static int sm_count() {
