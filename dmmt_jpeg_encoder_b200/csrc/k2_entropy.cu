@@ -1031,6 +1031,7 @@ __global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
     const int first_img = (int)((unsigned long long)blockIdx.x * (unsigned)n / gridDim.x);
     const unsigned long long seed = a.seed_src ? (*a.seed_src & 7ull) : a.seed_bits;
     const int visits = n < 3 ? n : 3;  // own image, then help the next two
+    const bool ahead = a.n_items >= 2u * gridDim.x * (EB / 32);
     for (int v = 0; v < visits; v++) {
         const int img = (first_img + v) % n;
         if (tid == 0) {
@@ -1054,7 +1055,8 @@ __global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
         int buf = 0;
         uint32_t p_tile = 0, p_bits = 0;
         // the ticket and the token count of the NEXT tile are requested while the current one is packed / copied out
-        // (a ticket holder only ever waits for lower tickets, all of which are held by running warps)
+        // (a ticket holder only ever waits for lower tickets, all of which are held by running warps) -- unless there
+        // are about as many warps as tiles (a single frame): a ticket taken ahead would then keep a tile from an idle warp
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(&a.ticket[img], 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
@@ -1065,7 +1067,7 @@ __global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
         while (true) {
             const bool have = tile < tiles;
             uint32_t next_raw = 0;
-            if (have && lane == 0) next_raw = atomicAdd(&a.ticket[img], 1u);
+            if (have && ahead && lane == 0) next_raw = atomicAdd(&a.ticket[img], 1u);
             uint32_t wbits = 0;
             bool cur_ovf = false;
             const uint32_t* __restrict__ tok = tok_img + (size_t)tile * a.tb.chunk_cap;
@@ -1081,6 +1083,7 @@ __global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
                 __syncwarp();
                 if (lane == 0) lookback_publish_aggregate(lb, (int)tile, wbits);
             }
+            if (have && !ahead && lane == 0) next_raw = atomicAdd(&a.ticket[img], 1u);
             const uint32_t tile_next = have ? __shfl_sync(0xffffffffu, next_raw, 0) : tile;
             const uint32_t ntok_next = tile_next < tiles ? a.tb.ntok[(size_t)img * tiles + tile_next] : 0u;
             if (have && tile_next < tiles) emit_first_run(tok_img + (size_t)tile_next * a.tb.chunk_cap, 0u, ntok_next, tn, tn_full);
