@@ -102,6 +102,9 @@ SIGNATURES = {
     "dmmt_plan_last_launch_count": (C.c_int, [_VP]),
     "dmmt_plan_fetch": (C.c_int, [_VP, C.c_int, C.c_int, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dmmt_plan_debug_dct": (C.c_int, [_VP, _VP, C.c_int, C.POINTER(C.c_float), C.c_size_t]),
+    "dmmt_mailbox_bytes": (C.c_size_t, [C.c_int]),
+    "dmmt_shard_launch_post": (C.c_int, [_VP, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_ulonglong, _VP, C.c_int]),
+    "dmmt_shard_launch_collect": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_ulonglong, C.c_int, C.c_int, _VP]),
     "dmmt_debug_stuff": (C.c_int, [_VP, _VP, C.c_size_t, C.c_int, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dmmt_plan_stream_blocks": (C.c_size_t, [_VP]),
     "dmmt_shard_create": (C.c_int, [_VP, C.c_uint16, C.c_uint16, C.c_int, C.c_uint16, C.POINTER(Options),

@@ -106,6 +106,12 @@ struct PeerPtrs {
     const void* p[DMMT_MAX_PEER_SHARDS];
 };
 cudaError_t launch_peer_exchange(const PeerPtrs& srcs, int n, int elems, int mode, long long* out, cudaStream_t st);
+// mailbox exchange between processes (see k_mailbox_post / k_mailbox_collect)
+size_t mailbox_bytes(int world, int slots);
+cudaError_t launch_mailbox_post(const PeerPtrs& boxes, int world, int rank, int slot, unsigned long long seq, const void* src,
+                                int n_words, cudaStream_t st);
+cudaError_t launch_mailbox_collect(void* box, int world, int slot, unsigned long long seq, int mode, int n_words, long long* out,
+                                   ImgMeta* meta, cudaStream_t st);
 // device-resident shard exchange helpers
 cudaError_t launch_shard_widen(const int16_t* last_dc3, int* out4, const unsigned int* hist, long long* hist64,
                                const ImgMeta* meta, long long* bits_out, cudaStream_t st, long long* err_out = nullptr);

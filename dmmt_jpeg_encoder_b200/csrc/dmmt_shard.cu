@@ -466,6 +466,39 @@ extern "C" int dmmt_shard_launch_count(const dmmt_shard* s) { return s ? s->plan
 
 // scan capacity of the shard's plan (see dmmt_plan_set_scan_capacity): DMMT_E_OVERFLOW from any phase means "grow and
 // run the phases again from dmmt_shard_transform / dmmt_shard_launch_transform"
+// ---- mailbox exchange (one process per GPU, no collective library on the data path) ----
+extern "C" size_t dmmt_mailbox_bytes(int world) {
+    return world > 0 && world <= DMMT_MAX_PEER_SHARDS ? mailbox_bytes(world, DMMT_MAILBOX_SLOTS) : 0;
+}
+extern "C" int dmmt_shard_launch_post(dmmt_shard* s, void* const* d_mailboxes, int rank, int world, int slot,
+                                      unsigned long long seq, const void* d_src, int n_words64) {
+    if (!s || !d_mailboxes || !d_src || world < 1 || world > DMMT_MAX_PEER_SHARDS || rank < 0 || rank >= world || slot < 0 ||
+        slot >= DMMT_MAILBOX_SLOTS || n_words64 < 1 || n_words64 > 1024 || seq == 0)
+        return DMMT_E_INVALID;
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    PeerPtrs pp{};
+    for (int r = 0; r < world; r++) {
+        if (!d_mailboxes[r]) return DMMT_E_INVALID;
+        pp.p[r] = d_mailboxes[r];
+    }
+    DMMT_CUDA(launch_mailbox_post(pp, world, rank, slot, seq, d_src, n_words64, p->stream));
+    p->last_launches += 1;
+    return DMMT_OK;
+}
+extern "C" int dmmt_shard_launch_collect(dmmt_shard* s, void* d_own_mailbox, int world, int slot, unsigned long long seq,
+                                         int mode, int n_words64, int64_t* d_out) {
+    if (!s || !d_own_mailbox || !d_out || world < 1 || world > DMMT_MAX_PEER_SHARDS || slot < 0 || slot >= DMMT_MAILBOX_SLOTS ||
+        mode < 0 || mode > 2 || n_words64 < 1 || n_words64 > 1024 || (mode == 2 && n_words64 != 1) || seq == 0)
+        return DMMT_E_INVALID;
+    dmmt_plan* p = s->plan;
+    DMMT_CUDA(cudaSetDevice(p->ctx->device));
+    DMMT_CUDA(launch_mailbox_collect(d_own_mailbox, world, slot, seq, mode, n_words64, reinterpret_cast<long long*>(d_out),
+                                     p->meta, p->stream));
+    p->last_launches += 1;
+    return DMMT_OK;
+}
+
 extern "C" size_t dmmt_shard_worst_case_scan_bytes(const dmmt_shard* s) {
     return s ? dmmt_plan_worst_case_scan_bytes(s->plan) : 0;
 }

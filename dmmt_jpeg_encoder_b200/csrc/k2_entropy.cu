@@ -1947,6 +1947,88 @@ cudaError_t launch_peer_exchange(const PeerPtrs& srcs, int n, int elems, int mod
     return cudaGetLastError();
 }
 
+// ---- mailbox exchange between PROCESSES (one per GPU): the values the shards of one image exchange ----------------
+// Every rank owns a mailbox in its device memory, mapped into the other processes through CUDA IPC.  k_mailbox_post
+// stores a rank's payload into row `rank` of slot `slot` of EVERY mailbox (its own and, over NVLink, the peers') and then
+// releases the row's flag with the sequence number of the encode; k_mailbox_collect, one kernel later on the same
+// stream, waits until all `world` flags of the slot carry that number and reduces / gathers the rows from LOCAL memory.
+// No host round trip, no library call: an exchange costs two small launches and one NVLink store latency.
+// A flag that does not arrive within MAILBOX_TIMEOUT_NS (a peer died) reports DMMT_E_NCCL instead of hanging the GPU.
+namespace {
+constexpr int MAILBOX_ROW_WORDS = 1024 + 8;          // payload (<= 1024 words of 8 bytes) + the flag word
+constexpr int MAILBOX_FLAG = 1024;
+constexpr unsigned long long MAILBOX_TIMEOUT_NS = 10ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ unsigned long long* mailbox_row(void* box, int world, int slot, int rank) {
+    return static_cast<unsigned long long*>(box) + ((size_t)slot * world + rank) * MAILBOX_ROW_WORDS;
+}
+__global__ void __launch_bounds__(256) k_mailbox_post(PeerPtrs boxes, int world, int rank, int slot, unsigned long long seq,
+                                                      const unsigned long long* __restrict__ src, int n_words) {
+    unsigned long long* row = mailbox_row(const_cast<void*>(boxes.p[blockIdx.x]), world, slot, rank);  // CTA = destination
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) row[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(row + MAILBOX_FLAG), "l"(seq) : "memory");
+}
+// mode 0: out[i] = sum over ranks (i < n_words); 1: out[r * n_words + i] (gather); 2 (n_words = 1): gather + exclusive
+// prefix sums in out[world ..]
+__global__ void __launch_bounds__(1024) k_mailbox_collect(void* box, int world, int slot, unsigned long long seq, int mode,
+                                                          int n_words, long long* out, ImgMeta* meta) {
+    __shared__ int s_timeout;
+    if (threadIdx.x == 0) s_timeout = 0;
+    __syncthreads();
+    if (threadIdx.x < world) {
+        const unsigned long long* flag = mailbox_row(box, world, slot, threadIdx.x) + MAILBOX_FLAG;
+        unsigned long long t0 = 0, v;
+        while (true) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+            if (v >= seq) break;
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            if (!t0) t0 = now;
+            if (now - t0 > MAILBOX_TIMEOUT_NS) {
+                s_timeout = 1;
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    if (s_timeout) {
+        if (threadIdx.x == 0 && meta) atomicCAS(&meta->error, 0, DMMT_E_NCCL);
+        return;
+    }
+    const int i = threadIdx.x;
+    if (mode == 0) {
+        for (int k = i; k < n_words; k += blockDim.x) {
+            long long acc = 0;
+            for (int r = 0; r < world; r++) acc += (long long)__ldcg(mailbox_row(box, world, slot, r) + k);
+            out[k] = acc;
+        }
+    } else {
+        for (int k = i; k < world * n_words; k += blockDim.x)
+            out[k] = (long long)__ldcg(mailbox_row(box, world, slot, k / n_words) + k % n_words);
+        if (mode == 2 && i == 0) {
+            long long run = 0;
+            for (int r = 0; r < world; r++) {
+                out[world + r] = run;
+                run += (long long)__ldcg(mailbox_row(box, world, slot, r));
+            }
+        }
+    }
+}
+}  // namespace
+size_t mailbox_bytes(int world, int slots) { return (size_t)slots * world * MAILBOX_ROW_WORDS * 8; }
+cudaError_t launch_mailbox_post(const PeerPtrs& boxes, int world, int rank, int slot, unsigned long long seq, const void* src,
+                                int n_words, cudaStream_t st) {
+    k_mailbox_post<<<world, 256, 0, st>>>(boxes, world, rank, slot, seq, static_cast<const unsigned long long*>(src), n_words);
+    return cudaGetLastError();
+}
+cudaError_t launch_mailbox_collect(void* box, int world, int slot, unsigned long long seq, int mode, int n_words, long long* out,
+                                   ImgMeta* meta, cudaStream_t st) {
+    k_mailbox_collect<<<1, 1024, 0, st>>>(box, world, slot, seq, mode, n_words, out, meta);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_shard_count_bytes(const uint8_t* scan, const ImgMeta* meta, const unsigned long long* seed_src,
                                      int owned_mode, const int* or_first_src, int is_first, int is_last,
                                      unsigned long long* ctr2, long long* n_bytes, cudaStream_t st) {

@@ -448,16 +448,82 @@ class PeerFile:
             pass
 
 
-def encode_sharded_peer(backend: CudaShardBackend, file: PeerFile, to_host: bool = True, mark=None):
+class PeerMailbox:
+    """The exchanges of the sharded encode WITHOUT a collective library on the data path: every rank owns a mailbox in
+    its HBM, mapped into the other processes through CUDA IPC (dmmt_mailbox_bytes, dmmt_peer_export / dmmt_peer_open);
+    dmmt_shard_launch_post stores a rank's values into every mailbox over NVLink and releases them with the sequence
+    number of the encode, dmmt_shard_launch_collect waits for all rows and sums / gathers them from local memory.
+    torch.distributed is only used here, once, to hand the IPC handles round.  Collective: every rank of `group`
+    constructs it after its CudaShardBackend and closes it with close()."""
+
+    DC, HIST, BITS, TAIL, NBYTES, RES = range(6)          # slots: one per exchange of an encode
+    SUM, GATHER, GATHER_SCAN = range(3)                   # modes of dmmt_shard_launch_collect
+
+    def __init__(self, backend: CudaShardBackend, group=None):
+        self.ctx, self.group = backend.ctx, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.seq = 0
+        self.bytes = int(F.lib().dmmt_mailbox_bytes(self.world))
+        if not self.bytes:
+            raise F.DmmtError(F.E_INVALID, "dmmt_mailbox_bytes")
+        self._own = C.c_void_p()
+        F.check(F.lib().dmmt_device_alloc(self.ctx.handle, self.bytes, C.byref(self._own)), "dmmt_device_alloc")
+        torch.as_tensor(_DevPtr(self._own.value, self.bytes), device=f"cuda:{self.ctx.device}").zero_()
+        torch.cuda.synchronize()
+        h = C.create_string_buffer(64)
+        F.check(F.lib().dmmt_peer_export(self.ctx.handle, self._own, h), "dmmt_peer_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, h.raw, group=group)
+        self._ptrs = (C.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                self._ptrs[r] = self._own.value
+            else:
+                q = C.c_void_p()
+                F.check(F.lib().dmmt_peer_open(self.ctx.handle, handles[r], C.byref(q)), "dmmt_peer_open")
+                self._ptrs[r] = q.value
+        dist.barrier(group=group)   # every mailbox is zeroed and mapped before anybody posts
+
+    def begin(self) -> int:
+        """sequence number of the next encode (the same on every rank: encodes are collective)"""
+        self.seq += 1
+        return self.seq
+
+    def exchange(self, backend: CudaShardBackend, slot: int, src: torch.Tensor, n_words: int, mode: int, out: torch.Tensor):
+        lib = F.lib()
+        F.check(lib.dmmt_shard_launch_post(backend._h, self._ptrs, self.rank, self.world, slot, self.seq,
+                                           C.c_void_p(src.data_ptr()), n_words), "dmmt_shard_launch_post")
+        F.check(lib.dmmt_shard_launch_collect(backend._h, self._own, self.world, slot, self.seq, mode, n_words,
+                                              C.c_void_p(out.data_ptr())), "dmmt_shard_launch_collect")
+
+    def close(self):
+        """Collective."""
+        if not self._own:
+            return
+        torch.cuda.synchronize()
+        for r in range(self.world):
+            if r != self.rank and self._ptrs[r]:
+                F.lib().dmmt_peer_close(self.ctx.handle, C.c_void_p(self._ptrs[r]))
+                self._ptrs[r] = None
+        dist.barrier(group=self.group)   # nobody maps this rank's mailbox any more
+        F.lib().dmmt_device_free(self.ctx.handle, self._own)
+        self._own = C.c_void_p()
+
+
+def encode_sharded_peer(backend: CudaShardBackend, file: PeerFile, to_host: bool = True, mark=None,
+                        mailbox: PeerMailbox | None = None):
     """see _encode_sharded_peer_once; DMMT_E_OVERFLOW on any shard: every rank grows its shard, runs once more"""
-    return _retry_on_overflow(_encode_sharded_peer_once, backend, file, to_host, mark)
+    return _retry_on_overflow(_encode_sharded_peer_once, backend, file, to_host, mark, mailbox)
 
 
-def _encode_sharded_peer_once(backend: CudaShardBackend, file: PeerFile, to_host: bool = True, mark=None):
+def _encode_sharded_peer_once(backend: CudaShardBackend, file: PeerFile, to_host: bool = True, mark=None,
+                              mailbox: PeerMailbox | None = None):
     """encode_sharded_device without the gather: after the tail exchange every shard counts its stuffed bytes
     (phase 5a), the counts are all-gathered and summed, and K4 (phase 5b) writes straight into `file` at the
     shard's final offset -- on the destination rank's own memory or, from the other ranks, over NVLink.  The
     closing all-gather of {end offset, error} is the completion barrier and the one host synchronisation.
+    With a `mailbox` the six exchanges are the library's own kernels over peer memory (PeerMailbox); without
+    one they are NCCL collectives on the same stream.
     Returns the file on the destination rank (bytes, or a view of `file` when to_host is False), None elsewhere."""
     group, dst = file.group, file.dst
     rank, world = file.rank, file.world
@@ -465,37 +531,58 @@ def _encode_sharded_peer_once(backend: CudaShardBackend, file: PeerFile, to_host
     b = getattr(backend, "_pbuf", None)
     if b is None or b["world"] != world:
         i32, i64 = dict(dtype=torch.int32, device=dev), dict(dtype=torch.int64, device=dev)
+        bits2, n2 = torch.empty(2 * world, **i64), torch.empty(2 * world, **i64)   # [values | exclusive prefix sums]
         b = backend._pbuf = {"world": world, "last": torch.empty(4, **i32), "all_dc": torch.empty(4 * world, **i32),
                              "hist": torch.empty(1024, **i64), "bits": torch.empty(1, **i64),
-                             "all_bits": torch.empty(world, **i64), "offs": torch.empty(world, **i64),
+                             "bits2": bits2, "all_bits": bits2[:world], "offs": bits2[world:],
                              "tail": torch.empty(2, **i32), "all_tail": torch.empty(2 * world, **i32),
-                             "n_bytes": torch.empty(1, **i64), "all_n": torch.empty(world, **i64),
-                             "byte_offs": torch.empty(world, **i64), "res": torch.empty(2, **i64),
-                             "all_res": torch.empty(2 * world, **i64)}
+                             "n_bytes": torch.empty(1, **i64), "n2": n2, "all_n": n2[:world], "byte_offs": n2[world:],
+                             "res": torch.empty(2, **i64), "all_res": torch.empty(2 * world, **i64)}
     mark = mark or (lambda name: None)
+    mb = mailbox
+    if mb is not None:
+        mb.begin()
     backend.launch_transform(b["last"].data_ptr())
-    dist.all_gather_into_tensor(b["all_dc"], b["last"], group=group)             # exchange 1: last DCs
+    if mb is not None:
+        mb.exchange(backend, mb.DC, b["last"], 2, mb.GATHER, b["all_dc"])
+    else:
+        dist.all_gather_into_tensor(b["all_dc"], b["last"], group=group)         # exchange 1: last DCs
     mark("transform")
     backend.launch_histogram(b["all_dc"].data_ptr() + 16 * (rank - 1) if rank else 0, b["hist"].data_ptr())
-    dist.all_reduce(b["hist"], op=dist.ReduceOp.SUM, group=group)                # exchange 2: global histograms
+    if mb is not None:
+        mb.exchange(backend, mb.HIST, b["hist"], 1024, mb.SUM, b["hist"])
+    else:
+        dist.all_reduce(b["hist"], op=dist.ReduceOp.SUM, group=group)            # exchange 2: global histograms
     mark("histogram")
     backend.launch_tables(b["hist"].data_ptr(), b["bits"].data_ptr())
-    dist.all_gather_into_tensor(b["all_bits"], b["bits"], group=group)           # exchange 3: bit counts
+    if mb is not None:
+        mb.exchange(backend, mb.BITS, b["bits"], 1, mb.GATHER_SCAN, b["bits2"])   # bit counts + exclusive bit offsets
+    else:
+        dist.all_gather_into_tensor(b["all_bits"], b["bits"], group=group)       # exchange 3: bit counts
+        torch.cumsum(b["all_bits"], 0, out=b["offs"])
+        b["offs"].sub_(b["all_bits"])                                            # exclusive global bit offsets
     mark("tables")
-    torch.cumsum(b["all_bits"], 0, out=b["offs"])
-    b["offs"].sub_(b["all_bits"])                                                # exclusive global bit offsets
     backend.launch_pack(b["offs"].data_ptr() + 8 * rank, rank == world - 1, b["tail"].data_ptr())
-    dist.all_gather_into_tensor(b["all_tail"], b["tail"], group=group)           # trailing partial bytes
+    if mb is not None:
+        mb.exchange(backend, mb.TAIL, b["tail"], 1, mb.GATHER, b["all_tail"])
+    else:
+        dist.all_gather_into_tensor(b["all_tail"], b["tail"], group=group)       # trailing partial bytes
     mark("pack")
     backend.launch_count_bytes(b["all_tail"].data_ptr(), b["offs"].data_ptr(), b["all_bits"].data_ptr(), rank, world,
                                b["n_bytes"].data_ptr())
-    dist.all_gather_into_tensor(b["all_n"], b["n_bytes"], group=group)           # exchange 4: byte counts, BEFORE K4
-    torch.cumsum(b["all_n"], 0, out=b["byte_offs"])
-    b["byte_offs"].sub_(b["all_n"])                                              # exclusive byte offsets in the file
+    if mb is not None:
+        mb.exchange(backend, mb.NBYTES, b["n_bytes"], 1, mb.GATHER_SCAN, b["n2"])  # byte counts + offsets in the file
+    else:
+        dist.all_gather_into_tensor(b["all_n"], b["n_bytes"], group=group)       # exchange 4: byte counts, BEFORE K4
+        torch.cumsum(b["all_n"], 0, out=b["byte_offs"])
+        b["byte_offs"].sub_(b["all_n"])                                          # exclusive byte offsets in the file
     mark("count")
     backend.launch_stuff_into(b["offs"].data_ptr(), rank, world, file.ptr, file.capacity,
                               b["byte_offs"].data_ptr() + 8 * rank, b["res"].data_ptr())
-    dist.all_gather_into_tensor(b["all_res"], b["res"], group=group)             # completion barrier + status
+    if mb is not None:
+        mb.exchange(backend, mb.RES, b["res"], 2, mb.GATHER, b["all_res"])
+    else:
+        dist.all_gather_into_tensor(b["all_res"], b["res"], group=group)         # completion barrier + status
     mark("stuff")
     res = b["all_res"].tolist()                                                  # the only host synchronisation
     mark("sync")

@@ -287,6 +287,24 @@ int dmmt_shard_launch_count_bytes(dmmt_shard *, const int32_t *d_all_tail2, cons
 int dmmt_shard_launch_stuff_into(dmmt_shard *, const int64_t *d_all_bit_offsets, int rank, int world, uint8_t *d_file,
                                  size_t file_capacity, const int64_t *d_byte_offset, int64_t *d_result2);
 
+/* Mailbox exchange: the small values the shards exchange between the phases, moved by the library's own kernels over
+ * peer memory instead of a collective library (one process per GPU on one NVLink / NVSwitch node).  Every rank allocates
+ * dmmt_mailbox_bytes(world) of ZEROED device memory (dmmt_device_alloc + cudaMemset, once), exports it and maps the
+ * others' (dmmt_peer_export / dmmt_peer_open).  dmmt_shard_launch_post stores n_words64 (<= 1024) 64-bit words into
+ * row `rank` of slot `slot` (0 .. DMMT_MAILBOX_SLOTS-1) of EVERY mailbox and releases the row with `seq`;
+ * dmmt_shard_launch_collect, launched after it on the same stream, waits until all rows of the slot carry a sequence
+ * number >= seq and writes d_out: mode 0 the element-wise sum over the ranks (n words), 1 the rows one after the other
+ * (world x n words), 2 (n = 1) the rows followed by their exclusive prefix sums (2 x world words).  `seq` must be the
+ * same on every rank and grow from one encode to the next (start at 1); a slot is used once per encode.  A peer that
+ * never posts makes the collect give up after 10 s with DMMT_E_NCCL in the shard's error flag (dmmt_shard_launch_error)
+ * rather than hang the device.  Asynchronous like the other dmmt_shard_launch_* calls. */
+#define DMMT_MAILBOX_SLOTS 8
+size_t dmmt_mailbox_bytes(int world);
+int dmmt_shard_launch_post(dmmt_shard *, void *const *d_mailboxes /* [world], own one included */, int rank, int world, int slot,
+                           unsigned long long seq, const void *d_src, int n_words64);
+int dmmt_shard_launch_collect(dmmt_shard *, void *d_own_mailbox, int world, int slot, unsigned long long seq, int mode,
+                              int n_words64, int64_t *d_out);
+
 /* ---- host ingest: ASCII P3 reader (replaces PPMImageReader::read_image, src/image/reader/ppm.rs:9-251) ----
  * Pure host code (no device needed): tokenises `len` bytes of a P3 file with the reference's rules (`#` comments
  * anywhere, Rust's ASCII whitespace set, every number a u16) and returns the raw samples (interleaved R,G,B u16,

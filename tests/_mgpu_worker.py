@@ -38,11 +38,17 @@ def main():
         pf = S.PeerFile(be)                                            # K4 of every rank writes into rank 0's file
         out_peer = S.encode_sharded_peer(be, pf)
         out_peer2 = S.encode_sharded_peer(be, pf)                      # buffers and counters are reusable
+        mb = S.PeerMailbox(be)                                         # the exchanges as the library's own kernels
+        out_mb = S.encode_sharded_peer(be, pf, mailbox=mb)
+        out_mb2 = S.encode_sharded_peer(be, pf, mailbox=mb)            # sequence numbers advance
+        out_nccl_again = S.encode_sharded_peer(be, pf)                 # and the two forms can alternate
+        mb.close()
         pf.close()
         if rank == 0:
             full = synth.make("smooth", 7, h, w, "cpu").numpy()
             whole = ctx.encode(full, 255, opts)
             ok = out == whole and out_dev == whole and out_peer == whole and out_peer2 == whole
+            ok = ok and out_mb == whole and out_mb2 == whole and out_nccl_again == whole
             if use_oracle:
                 from oracle import oracle as O
 
