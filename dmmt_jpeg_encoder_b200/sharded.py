@@ -9,7 +9,9 @@ small exchanges run over torch.distributed (NCCL over NVLink on GPUs, gloo in th
   4. all_gather of the stuffed byte counts                   -> byte offsets; send/recv to rank 0
 
 `ShardBackend` is the seam: `CudaShardBackend` is the product; the CPU tests plug in a simulator so
-the exchange arithmetic is covered without a GPU.
+the exchange arithmetic is covered without a GPU.  On one NVLink node the peer path (`encode_sharded_peer`) needs no
+collective library at all: `PeerFile` lets K4 of every rank store into the destination rank's file, `PeerMailbox` moves
+the exchanged values with the library's own kernels (dmmt_shard_launch_post / dmmt_shard_launch_collect).
 """
 from __future__ import annotations
 
