@@ -163,6 +163,26 @@ __device__ __forceinline__ unsigned long long lookback_resolve_warp(unsigned lon
 }
 
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The kernels of the launch chain are stream-ordered, but each of them may be
+// SCHEDULED while its predecessor still drains: pdl_wait() at its top blocks (in hardware, not by spinning) until the
+// predecessor grid has completed and its writes are visible; pdl_trigger() says "every CTA of this grid that has reached
+// this point no longer minds the next kernel's CTAs becoming resident".  Both are no-ops for a normal launch.
+// Every kernel launched through launch_pdl() calls pdl_wait() in ALL its CTAs before anything else (ordering is then
+// transitive along the chain).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Measured on the B200 (tools/ab_pdl.sh): with the early trigger the waiting CTAs of the next kernel cost more than the
+// overlap wins -- 1024 frames 7.23 -> 7.35 ms, a lone 4K frame 82.5 -> 93.5 us -- so the trigger is compiled out and a
+// dependent kernel is only pre-staged (its launch latency hides behind its predecessor: 82.5 -> 81.3 us, batch unchanged).
+#ifndef DMMT_PDL_TRIGGER
+#define DMMT_PDL_TRIGGER 0
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if DMMT_PDL_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
 // Block-wide exclusive scan of one u32 per thread (blockDim.x == NT, multiple of 32, <= 1024).
 // Returns the exclusive prefix; *total receives the block sum.  `warp_sums` = NT/32 + 1 u32 of smem.
 template <int NT>

@@ -924,6 +924,7 @@ __global__ void __launch_bounds__(P420_THREADS, FUSED ? K1_MINB : 6) k1_transfor
     __shared__ uint32_t s_flut[FUSED && K1_WALK2 ? 128 : 1];   // k1_run_lut_entry: luma | chroma
     __shared__ int s_flag;
     constexpr int BPM = 6, MPT = 16, NUNITS = 96;
+    pdl_trigger();   // (compiled out, see dmmt_common.cuh: K2b's CTAs becoming resident while the last tiles drain did not pay)
     if constexpr (FMT == DMMT_RGB_F32_NORM) {
         if (threadIdx.x == 0) s_flag = 0;
         __syncthreads();

@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_tables(const __grid_constant_
     __shared__ uint32_t s_warp[K2B_THREADS / 32 + 1];
     __shared__ int s_err, s_is_last;
 
+    pdl_wait();
+    pdl_trigger();
     const int t = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
     const int nsym_max = (t & 1) ? 256 : 16;
     unsigned int* lh = a.hist + (size_t)img * 1024;
@@ -469,6 +471,8 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_tables(const __grid_constant_
 // the device): grid (Z, n), each row strides over that image's words.
 __global__ void k_zero_scan(uint32_t* scan, size_t scan_img_stride_words, const ImgMeta* meta,
                             unsigned long long seed_bits, const unsigned long long* seed_src) {
+    pdl_wait();
+    pdl_trigger();
     if (seed_src) seed_bits = *seed_src & 7ull;  // device-resident shard exchange
     const int img = blockIdx.y;
     if (meta[img].error) return;
@@ -848,6 +852,8 @@ __global__ void __launch_bounds__(EB, 4) k3_pack(const K3Args a) {
     __shared__ int s_err_next;
     __shared__ unsigned int s_ovf_tag;  // = 1 + item in which some warp's range did not fit its buffer
 
+    pdl_wait();
+    pdl_trigger();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
         s_next = atomicAdd(a.ticket, 1u);
@@ -1025,6 +1031,8 @@ __global__ void __launch_bounds__(EB, K3_MINB) k3_pack_tiles(const K3Args a) {
     __shared__ int s_err_img;
     __shared__ unsigned int s_left;
 
+    pdl_wait();
+    pdl_trigger();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = (int)(a.n_items / a.n_chunks);  // images of this launch (n_chunks = tiles per image here)
     const uint32_t tiles = a.n_segs;
@@ -1185,6 +1193,7 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINB) k4_stuff(const K4Args a) 
     __shared__ uint32_t s_warp[K4_THREADS / 32 + 1];
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned int s_chunk;
+    pdl_wait();
     const int img = blockIdx.y, tid = threadIdx.x;
     ImgMeta* meta = a.meta + img;
     if (meta->error) {
@@ -1400,6 +1409,7 @@ __global__ void __launch_bounds__(K4_THREADS, K4G_MINB) k4_stuff_gather(const K4
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned int s_chunk;
     const uint32_t* s_bm = reinterpret_cast<const uint32_t*>(s_bm16);
+    pdl_wait();
     const int img = blockIdx.y, tid = threadIdx.x;
     ImgMeta* meta = a.meta + img;
     if (meta->error) {
@@ -1713,6 +1723,28 @@ cudaError_t launch_k2(const Geom& g, const int16_t* coef, size_t coef_img_stride
     return cudaGetLastError();
 }
 
+// Launch with the programmatic-stream-serialisation attribute (see pdl_wait in dmmt_common.cuh); DMMT_PDL=0 in the
+// environment makes these plain launches (A/B, debugging).
+namespace {
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("DMMT_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+}  // namespace
+
 cudaError_t launch_k2b(const Geom& g, const K2bHostArgs& h, int n, cudaStream_t st) {
     K2bArgs a;
     a.hist = h.hist;
@@ -1737,15 +1769,13 @@ cudaError_t launch_k2b(const Geom& g, const K2bHostArgs& h, int n, cudaStream_t 
     a.lcount = h.lcount;
     a.fix_dc = h.fix ? 1 : 0;
     a.fo = h.fix ? *h.fix : TileTok{};
-    k2b_tables<<<dim3(4, n), K2B_THREADS, 0, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(k2b_tables, dim3(4, n), dim3(K2B_THREADS), 0, st, a);
 }
 
 cudaError_t launch_zero_scan(uint32_t* scan, size_t stride_words, const ImgMeta* meta, int n,
                              unsigned long long seed_bits, int blocks_per_image, cudaStream_t st,
                              const unsigned long long* seed_src) {
-    k_zero_scan<<<dim3(blocks_per_image, n), 256, 0, st>>>(scan, stride_words, meta, seed_bits, seed_src);
-    return cudaGetLastError();
+    return launch_pdl(k_zero_scan, dim3(blocks_per_image, n), dim3(256), 0, st, scan, stride_words, meta, seed_bits, seed_src);
 }
 
 uint32_t k4_max_chunks(size_t scan_cap_bytes) {
@@ -1804,12 +1834,10 @@ cudaError_t launch_k3(uint32_t n_chunks, uint32_t n_segs, int n, const TokBuf& t
         }
         const uint32_t want = (a.n_items + EB / 32 - 1) / (EB / 32);
         const uint32_t grid_t = want < (uint32_t)resident_t ? want : (uint32_t)resident_t;
-        k3_pack_tiles<<<grid_t ? grid_t : 1u, EB, K3_LUT_BYTES, st>>>(a);
-        return cudaGetLastError();
+        return launch_pdl(k3_pack_tiles, dim3(grid_t ? grid_t : 1u), dim3(EB), K3_LUT_BYTES, st, a);
     }
     const uint32_t grid = a.n_items < (uint32_t)resident ? a.n_items : (uint32_t)resident;
-    k3_pack<<<grid ? grid : 1u, EB, K3_LUT_BYTES, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(k3_pack, dim3(grid ? grid : 1u), dim3(EB), K3_LUT_BYTES, st, a);
 }
 
 cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStream_t st) {
@@ -1824,11 +1852,10 @@ cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStre
     if (grid_chunks == 0) grid_chunks = 1;
     if (per_image > grid_chunks) per_image = grid_chunks;
 #if K4_GATHER
-    k4_stuff_gather<<<dim3(per_image, n), K4_THREADS, 0, st>>>(a);
+    return launch_pdl(k4_stuff_gather, dim3(per_image, n), dim3(K4_THREADS), 0, st, a);
 #else
-    k4_stuff<<<dim3(per_image, n), K4_THREADS, 0, st>>>(a);
+    return launch_pdl(k4_stuff, dim3(per_image, n), dim3(K4_THREADS), 0, st, a);
 #endif
-    return cudaGetLastError();
 }
 
 // ---- device-resident shard exchange helpers (dmmt_shard.cu) ------------------------------------
