@@ -522,6 +522,9 @@ __device__ __forceinline__ void or_bits(uint32_t* words, unsigned long long pos,
     }
 }
 
+#ifndef K3_LUT_COPIES
+#define K3_LUT_COPIES 1   // copies of the fast path's code LUT in shared memory (2: odd lanes read the second one)
+#endif
 constexpr int K3_RUN = 8;                    // consecutive tokens per lane and step
 constexpr int K3_STEP = 32 * K3_RUN;         // tokens per warp step
 constexpr int K3_HALF_STEP = K3_STEP / 2;    // the fast path's tail step: 4 tokens per lane
@@ -718,13 +721,15 @@ __device__ __forceinline__ uint32_t emit_step_fast(const uint32_t (&t)[K3_RUN], 
     const int lane = threadIdx.x & 31;
     uint32_t val[RUN], ln[RUN];
     uint32_t tor = 0u, flags = 0u;
+    // (K3_LUT_COPIES = 2: odd lanes read a second copy of the LUT, which halves the lanes that can collide on a bank pair)
+    const uint2* lut = s_enc2 + (K3_LUT_COPIES > 1 ? (lane & 1) * 2048 : 0);
     // ONE 64-bit LUT read per token, indexed by table | symbol | "one ZRL in front" (token bit 10): the second half of
     // the LUT holds every AC symbol with its table's ZRL code (categorize.rs:139-142) already in front of it, so a
     // run of 16..31 zeros costs nothing here.  Entries that do not fit 31 bits read as length 64 and fail the pair
     // test below; two or three ZRLs (token bit 11, runs of 32.., rare) take the general path as well.
 #pragma unroll
     for (int i = 0; i < RUN; i++) {
-        const uint2 e = s_enc2[t[i] & 0x7FFu];
+        const uint2 e = lut[t[i] & 0x7FFu];
         val[i] = e.x | (t[i] >> 16);
         ln[i] = e.y;
         tor |= t[i];
@@ -820,13 +825,15 @@ __device__ __forceinline__ unsigned long long emit_range_fast(const uint32_t* __
 __device__ __forceinline__ void k3_install(uint2* s_enc2, uint32_t i, uint32_t e, uint32_t ez) {
     const uint32_t len = e >> 16, code = e & 0xFFFFu, cat = i & 15u, tbl = i >> 8;
     const uint32_t at = (i & 0x300u) | tok_swz(tbl, i & 255u);
-    s_enc2[at] = len ? make_uint2(code << cat, len + cat) : make_uint2(i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
+    const uint2 own = len ? make_uint2(code << cat, len + cat) : make_uint2(i == K3_PAD_TOKEN ? 0u : 0x80000000u, 0u);
     const uint32_t zlen = ez >> 16, tot = len + cat + zlen;
     const bool fast = (tbl == T_YAC || tbl == T_CAC) && len && zlen && tot <= 31u;
-    s_enc2[0x400u | at] = fast ? make_uint2(((ez & 0xFFFFu) << (len + cat)) | (code << cat), tot) : make_uint2(0u, 64u);
+    const uint2 zrl = fast ? make_uint2(((ez & 0xFFFFu) << (len + cat)) | (code << cat), tot) : make_uint2(0u, 64u);
+#pragma unroll
+    for (int c = 0; c < K3_LUT_COPIES; c++) s_enc2[c * 2048 + at] = own, s_enc2[c * 2048 + (0x400u | at)] = zrl;
 }
 
-constexpr size_t K3_LUT_BYTES = 2 * 4 * 256 * sizeof(uint2);  // dynamic shared memory of both K3 kernels
+constexpr size_t K3_LUT_BYTES = K3_LUT_COPIES * 2 * 4 * 256 * sizeof(uint2);  // dynamic shared memory of both K3 kernels
 constexpr int K3_WBUF_WORDS = 576;  // per-warp private bit buffer: 18432 bits; two of them per warp (pipelined chunks)
 
 __device__ __forceinline__ uint32_t k3_load_ntok(const K3Args& a, int img, uint32_t chunk, int wid) {
