@@ -450,3 +450,21 @@ def test_shard_row_partition():
     assert rows[0] == (0, 256) and rows[-1] == (1792, 2048)
     assert all(rows[i][1] == rows[i + 1][0] for i in range(7))
     assert S.pixel_row_range(1080, Options(2), 60, 68) == (960, 1080)
+
+
+def test_mailbox_and_debug_entry_points_validate_their_arguments():
+    """the exchange / test-hook entry points added in round 2 reject bad arguments before touching a device"""
+    import ctypes as C
+
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    L = F.lib()
+    assert L.dmmt_mailbox_bytes(0) == 0 and L.dmmt_mailbox_bytes(65) == 0
+    one, eight = L.dmmt_mailbox_bytes(1), L.dmmt_mailbox_bytes(8)
+    assert one > 0 and eight == 8 * one                      # slots x world rows of payload + flag
+    got = C.c_size_t(0)
+    buf = (C.c_uint8 * 16)()
+    assert L.dmmt_debug_stuff(None, buf, 16, 0, buf, 16, C.byref(got)) == F.E_INVALID
+    boxes = (C.c_void_p * 2)()
+    assert L.dmmt_shard_launch_post(None, boxes, 0, 2, 0, 1, buf, 1) == F.E_INVALID
+    assert L.dmmt_shard_launch_collect(None, buf, 2, 0, 1, 0, 1, buf) == F.E_INVALID
