@@ -34,11 +34,28 @@ struct dmmt_batch {
         int first = 0, m = 0;
     };
     std::vector<Pending> pending;
+    // CUDA graph of one whole dmmt_batch_encode_device call (all sub-batches, all slot streams): captured when a call
+    // repeats the arguments of the previous one, replayed while they stay the same (DMMT_BATCH_GRAPH=0: never)
+    struct {
+        const void* px = nullptr;
+        const void *dense = nullptr, *offs = nullptr, *lens = nullptr;
+        uint64_t cap = 0;
+        int n = 0;
+    } last;                          // arguments of the previous device-resident call
+    cudaGraphExec_t gexec = nullptr; // built for `last`
+    int g_launches = 0;
 };
+
+static void batch_drop_graph(dmmt_batch* b) {
+    if (b->gexec) (void)cudaGraphExecDestroy(b->gexec);
+    b->gexec = nullptr;
+    b->last = {};
+}
 
 extern "C" void dmmt_batch_destroy(dmmt_batch* b) {
     if (!b) return;
     (void)cudaSetDevice(b->ctx->device);
+    batch_drop_graph(b);
     for (dmmt_plan* p : b->slots) dmmt_plan_destroy(p);
     for (auto e : b->ev_k5) (void)cudaEventDestroy(e);
     for (auto e : b->ev_meta) (void)cudaEventDestroy(e);
@@ -96,6 +113,7 @@ extern "C" int dmmt_batch_create(dmmt_ctx* ctx, uint16_t width, uint16_t height,
 
 extern "C" int dmmt_batch_set_scan_capacity(dmmt_batch* b, size_t bytes_per_image) {
     if (!b) return DMMT_E_INVALID;
+    batch_drop_graph(b);  // the scratch buffers the graph points at are replaced
     for (dmmt_plan* p : b->slots) DMMT_TRY(dmmt_plan_set_scan_capacity(p, bytes_per_image));
     return DMMT_OK;
 }
@@ -106,6 +124,7 @@ extern "C" size_t dmmt_batch_worst_case_scan_bytes(const dmmt_batch* b) {
 
 extern "C" int dmmt_batch_set_profiling(dmmt_batch* b, int enabled) {
     if (!b) return DMMT_E_INVALID;
+    batch_drop_graph(b);
     for (dmmt_plan* p : b->slots) DMMT_TRY(dmmt_plan_set_profiling(p, enabled));
     b->profiling = enabled != 0;
     return DMMT_OK;
@@ -135,10 +154,9 @@ static int join_slots(dmmt_batch* b) {
     return DMMT_OK;
 }
 
-extern "C" int dmmt_batch_encode_device(dmmt_batch* b, const void* d_pixels, int n, uint8_t* d_dense,
-                                        uint64_t dense_cap, uint64_t* d_offsets, uint64_t* d_lens) {
-    if (!b || !d_pixels || n <= 0 || !d_dense || !d_offsets || !d_lens) return DMMT_E_INVALID;
-    DMMT_CUDA(cudaSetDevice(b->ctx->device));
+// issues one whole device-resident batch on the context's stream and the slot streams (forked from / joined into it)
+static int batch_issue_device(dmmt_batch* b, const void* d_pixels, int n, uint8_t* d_dense, uint64_t dense_cap,
+                              uint64_t* d_offsets, uint64_t* d_lens) {
     auto* offs = reinterpret_cast<unsigned long long*>(d_offsets);
     auto* lens = reinterpret_cast<unsigned long long*>(d_lens);
     DMMT_CUDA(cudaMemsetAsync(b->d_err, 0, sizeof(int), b->ctx->stream));
@@ -181,6 +199,58 @@ extern "C" int dmmt_batch_encode_device(dmmt_batch* b, const void* d_pixels, int
     }
     DMMT_TRY(join_slots(b));
     b->last_launches = launches;
+    return DMMT_OK;
+}
+
+static bool batch_graphs_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("DMMT_BATCH_GRAPH");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+extern "C" int dmmt_batch_encode_device(dmmt_batch* b, const void* d_pixels, int n, uint8_t* d_dense,
+                                        uint64_t dense_cap, uint64_t* d_offsets, uint64_t* d_lens) {
+    if (!b || !d_pixels || n <= 0 || !d_dense || !d_offsets || !d_lens) return DMMT_E_INVALID;
+    DMMT_CUDA(cudaSetDevice(b->ctx->device));
+    const bool same = b->last.px == d_pixels && b->last.n == n && b->last.dense == d_dense && b->last.cap == dense_cap &&
+                      b->last.offs == d_offsets && b->last.lens == d_lens;
+    if (b->profiling || !batch_graphs_enabled()) return batch_issue_device(b, d_pixels, n, d_dense, dense_cap, d_offsets, d_lens);
+    if (b->gexec && same) {
+        DMMT_CUDA(cudaGraphLaunch(b->gexec, b->ctx->stream));
+        b->last_launches = b->g_launches;
+        return DMMT_OK;
+    }
+    if (b->gexec) batch_drop_graph(b);
+    if (!same) {  // first call with these arguments: plain launches (lazy allocations and one-time set-up happen here)
+        const int rc = batch_issue_device(b, d_pixels, n, d_dense, dense_cap, d_offsets, d_lens);
+        b->last.px = d_pixels, b->last.n = n, b->last.dense = d_dense, b->last.cap = dense_cap;
+        b->last.offs = d_offsets, b->last.lens = d_lens;
+        if (rc != DMMT_OK) b->last = {};
+        return rc;
+    }
+    // second identical call: capture it (the slot streams join the capture through the fork / join events), replay it
+    cudaGraph_t graph = nullptr;
+    DMMT_CUDA(cudaStreamBeginCapture(b->ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = batch_issue_device(b, d_pixels, n, d_dense, dense_cap, d_offsets, d_lens);
+    const cudaError_t ce = cudaStreamEndCapture(b->ctx->stream, &graph);
+    if (rc != DMMT_OK || ce != cudaSuccess || !graph) {
+        if (graph) (void)cudaGraphDestroy(graph);
+        (void)cudaGetLastError();
+        b->last = {};
+        if (rc != DMMT_OK) return rc;
+        return batch_issue_device(b, d_pixels, n, d_dense, dense_cap, d_offsets, d_lens);  // capture refused: plain launches
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&b->gexec, graph, 0);
+    (void)cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+        (void)cudaGetLastError();
+        b->gexec = nullptr, b->last = {};
+        return batch_issue_device(b, d_pixels, n, d_dense, dense_cap, d_offsets, d_lens);
+    }
+    b->g_launches = b->last_launches;
+    DMMT_CUDA(cudaGraphLaunch(b->gexec, b->ctx->stream));
     return DMMT_OK;
 }
 

@@ -661,6 +661,44 @@ def test_graph_replay_follows_the_data(D, ctx, O):
         assert ctx.encode(px, 255) == O.encode(px, 255, O.P420).jpeg
 
 
+def test_batch_graph_replay_follows_the_data(D, ctx, O):
+    """dmmt_batch_encode_device repeated with the same pointers is captured into ONE CUDA graph (all sub-batches, all
+    slot streams) and replayed: the replays must re-read the pixels, an odd last sub-batch must survive, a capacity
+    change drops the graph, and other arguments go back to plain launches."""
+    from dmmt_jpeg_encoder_b200 import _ffi as F
+
+    w, h, n = 200, 136, 7                                     # sub-batches of 3, 3, 1 on two slot streams
+    batch = D.Batch(ctx, w, h, F.FMT_U8, 255, D.Options(F.P420, 8, 0), 3, 2)
+    d_px = torch.empty((n, h, w, 3), dtype=torch.uint8, device="cuda")
+    cap = n * w * h * 2
+    d_dense = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    d_len = torch.zeros(n, dtype=torch.int64, device="cuda")
+
+    def run(count=n, px=d_px):
+        batch.encode_device(px.data_ptr(), count, d_dense.data_ptr(), cap, d_off.data_ptr(), d_len.data_ptr())
+        batch.status()
+        off, ln, dense = d_off.cpu().numpy(), d_len.cpu().numpy(), d_dense.cpu().numpy()
+        return [dense[off[i]: off[i] + ln[i]].tobytes() for i in range(count)]
+
+    for rnd, kind in enumerate(["photo", "grad", "uniform", "photo", "grad"]):   # call 2: capture, 3 onwards: replays
+        imgs = [synth_image(kind, w, h, 10 * rnd + i) for i in range(n)]
+        d_px.copy_(torch.from_numpy(np.stack(imgs)))
+        torch.cuda.synchronize()
+        got = run()
+        for i in range(n):
+            assert got[i] == O.encode(imgs[i], 255, O.P420).jpeg, (rnd, kind, i)
+    want = [O.encode(im, 255, O.P420).jpeg for im in imgs]
+    assert run(5) == want[:5]                                                     # other arguments: plain launches again
+    assert run(5) == want[:5] and run(5) == want[:5]                              # ... captured and replayed in turn
+    batch.set_scan_capacity(batch.worst_case_scan_bytes())                        # buffers move: the graph is dropped
+    for _ in range(3):
+        assert run() == want
+    d_px2 = d_px.clone()
+    assert run(px=d_px2) == want and run() == want                                # alternating buffers never replay a stale graph
+    batch.close()
+
+
 def test_4k_frame_matches_oracle_and_decodes(D, ctx, O):
     """BASELINE config 3 geometry (3840x2160)."""
     from PIL import Image
