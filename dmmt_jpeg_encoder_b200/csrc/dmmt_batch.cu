@@ -232,7 +232,12 @@ extern "C" int dmmt_batch_encode_device(dmmt_batch* b, const void* d_pixels, int
     }
     // second identical call: capture it (the slot streams join the capture through the fork / join events), replay it
     cudaGraph_t graph = nullptr;
-    DMMT_CUDA(cudaStreamBeginCapture(b->ctx->stream, cudaStreamCaptureModeThreadLocal));
+    if (cudaStreamBeginCapture(b->ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        // a stream that cannot be captured (the legacy default stream, or one the caller is capturing already)
+        (void)cudaGetLastError();
+        b->last = {};
+        return batch_issue_device(b, d_pixels, n, d_dense, dense_cap, d_offsets, d_lens);
+    }
     const int rc = batch_issue_device(b, d_pixels, n, d_dense, dense_cap, d_offsets, d_lens);
     const cudaError_t ce = cudaStreamEndCapture(b->ctx->stream, &graph);
     if (rc != DMMT_OK || ce != cudaSuccess || !graph) {
