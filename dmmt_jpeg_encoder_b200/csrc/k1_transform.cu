@@ -1293,10 +1293,14 @@ cudaError_t launch_fmt(const K1Args& a, dim3 grid, bool dbg, bool exact, cudaStr
     if constexpr (HR == 2 && VR == 2) {
         if (!dbg && !exact && !a.force_scalar) {
             // shared memory is what bounds residency, L1 is barely used (streaming loads): take the largest carve-out
-            static const cudaError_t carve[2] = {
-                cudaFuncSetAttribute(k1_transform_p420<FMT, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
-                cudaFuncSetAttribute(k1_transform_p420<FMT, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)};
-            (void)carve;
+            // (function attributes are per device: a process that drives several devices sets them on each)
+            static bool carved[64] = {};
+            int dev = 0;
+            if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !carved[dev]) {
+                (void)cudaFuncSetAttribute(k1_transform_p420<FMT, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+                (void)cudaFuncSetAttribute(k1_transform_p420<FMT, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+                carved[dev] = true;
+            }
             if (a.fo.tok) {
                 if (a.vec_ok) k1_transform_p420<FMT, true, true><<<grid, P420_THREADS, 0, st>>>(a);
                 else k1_transform_p420<FMT, true, false><<<grid, P420_THREADS, 0, st>>>(a);
