@@ -102,6 +102,7 @@ SIGNATURES = {
     "dmmt_plan_last_launch_count": (C.c_int, [_VP]),
     "dmmt_plan_fetch": (C.c_int, [_VP, C.c_int, C.c_int, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dmmt_plan_debug_dct": (C.c_int, [_VP, _VP, C.c_int, C.POINTER(C.c_float), C.c_size_t]),
+    "dmmt_encode_sharded_last_ms": (C.c_double, []),
     "dmmt_mailbox_bytes": (C.c_size_t, [C.c_int]),
     "dmmt_shard_launch_post": (C.c_int, [_VP, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_ulonglong, _VP, C.c_int]),
     "dmmt_shard_launch_collect": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_ulonglong, C.c_int, C.c_int, _VP]),

@@ -9,6 +9,7 @@
 //   3. entropy-coded bits of every shard                -> global bit offsets (binary_stream.rs:38-66)
 //   4. stuffed byte counts                              -> final byte offsets of the shard outputs
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -744,6 +745,9 @@ int sharded_run_host(ShardedJob& J, uint8_t** out, uint64_t* out_len, int* err) 
 }
 }  // namespace
 
+static thread_local double g_sharded_last_ms = -1.0;
+extern "C" double dmmt_encode_sharded_last_ms(void) { return g_sharded_last_ms; }
+
 extern "C" int dmmt_encode_sharded(dmmt_ctx* const* ctxs, int nctx, const dmmt_image* im, const dmmt_options* o,
                                    uint8_t** jpeg, size_t* len) {
     if (!ctxs || nctx <= 0 || !im || !o || !jpeg || !len || !im->pixels || o->subsampling > DMMT_P420)
@@ -783,7 +787,22 @@ extern "C" int dmmt_encode_sharded(dmmt_ctx* const* ctxs, int nctx, const dmmt_i
                 DMMT_CUDA(cudaSetDevice(ctxs[0]->device));
                 DMMT_CUDA(cudaMalloc(&J.d_file, J.file_cap));
             }
+            // measurement hook (DMMT_SHARDED_TIMING=1): wall clock of the phase section alone -- every H2D copy done
+            // before it starts, the one host synchronisation of sharded_run_peer at its end
+            static const bool timing = [] {
+                const char* e = getenv("DMMT_SHARDED_TIMING");
+                return e && e[0] == '1';
+            }();
+            std::chrono::steady_clock::time_point t0;
+            if (timing) {
+                for (int r = 0; r < ns; r++) {
+                    DMMT_CUDA(cudaSetDevice(ctxs[r]->device));
+                    DMMT_CUDA(cudaStreamSynchronize(ctxs[r]->stream));
+                }
+                t0 = std::chrono::steady_clock::now();
+            }
             DMMT_TRY(sharded_run_peer(J, &total, &err));
+            if (timing) g_sharded_last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             if (err == DMMT_OK) {
                 buf = static_cast<uint8_t*>(malloc(total ? total : 1));
                 if (!buf) return DMMT_E_NOMEM;

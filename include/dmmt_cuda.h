@@ -287,6 +287,11 @@ int dmmt_shard_launch_count_bytes(dmmt_shard *, const int32_t *d_all_tail2, cons
 int dmmt_shard_launch_stuff_into(dmmt_shard *, const int64_t *d_all_bit_offsets, int rank, int world, uint8_t *d_file,
                                  size_t file_capacity, const int64_t *d_byte_offset, int64_t *d_result2);
 
+/* measurement hook: with DMMT_SHARDED_TIMING=1 in the environment, the wall-clock milliseconds the phase section of this
+ * thread's last dmmt_encode_sharded took on the peer-memory path (every H2D copy finished before it, its one host
+ * synchronisation at the end; the retry after DMMT_E_OVERFLOW overwrites it); -1 if never measured */
+double dmmt_encode_sharded_last_ms(void);
+
 /* Mailbox exchange: the small values the shards exchange between the phases, moved by the library's own kernels over
  * peer memory instead of a collective library (one process per GPU on one NVLink / NVSwitch node).  Every rank allocates
  * dmmt_mailbox_bytes(world) of ZEROED device memory (dmmt_device_alloc + cudaMemset, once), exports it and maps the
