@@ -133,6 +133,9 @@ __device__ __forceinline__ void lookback_publish_aggregate(unsigned long long* s
                                                            unsigned long long aggregate) {
     st_relaxed_u64(&state[chunk], (chunk == 0 ? LB_INC : LB_AGG) | aggregate);
 }
+#ifndef LB_WARP_SLEEP_NS
+#define LB_WARP_SLEEP_NS 20
+#endif
 __device__ __forceinline__ unsigned long long lookback_resolve_warp(unsigned long long* state, int chunk,
                                                                     unsigned long long aggregate) {
     const int lane = threadIdx.x & 31;
@@ -148,7 +151,7 @@ __device__ __forceinline__ unsigned long long lookback_resolve_warp(unsigned lon
         const int f = inc_mask ? __ffs(inc_mask) - 1 : 32;                // nearest inclusive prefix in this window
         const unsigned int needed = f >= 31 ? 0xffffffffu : ((2u << f) - 1u);  // lanes 0..f (all when there is none)
         if (wait_mask & needed) {
-            __nanosleep(20);
+            __nanosleep(LB_WARP_SLEEP_NS);
             continue;
         }
         unsigned long long v = lane <= f ? (s & LB_VAL) : 0ull;
