@@ -235,7 +235,10 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_tables(const __grid_constant_
 
     pdl_wait();
     pdl_trigger();
-    const int t = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+    // grid (image, slot): the two AC tables of every image are dispatched before any DC table -- the AC tables take the
+    // whole 30 us, the DC tables (<= 12 symbols) a third of it, and with a launch that does not fit one wave the AC CTAs of
+    // the later images must not queue behind DC CTAs of the earlier ones
+    const int t = (blockIdx.y < 2 ? 1 : 0) + 2 * (blockIdx.y & 1), img = blockIdx.x, tid = threadIdx.x;
     const int nsym_max = (t & 1) ? 256 : 16;
     unsigned int* lh = a.hist + (size_t)img * 1024;
     ImgMeta* meta = a.meta + img;
@@ -1796,7 +1799,7 @@ cudaError_t launch_k2b(const Geom& g, const K2bHostArgs& h, int n, cudaStream_t 
     a.lcount = h.lcount;
     a.fix_dc = h.fix ? 1 : 0;
     a.fo = h.fix ? *h.fix : TileTok{};
-    return launch_pdl(k2b_tables, dim3(4, n), dim3(K2B_THREADS), 0, st, a);
+    return launch_pdl(k2b_tables, dim3(n, 4), dim3(K2B_THREADS), 0, st, a);
 }
 
 cudaError_t launch_zero_scan(uint32_t* scan, size_t stride_words, const ImgMeta* meta, int n,
