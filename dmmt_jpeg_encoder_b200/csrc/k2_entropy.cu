@@ -1379,7 +1379,8 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINB) k4_stuff(const K4Args a) 
 //      two aligned 128-bit shared loads + a realignment give the 16 source bytes, the bitmap their 0xFF flags;
 //      a unit without a stuffing zero (93 % of them) is done -- otherwise one byte-insertion per zero (PRMT);
 //      one aligned 128-bit store (byte stores only in the first and last unit of the chunk).
-// No zeroed tile, no atomics, no second pass: 360 instead of 800 instructions per thread and chunk.
+// No zeroed tile, no atomics, no second pass: 5450 instead of 7000 warp-instructions per chunk (ncu), 28 k instead of
+// 4.7 M shared-memory bank conflicts per launch, 0.41 instead of 0.51 ms per 1024 frames.
 #ifndef K4_GATHER
 #define K4_GATHER 1
 #endif
