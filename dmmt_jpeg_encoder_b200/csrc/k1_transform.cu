@@ -584,7 +584,8 @@ __device__ __forceinline__ void fast_arai2(f2 x0, f2 x1, f2 x2, f2 x3, f2 x4, f2
 }
 
 #ifndef K1_I2FP
-#define K1_I2FP 2   // bit ch set: channel ch of u8 input is converted by PRMT + I2FP.F32.U32 (integer pipe) instead of I2F.U8
+#define K1_I2FP 1   // bit ch set: channel ch of u8 input is converted by PRMT + I2FP.F32.U32 (integer pipe) instead of I2F.U8
+                    // (one channel off the conversion pipe pays; which one is a scheduling matter: R 5.26, G 5.28, B 5.36 ms)
 #endif
 // raw sample i (0..47) of a strip row as f32 (before normalisation)
 template <int FMT, int NW>
