@@ -29,7 +29,10 @@ namespace dmmt {
 namespace {
 
 constexpr int EB = 256;           // blocks per CTA chunk in K2/K3 (= threads)
-constexpr int K4_THREADS = 256;
+#ifndef K4_THREADS_N
+#define K4_THREADS_N 256
+#endif
+constexpr int K4_THREADS = K4_THREADS_N;
 constexpr int K4_BYTES_PER_THREAD = 32;
 constexpr int K4_CHUNK = K4_THREADS * K4_BYTES_PER_THREAD;  // 8 KB of unstuffed scan per CTA
 
@@ -1390,7 +1393,7 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINB) k4_stuff(const K4Args a) 
 // input bytes per chunk: 128 short of the 8 KB the CTA stages, so that the output (input + stuffing zeros + misalignment)
 // still fits 512 file units = two full rounds of the 256 threads (8192 bytes of input made round three a 3-unit straggler)
 #ifndef K4G_CHUNK_BYTES
-#define K4G_CHUNK_BYTES 8064
+#define K4G_CHUNK_BYTES (K4_THREADS_N * 32 - K4_THREADS_N / 2)
 #endif
 constexpr int K4G_CHUNK = K4G_CHUNK_BYTES;
 static_assert(K4G_CHUNK % 32 == 0 && K4G_CHUNK <= K4_CHUNK, "whole 32-byte groups, at most one per thread");
@@ -1878,7 +1881,7 @@ cudaError_t launch_k4(const K4HostArgs& h, int n, uint32_t grid_chunks, cudaStre
              h.base_src ? DMMT_E_WRITE : DMMT_E_OVERFLOW};
     // CTAs take chunks by ticket, so the grid only has to keep the device busy: about 8 CTAs per SM
     // over all images, never more than the chunks an image can have
-    uint32_t per_image = (uint32_t)((sm_count() * 8 + n - 1) / n);
+    uint32_t per_image = (uint32_t)((sm_count() * (2048 / K4_THREADS) + n - 1) / n);
     if (per_image < 8) per_image = 8;
     if (grid_chunks == 0) grid_chunks = 1;
     if (per_image > grid_chunks) per_image = grid_chunks;
