@@ -1194,6 +1194,10 @@ struct K4Args {
     int slot_err;
 };
 
+#ifndef K4_GATHER
+#define K4_GATHER 1
+#endif
+#if !K4_GATHER   // round 1's push form, compiled only for A/B (-DK4_GATHER=0)
 constexpr int K4_ROW = K4_BYTES_PER_THREAD + 16;              // padded row: conflict-free 128-bit access
 constexpr int K4_OUT_WORDS = (2 * K4_CHUNK + 16 + 16) / 4;    // worst case: every byte is 0xFF
 
@@ -1371,6 +1375,8 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINB) k4_stuff(const K4Args a) 
     }
 }
 
+#endif  // !K4_GATHER
+
 // K4, output-centric ("gather") form -- the one that is launched.  Same chunking, ticket, look-back and file layout as
 // k4_stuff above; what differs is how a chunk's bytes reach the file.  k4_stuff pushes: every thread ORs its 32 input bytes,
 // spread around their 0xFF bytes, into a zeroed shared tile (8 x 3 shared-memory atomics, 8-way bank conflicts), and the
@@ -1384,9 +1390,6 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINB) k4_stuff(const K4Args a) 
 //      one aligned 128-bit store (byte stores only in the first and last unit of the chunk).
 // No zeroed tile, no atomics, no second pass: 5450 instead of 7000 warp-instructions per chunk (ncu), 28 k instead of
 // 4.7 M shared-memory bank conflicts per launch, 0.41 instead of 0.51 ms per 1024 frames.
-#ifndef K4_GATHER
-#define K4_GATHER 1
-#endif
 #ifndef K4G_MINB
 #define K4G_MINB 8
 #endif
