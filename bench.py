@@ -761,9 +761,16 @@ def main():
         return
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: re-launch under torchrun, one rank per GPU
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
-               "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.abspath(__file__)] + sys.argv[1:]
-        raise SystemExit(subprocess.call(cmd))
+        rc = 1
+        for attempt in range(3):   # the free port can be taken again before torchrun binds it: try another one
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", str(free_port()), os.path.abspath(__file__)] + sys.argv[1:]
+            p = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
+            sys.stderr.write(p.stderr)
+            rc = p.returncode
+            if rc == 0 or "EADDRINUSE" not in p.stderr:
+                break
+        raise SystemExit(rc)
     run_ours(args)
 
 

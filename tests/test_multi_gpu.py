@@ -29,9 +29,12 @@ def _need(n):
 def test_mcu_row_shards_over_nccl(world):
     """BASELINE config 5 at test size: one process per GPU, the four small exchanges over NCCL."""
     _need(world)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-                        "--master-addr", "127.0.0.1", "--master-port", str(_port()),
-                        os.path.join(ROOT, "tests", "_mgpu_worker.py")], capture_output=True, text=True, timeout=600)
+    for attempt in range(3):   # the free port found by _port() can be taken again before torchrun binds it
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                            "--master-addr", "127.0.0.1", "--master-port", str(_port()),
+                            os.path.join(ROOT, "tests", "_mgpu_worker.py")], capture_output=True, text=True, timeout=600)
+        if r.returncode == 0 or "EADDRINUSE" not in r.stderr:
+            break
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(": OK") == 4, r.stdout
 
